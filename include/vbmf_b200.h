@@ -1,0 +1,197 @@
+/* vbmf_b200 -- C ABI of the B200-native VB matrix-factorisation update loop.
+ *
+ * Drop-in boundary for the hot path of vitskvara/VBMatrixFactorization.jl (the `while` loops of vbmf!, vbmf_sparse!,
+ * vbmf_dual! and the update!/lowerBound step functions they call).  A Julia `ccall` shim (julia/VBMatrixFactorizationB200.jl,
+ * INTEGRATION.md) or any other FFI binds exactly these symbols.  Citations are file:line in the reference repository.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices are host memory in Julia layout (column-major, Float64), labels are
+ *     1-based Int64 exactly as Julia passes them; the library copies in and out, device memory is owned by ctx/solver.
+ *   - every function returns 0 on success, <0 on error; vbmf_b200_last_error() gives the message (thread-local).
+ *     There is no CPU fallback: no CUDA device => error.
+ *   - calls on one ctx are synchronous and not re-entrant.
+ *   - sharding: one ctx per GPU/rank owns the columns [col_offset, col_offset + M_local) of Y and the matching rows of
+ *     AHat and per-element vectors; BHat, SigmaB, CB, noise and hyper-prior scalars are replicated.  world == 1 is the
+ *     single-GPU case.  One packed all-reduce (NCCL, double, sum) of [Y*AHat | AHat'AHat | sum Sigma_m | prior sums]
+ *     is issued per iteration.
+ */
+#ifndef VBMF_B200_H
+#define VBMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vbmf_b200_ctx vbmf_b200_ctx;       /* one GPU: stream, communicator, resident shard of Y */
+typedef struct vbmf_b200_solver vbmf_b200_solver; /* device-resident parameter state of one problem */
+
+enum { VBMF_B200_DENSE = 0, VBMF_B200_SPARSE = 1, VBMF_B200_DUAL = 2 };
+enum { VBMF_B200_NORM_SPECTRAL = 0,   /* Julia 0.5 norm(::Matrix) in delta(), src/util.jl:27-29 (default) */
+       VBMF_B200_NORM_FROBENIUS = 1 };
+/* option bits (keyword arguments of vbmf!/vbmf_sparse!/vbmf_dual! and of the step functions) */
+enum {
+    VBMF_B200_DIAG_VAR = 1,    /* diag_var   src/vbmf_sparse.jl:345 */
+    VBMF_B200_FULL_COV = 2,    /* full_cov   src/vbmf_sparse.jl:345 */
+    VBMF_B200_EST_CB = 4,      /* est_cb     src/vbmf_sparse.jl:345 */
+    VBMF_B200_EST_PRIORS = 8,  /* est_priors src/vbmf_dual.jl:456 */
+    VBMF_B200_EST_COVS = 16,   /* est_covs   src/vbmf.jl:175 */
+    VBMF_B200_EST_VAR = 32     /* est_var    src/vbmf.jl:176 */
+};
+/* step functions of the reference, callable one by one (examples/mil_util.jl:183-197 does exactly that) */
+enum {
+    VBMF_B200_STEP_UPDATE_A = 0,       /* updateA!       src/vbmf.jl:95, src/vbmf_sparse.jl:176, src/vbmf_dual.jl:216 */
+    VBMF_B200_STEP_UPDATE_B = 1,       /* updateB!       src/vbmf.jl:109, src/vbmf_sparse.jl:254, src/vbmf_dual.jl:292 */
+    VBMF_B200_STEP_UPDATE_CA = 2,      /* updateCA!      src/vbmf.jl:129, src/vbmf_sparse.jl:284, src/vbmf_dual.jl:322 */
+    VBMF_B200_STEP_UPDATE_CB = 3,      /* updateCB!      src/vbmf.jl:141, src/vbmf_sparse.jl:295, src/vbmf_dual.jl:358 */
+    VBMF_B200_STEP_UPDATE_SIGMA = 4,   /* updateSigma2!  src/vbmf.jl:153 / updateSigma! src/vbmf_sparse.jl:307, src/vbmf_dual.jl:370 */
+    VBMF_B200_STEP_UPDATE_ALPHA00 = 5, /* updateAlpha00! src/vbmf_dual.jl:393 */
+    VBMF_B200_STEP_UPDATE_ALPHA01 = 6, /* updateAlpha01! src/vbmf_dual.jl:417 */
+    VBMF_B200_STEP_UPDATE_BETA00 = 7,  /* updateBeta00!  src/vbmf_dual.jl:408 */
+    VBMF_B200_STEP_UPDATE_BETA01 = 8   /* updateBeta01!  src/vbmf_dual.jl:432 */
+};
+
+/* `vbmf_parameters`, src/vbmf.jl:22-40.  M = number of columns of Y held by this ctx. */
+typedef struct {
+    int64_t L, M, H, H1;
+    int64_t n_labels;
+    const int64_t* labels;   /* 1-based rows of AHat (shard-local) */
+    double* AHat;            /* M x H */
+    double* BHat;            /* L x H */
+    double* SigmaA;          /* H x H */
+    double* SigmaB;          /* H x H */
+    double* CA;              /* H x H */
+    double* CB;              /* H x H */
+    double* invCA;           /* H x H */
+    double* invCB;           /* H x H */
+    double sigma2;
+    double* YHat;            /* L x M or NULL (not produced when NULL; src/vbmf.jl:120) */
+} vbmf_b200_dense_state;
+
+/* `vbmf_sparse_parameters`, src/vbmf_sparse.jl:47-90.  SigmaATVec / invSigmaATVec ((MH)x(MH), :55,:57) are block
+ * diagonal and exposed as M blocks of H x H (block m column-major, blocks consecutive) or NULL. */
+typedef struct {
+    int64_t L, M, H, MH, H1;
+    int64_t n_labels;
+    const int64_t* labels;
+    double* AHat;            /* M x H */
+    double* ATVecHat;        /* MH   (= vec(AHat'), H fastest) */
+    double* SigmaATVec_blocks;     /* M*H*H or NULL */
+    double* diagSigmaATVec;  /* MH */
+    double* SigmaA;          /* H x H */
+    double* BHat;            /* L x H */
+    double* SigmaB;          /* H x H */
+    double* CA;              /* MH */
+    double alpha0, beta0, alpha;
+    double* beta;            /* MH */
+    double* CB;              /* H */
+    double gamma0, delta0, gamma;
+    double* delta;           /* H */
+    double sigmaHat, eta0, zeta0, eta, zeta;
+    double* sigmaVecHat;     /* L */
+    double* etaVec;          /* L */
+    double* zetaVec;         /* L */
+    double* YHat;            /* L x M or NULL */
+    double trYTY;
+} vbmf_b200_sparse_state;
+
+/* `vbmf_dual_parameters`, src/vbmf_dual.jl:59-112 (H1 = H - H0). */
+typedef struct {
+    int64_t L, M, MH, H, H0, H1;
+    double* AHat;            /* M x H */
+    double* ATVecHat;        /* MH */
+    double* SigmaATVec_blocks;     /* M*H*H or NULL */
+    double* diagSigmaATVec;  /* MH */
+    double* SigmaA;          /* H x H */
+    double* A0Hat;           /* M x H0 */
+    double* A1Hat;           /* M x H1 */
+    double* BHat;            /* L x H */
+    double* SigmaB;          /* H x H */
+    double* CA;              /* MH, per-row interleave [CA0 block m ; CA1 block m] */
+    double* alpha;           /* 2 = [alpha0, alpha1] */
+    double* beta;            /* MH, interleaved like CA */
+    double* CA0;             /* M*H0 */
+    double alpha00, beta00, alpha0;
+    double* beta0;           /* M*H0 */
+    double* CA1;             /* M*H1 */
+    double alpha01, beta01, alpha1;
+    double* beta1;           /* M*H1 */
+    double* CB;              /* H */
+    double gamma0, delta0, gamma;
+    double* delta;           /* H */
+    double sigmaHat, eta0, zeta0, eta, zeta;
+    double* sigmaVecHat;     /* L */
+    double* etaVec;          /* L */
+    double* zetaVec;         /* L */
+    double* YHat;            /* L x M or NULL */
+    double trYTY;
+} vbmf_b200_dual_state;
+
+/* ---- library ---- */
+int vbmf_b200_version(void);
+const char* vbmf_b200_last_error(void);
+int vbmf_b200_device_count(void);
+
+/* ---- context ---- */
+/* 128-byte NCCL unique id for a multi-rank job: rank 0 calls this and sends the bytes to the other ranks. */
+int vbmf_b200_nccl_unique_id(void* id128);
+/* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's current stream) or NULL to create one. */
+int vbmf_b200_ctx_create(int device, int rank, int world, const void* nccl_id128, void* cuda_stream, vbmf_b200_ctx** out);
+int vbmf_b200_ctx_destroy(vbmf_b200_ctx* ctx);
+/* Y: L x M_local column-major host matrix with leading dimension ldY (the argument `Y` of every reference function). */
+int vbmf_b200_attach_Y(vbmf_b200_ctx* ctx, const double* Y, int64_t L, int64_t M_local, int64_t ldY, int64_t M_global,
+                       int64_t col_offset);
+/* Low-rank-plus-noise Y generated on the device (Philox4x32-10, keyed by the global column so any sharding agrees). */
+int vbmf_b200_synth_Y(vbmf_b200_ctx* ctx, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset, int rank,
+                      double noise, uint64_t seed);
+int vbmf_b200_download_Y(vbmf_b200_ctx* ctx, double* Y_out, int64_t ldY);
+int vbmf_b200_trYTY(vbmf_b200_ctx* ctx, double* out);          /* traceXTY(Y, Y), src/vbmf_sparse.jl:150 */
+int vbmf_b200_ctx_sync(vbmf_b200_ctx* ctx);
+/* instrumentation for bench.py: kernel launches issued so far; CUDA-event time of the K1/K2 launches when profiling is on */
+int64_t vbmf_b200_launch_count(void);
+int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
+int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
+
+/* ---- K1 / K2 on their own (parity tests of the two contractions) ---- */
+/* P (M_local x H, column-major) = Y' * B ;  B is L x H column-major.  src/vbmf.jl:98 */
+int vbmf_b200_gemm_YtB(vbmf_b200_ctx* ctx, const double* B, int64_t H, double* P);
+/* Q (L x H, column-major) = Y * A over this shard's columns;  A is M_local x H column-major.  src/vbmf.jl:112 */
+int vbmf_b200_gemm_YA(vbmf_b200_ctx* ctx, const double* A, int64_t H, double* Q);
+
+/* ---- device-resident solver ---- */
+/* h_split: H1 (masked trailing columns) for dense/sparse, H0 for dual.  labels: shard-local, 1-based, may be NULL. */
+int vbmf_b200_solver_create(vbmf_b200_ctx* ctx, int kind, int64_t H, int64_t h_split, int64_t n_labels,
+                            const int64_t* labels, int keep_blocks, vbmf_b200_solver** out);
+int vbmf_b200_solver_destroy(vbmf_b200_solver* s);
+int vbmf_b200_dense_upload(vbmf_b200_solver* s, const vbmf_b200_dense_state* st);
+int vbmf_b200_dense_download(vbmf_b200_solver* s, vbmf_b200_dense_state* st);
+int vbmf_b200_sparse_upload(vbmf_b200_solver* s, const vbmf_b200_sparse_state* st);
+int vbmf_b200_sparse_download(vbmf_b200_solver* s, vbmf_b200_sparse_state* st);
+int vbmf_b200_dual_upload(vbmf_b200_solver* s, const vbmf_b200_dual_state* st);
+int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state* st);
+/* one reference step function on the resident state */
+int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags);
+/* the while-loop of vbmf! (src/vbmf.jl:193-214), vbmf_sparse! (src/vbmf_sparse.jl:368-393), vbmf_dual!
+ * (src/vbmf_dual.jl:480-513) with the convergence test on the device.  iters = iterations done, d = last delta. */
+int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode, int64_t* iters, double* d);
+/* lowerBound (trimmed = 0) / lowerBoundTrimmed (trimmed = 1), src/vbmf_sparse.jl:435-489, src/vbmf_dual.jl:556-617 */
+int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, int trimmed, double* out);
+/* updateYHat!: YHat (L x M_local, leading dimension ld) = BHat*AHat', src/vbmf.jl:120 */
+int vbmf_b200_solver_yhat(vbmf_b200_solver* s, double* YHat, int64_t ld);
+
+/* ---- one-call drop-ins: upload + loop + updateYHat! + download ---- */
+/* vbmf!(Y, params, niter; eps, est_covs, est_var)   src/vbmf.jl:175 */
+int vbmf_b200_dense_run(vbmf_b200_ctx* ctx, vbmf_b200_dense_state* st, int64_t niter, double eps, int est_covs, int est_var,
+                        int norm_mode, int64_t* iters, double* d);
+/* vbmf_sparse!(Y, params, niter; eps, diag_var, full_cov, est_cb)   src/vbmf_sparse.jl:344 */
+int vbmf_b200_sparse_run(vbmf_b200_ctx* ctx, vbmf_b200_sparse_state* st, int64_t niter, double eps, int diag_var,
+                         int full_cov, int est_cb, int norm_mode, int64_t* iters, double* d);
+/* vbmf_dual!(Y, params, niter; eps, diag_var, full_cov, est_priors, est_cb)   src/vbmf_dual.jl:455 */
+int vbmf_b200_dual_run(vbmf_b200_ctx* ctx, vbmf_b200_dual_state* st, int64_t niter, double eps, int diag_var, int full_cov,
+                       int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBMF_B200_H */

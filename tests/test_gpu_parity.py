@@ -1,0 +1,275 @@
+"""GPU parity tests proper (run with -m gpu on a B200): every path goes through the C ABI (ctypes -> libvbmf_b200.so).
+
+Tolerance: north_star asks for <= 1e-10 relative error on factors / noise / ELBO per iteration and an identical
+convergence iteration count.  TOL below is that bar; golden-trajectory checks use it against the reference's own logs.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import vbmf_oracle as vo
+from tests.helpers import dense_state_from_golden, jl, load_golden, sparse_state_from_golden, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def G():
+    from tests import gpu_helpers
+    return gpu_helpers
+
+
+@pytest.fixture(scope="module")
+def ctx(G):
+    c = G.vb.Context(device=0)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------ K1 / K2
+@pytest.mark.parametrize("L,M,H", [(10, 20, 2), (257, 1000, 64), (1000, 3001, 32), (130, 517, 128), (64, 300, 5),
+                                   (2048, 4096, 64), (33, 7, 16), (16, 16, 1)])
+def test_contractions(G, ctx, L, M, H):
+    rng = np.random.default_rng(L * 7 + M)
+    Y = np.asfortranarray(rng.standard_normal((L, M)))
+    B = np.asfortranarray(rng.standard_normal((L, H)))
+    A = np.asfortranarray(rng.standard_normal((M, H)))
+    ctx.attach(Y, force=True)
+    assert abs(ctx.trYTY() - float(np.sum(Y * Y))) <= 1e-12 * float(np.sum(Y * Y))
+    P = ctx.gemm_YtB(B)
+    Q = ctx.gemm_YA(A)
+    # FP64 accumulate in a different order than BLAS: |err| <= ~K*eps*|a||b|
+    assert G.rel(P, Y.T @ B) < 1e-13
+    assert G.rel(Q, Y @ A) < 1e-13
+
+
+def test_contraction_linearity_large(G, ctx):
+    """Size-independent property at a shape the oracle would not finish quickly: linearity in the small operand."""
+    L, M, H = 4096, 20000, 64
+    ctx.synth(L, M, rank=8, noise=0.1, seed=7)
+    rng = np.random.default_rng(3)
+    B1, B2 = rng.standard_normal((L, H)), rng.standard_normal((L, H))
+    P1, P2, P12 = ctx.gemm_YtB(B1), ctx.gemm_YtB(B2), ctx.gemm_YtB(B1 + 2.0 * B2)
+    assert G.rel(P12, P1 + 2.0 * P2) < 1e-12
+    A1, A2 = rng.standard_normal((M, H)), rng.standard_normal((M, H))
+    Q1, Q2, Q12 = ctx.gemm_YA(A1), ctx.gemm_YA(A2), ctx.gemm_YA(A1 - 0.5 * A2)
+    assert G.rel(Q12, Q1 - 0.5 * Q2) < 1e-12
+    # checksum of checksums: sum(P .* A) == sum(Q .* B) == tr(A' Y' B)
+    assert abs(np.sum(P1 * A1) - np.sum(Q1 * B1)) <= 1e-11 * abs(np.sum(P1 * A1))
+
+
+# ------------------------------------------------------------------------------------------------ golden trajectories
+@pytest.mark.parametrize("niter", [1, 2, 10, 100])
+def test_dense_golden(G, ctx, niter):
+    g = load_golden("vbmf_test")
+    Y, p = dense_state_from_golden(g)
+    q = G.to_gpu_params(p)
+    G.vb.vbmf_(np.asfortranarray(Y), q, niter, eps=1e-6, est_covs=True, est_var=True, ctx=ctx)
+    assert q.iterations == niter
+    for f in ("AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "invCA", "invCB"):
+        assert G.rel(getattr(q, f), jl(g["log_" + f], niter)) < TOL, f
+    assert abs(q.sigma2 - g["log_sigma2"][niter]) < TOL * g["log_sigma2"][niter]
+    assert G.rel(q.YHat, q.BHat @ q.AHat.T) < 1e-13
+
+
+@pytest.mark.parametrize("niter", [1, 2, 10, 100])
+def test_sparse_golden(G, ctx, niter):
+    g = load_golden("sparse_test")
+    Y, p = sparse_state_from_golden(g)
+    q = G.to_gpu_params(p)
+    d = G.vb.vbmf_sparse_(np.asfortranarray(Y), q, niter, eps=1e-6, full_cov=True, diag_var=False, est_cb=True, ctx=ctx,
+                          keep_blocks=True)
+    assert q.iterations == niter
+    for f in ("AHat", "BHat", "SigmaA", "SigmaB"):
+        assert G.rel(getattr(q, f), jl(g["log_" + f], niter)) < TOL, f
+    for f in ("ATVecHat", "diagSigmaATVec", "CA", "beta", "CB", "delta"):
+        assert G.rel(getattr(q, f), g["log_" + f][niter]) < TOL, f
+    for f in ("sigmaHat", "zeta"):
+        assert abs(getattr(q, f) - g["log_" + f][niter]) < TOL * abs(g["log_" + f][niter]), f
+    assert G.rel(q.SigmaATVec_blocks, g["log_SigmaATVec"][niter]) < TOL
+    assert d > 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ differential vs oracle
+def _dense_case(L, M, H, seed, H1=0, labels=()):
+    Y = synth(L, M, max(1, H // 2), seed)
+    p = vo.vbmf_init(Y, H, ca=1.0, cb=1.0, sigma2=1.0, H1=H1, labels=labels, rng=np.random.default_rng(seed + 1))
+    return Y, p
+
+
+@pytest.mark.parametrize("L,M,H,H1,est", [(40, 150, 4, 0, (True, True)), (64, 500, 8, 2, (True, True)),
+                                          (100, 257, 16, 0, (False, True)), (31, 77, 3, 1, (True, False)),
+                                          (200, 1000, 64, 0, (True, True))])
+def test_dense_vs_oracle(G, ctx, L, M, H, H1, est):
+    labels = list(range(1, M + 1, 3)) if H1 else []
+    Y, p = _dense_case(L, M, H, seed=L + M, H1=H1, labels=labels)
+    Yf = np.asfortranarray(Y)
+    # per-iteration parity (north_star): one GPU iteration from the oracle's state of every iteration
+    po = copy.deepcopy(p)
+    for i in range(12):
+        q = G.to_gpu_params(po)
+        vo.vbmf_run(Y, po, 1, eps=0.0, est_covs=est[0], est_var=est[1])
+        G.vb.vbmf_(Yf, q, 1, eps=0.0, est_covs=est[0], est_var=est[1], ctx=ctx)
+        G.compare(q, po, TOL)
+    # free-running: agreement down to the trajectory's own sensitivity to 1e-14 perturbations
+    for niter in (1, 3, 12):
+        po = copy.deepcopy(p)
+        _, it_o, d_o = vo.vbmf_run(Y, po, niter, eps=1e-9, est_covs=est[0], est_var=est[1])
+        q = G.to_gpu_params(p)
+        G.vb.vbmf_(Yf, q, niter, eps=1e-9, est_covs=est[0], est_var=est[1], ctx=ctx)
+        assert q.iterations == it_o
+        floor = G.sensitivity(lambda s: vo.vbmf_run(Y, s, niter, eps=1e-9, est_covs=est[0], est_var=est[1]), p, ["AHat", "BHat"])
+        G.compare(q, po, max(TOL, 100 * floor))
+        assert abs(q.d - d_o) <= max(1e-8, 1e4 * floor) * abs(d_o)
+
+
+def test_dense_convergence_iteration(G, ctx):
+    """Early exit: the device-side test must stop at the same iteration as the reference loop (spectral norm, Q1)."""
+    Y, p = _dense_case(50, 300, 4, seed=11)
+    for eps, norm in ((1e-3, "spectral"), (1e-4, "spectral"), (1e-3, "frobenius")):
+        po = copy.deepcopy(p)
+        _, it_o, d_o = vo.vbmf_run(Y, po, 500, eps=eps, est_covs=True, est_var=True, norm=norm)
+        q = G.to_gpu_params(p)
+        G.vb.vbmf_(np.asfortranarray(Y), q, 500, eps=eps, est_covs=True, est_var=True, norm=norm, ctx=ctx)
+        assert it_o < 500
+        assert q.iterations == it_o
+        assert abs(q.d - d_o) <= 1e-7 * d_o
+        G.compare(q, po, 1e-9)
+
+
+SPARSE_CASES = [
+    # L, M, H, H1, full_cov, diag_var, est_cb
+    (30, 120, 4, 0, False, False, True),     # diagonal path incl. Q2 repeat(inner)
+    (30, 120, 4, 0, True, False, True),
+    (45, 200, 6, 2, False, False, False),    # labels / H1 mask, CB fixed
+    (45, 200, 6, 2, True, True, True),       # heteroscedastic noise, full covariance
+    (64, 333, 8, 0, False, True, True),      # heteroscedastic, diagonal (Q4)
+    (80, 600, 32, 0, True, False, True),     # warp-per-matrix limit H = 32
+    (40, 90, 40, 0, True, False, True),      # CTA-per-matrix path H > 32
+]
+
+
+@pytest.mark.parametrize("L,M,H,H1,full_cov,diag_var,est_cb", SPARSE_CASES)
+def test_sparse_vs_oracle(G, ctx, L, M, H, H1, full_cov, diag_var, est_cb):
+    Y = synth(L, M, max(1, H // 2), seed=L * M)
+    labels = list(range(2, M + 1, 4)) if H1 else []
+    p = vo.vbmf_sparse_init(Y, H, H1=H1, labels=labels, rng=np.random.default_rng(5))
+    kw = dict(diag_var=diag_var, full_cov=full_cov, est_cb=est_cb)
+    for niter in (1, 2, 8):
+        po = copy.deepcopy(p)
+        d_o, it_o = vo.vbmf_sparse_run(Y, po, niter, eps=1e-12, **kw)
+        q = G.to_gpu_params(p)
+        d = G.vb.vbmf_sparse_(np.asfortranarray(Y), q, niter, eps=1e-12, ctx=ctx, keep_blocks=full_cov, **kw)
+        assert q.iterations == it_o
+        floor = G.sensitivity(lambda s: vo.vbmf_sparse_run(Y, s, niter, eps=1e-12, **kw), p, ["AHat", "BHat"])
+        G.compare(q, po, max(TOL, 100 * floor))
+        assert abs(d - d_o) <= 1e-8 * abs(d_o)
+        if full_cov:
+            assert G.rel(q.SigmaATVec_blocks, po.SigmaATVec_blocks) < TOL
+        assert G.rel(q.YHat, po.BHat @ po.AHat.T) < TOL
+
+
+DUAL_CASES = [(30, 100, 4, 2, False, False, True, True), (30, 100, 4, 1, True, False, True, True),
+              (50, 256, 8, 8, False, False, True, False), (50, 256, 8, 0, False, True, False, True),
+              (36, 140, 6, 3, True, True, True, True)]
+
+
+@pytest.mark.parametrize("L,M,H,H0,full_cov,diag_var,est_priors,est_cb", DUAL_CASES)
+def test_dual_vs_oracle(G, ctx, L, M, H, H0, full_cov, diag_var, est_priors, est_cb):
+    Y = synth(L, M, max(1, H // 2), seed=L + 3 * M)
+    p = vo.vbmf_dual_init(Y, H, H0, rng=np.random.default_rng(9))
+    for niter in (1, 2, 6):
+        po = copy.deepcopy(p)
+        d_o, it_o = vo.vbmf_dual_run(Y, po, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov, est_priors=est_priors, est_cb=est_cb)
+        q = G.to_gpu_params(p)
+        d = G.vb.vbmf_dual_(np.asfortranarray(Y), q, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov,
+                            est_priors=est_priors, est_cb=est_cb, ctx=ctx)
+        assert q.iterations == it_o
+        floor = G.sensitivity(lambda s: vo.vbmf_dual_run(Y, s, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov,
+                                                         est_priors=est_priors, est_cb=est_cb), p, ["AHat", "BHat"])
+        G.compare(q, po, max(TOL, 100 * floor))
+        assert abs(d - d_o) <= 1e-8 * abs(d_o)
+
+
+def test_dual_H_lt_H0_errors(G, ctx):
+    Y = synth(10, 20, 2, 0)
+    with pytest.raises(G.vb.VBMFError, match="H must be at least H0"):
+        G.vb.vbmf_dual_init(Y, 2, 3)
+
+
+# ------------------------------------------------------------------------------------------------ lower bound
+@pytest.mark.parametrize("kind", ["sparse", "dual"])
+@pytest.mark.parametrize("full_cov", [False, True])
+def test_lower_bound(G, ctx, kind, full_cov):
+    L, M, H = 12, 60, 4
+    Y = synth(L, M, 2, seed=21)
+    if kind == "sparse":
+        p = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(2))
+        vo.vbmf_sparse_run(Y, p, 15, eps=0.0, full_cov=full_cov)
+        lb_o, lbt_o = vo.sparse_lowerBound(Y, p), vo.sparse_lowerBoundTrimmed(Y, p, 1e-1)
+    else:
+        p = vo.vbmf_dual_init(Y, H, 2, rng=np.random.default_rng(2))
+        vo.vbmf_dual_run(Y, p, 15, eps=0.0, full_cov=full_cov)
+        lb_o, lbt_o = vo.dual_lowerBound(Y, p), vo.dual_lowerBoundTrimmed(Y, p, 1e-1)
+    q = G.to_gpu_params(p)
+    Yf = np.asfortranarray(Y)
+    lb = G.vb.lowerBound(Yf, q, ctx=ctx)
+    lbt = G.vb.lowerBoundTrimmed(Yf, q, 1e-1, ctx=ctx)
+    assert abs(lb - lb_o) <= TOL * abs(lb_o), (lb, lb_o)
+    assert abs(lbt - lbt_o) <= TOL * abs(lbt_o), (lbt, lbt_o)
+
+
+def test_lower_bound_golden_state(G, ctx):
+    """ELBO of the reference's own logged final state (sparse fixture, iteration 100): oracle vs GPU."""
+    g = load_golden("sparse_test")
+    Y, p = sparse_state_from_golden(g, 100)
+    lb_o = vo.sparse_lowerBound(Y, p)
+    lb = G.vb.lowerBound(np.asfortranarray(Y), G.to_gpu_params(p), ctx=ctx)
+    assert abs(lb - lb_o) <= TOL * abs(lb_o)
+
+
+# ------------------------------------------------------------------------------------------------ step-level API (MIL call pattern)
+@pytest.mark.parametrize("kind", ["dense", "sparse", "dual"])
+def test_vbls_steps(G, ctx, kind):
+    """examples/mil_util.jl:179-203: updateA!, updateCA!, updateSigma*! with BHat fixed, called one by one."""
+    L, M, H = 20, 37, 4
+    Y = synth(L, M, 2, seed=33)
+    rng = np.random.default_rng(4)
+    if kind == "dense":
+        p = vo.vbmf_init(Y, H, rng=rng)
+        kw = {}
+    elif kind == "sparse":
+        p = vo.vbmf_sparse_init(Y, H, rng=rng)
+        kw = {"full_cov": True}
+    else:
+        p = vo.vbmf_dual_init(Y, H, 2, rng=rng)
+        kw = {"full_cov": True}
+    q = G.to_gpu_params(p)
+    vo.vbls(Y, p, 5, **kw)
+    A = G.vb.vbls_(np.asfortranarray(Y), q, 5, ctx=ctx, **kw)
+    assert G.rel(A, p.AHat) < TOL
+    G.compare(q, p, TOL)
+    assert G.rel(q.YHat, p.YHat) < TOL
+
+
+def test_single_steps_sparse(G, ctx):
+    L, M, H = 25, 80, 6
+    Y = synth(L, M, 3, seed=44)
+    Yf = np.asfortranarray(Y)
+    p = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(6))
+    q = G.to_gpu_params(p)
+    vo.sparse_updateA(Y, p); G.vb.updateA_(Yf, q, ctx=ctx); G.compare(q, p, TOL)
+    vo.sparse_updateB(Y, p); G.vb.updateB_(Yf, q, ctx=ctx); G.compare(q, p, TOL)
+    vo.sparse_updateCA(p); G.vb.updateCA_(q, ctx=ctx); G.compare(q, p, TOL)
+    vo.sparse_updateCB(p); G.vb.updateCB_(q, ctx=ctx); G.compare(q, p, TOL)
+    vo.sparse_updateSigma(Y, p); G.vb.updateSigma_(Yf, q, ctx=ctx); G.compare(q, p, TOL)
+
+
+def test_no_y_attached_errors(G):
+    c = G.vb.Context(device=0)
+    p = G.vb.vbmf_init(np.zeros((4, 5)), 2)
+    with pytest.raises(G.vb.VBMFError):
+        G.vb.Solver(c, p)
+    c.close()

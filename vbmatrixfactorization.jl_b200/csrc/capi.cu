@@ -1,0 +1,901 @@
+// C ABI of vbmf_b200 (include/vbmf_b200.h): context, resident solver state, step functions, the device-side loop.
+#include "../../include/vbmf_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace vb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------- NCCL (loaded at run time)
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {getenv("VBMF_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (n == nullptr || *n == 0) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { set_error("NCCL not found (set VBMF_B200_NCCL_LIB): %s", dlerror()); return -1; }
+    g_nccl.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("NCCL library lacks a required symbol");
+        return -1;
+    }
+    g_nccl.handle = h;
+    return 0;
+}
+#define VB_NCCL_OK(call)                                                                        \
+    do {                                                                                        \
+        int r__ = (call);                                                                       \
+        if (r__ != 0) {                                                                         \
+            vb::set_error("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+}  // namespace vb
+
+using namespace vb;
+
+// ------------------------------------------------------------------------------------------- context
+struct vbmf_b200_ctx {
+    int device = 0, rank = 0, world = 1, num_sms = 148;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    void* comm = nullptr;
+    // resident shard of Y (column-major L x Mloc, leading dimension ldY)
+    double* Y = nullptr;
+    int L = 0, Mloc = 0, Mglob = 0, moff = 0, ldY = 0;
+    double* rowY2 = nullptr;
+    double* d_tr = nullptr;
+    double* stats_part = nullptr;
+    double trYTY = 0.0;
+    CUtensorMap tmY1, tmY2;
+    bool have_Y = false;
+    bool simt = false;
+    // profiling of the two contractions
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_k1, ev_k2;
+};
+
+static int ctx_allreduce(vbmf_b200_ctx* c, double* buf, size_t n) {
+    if (c->world <= 1 || n == 0) return 0;
+    VB_NCCL_OK(g_nccl.AllReduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->st));
+    return 0;
+}
+
+extern "C" int vbmf_b200_version(void) { return 100; }
+extern "C" const char* vbmf_b200_last_error(void) { return g_err; }
+extern "C" int64_t vbmf_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int vbmf_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int vbmf_b200_nccl_unique_id(void* id128) {
+    if (load_nccl()) return -1;
+    NcclUniqueId id;
+    VB_NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int vbmf_b200_ctx_create(int device, int rank, int world, const void* nccl_id128, void* cuda_stream,
+                                    vbmf_b200_ctx** out) {
+    if (out == nullptr) { set_error("ctx_create: out is NULL"); return -1; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: vbmf_b200 has no CPU fallback");
+        return -1;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return -1; }
+    VB_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return -1;
+    }
+    vbmf_b200_ctx* c = new vbmf_b200_ctx();
+    c->device = device; c->rank = rank; c->world = world < 1 ? 1 : world;
+    c->num_sms = prop.multiProcessorCount;
+    if (cuda_stream != nullptr) { c->st = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return -1; }
+        c->own_stream = true;
+    }
+    const char* g = getenv("VBMF_B200_GEMM");
+    c->simt = (g != nullptr && strcmp(g, "simt") == 0);
+    if (c->world > 1) {
+        if (nccl_id128 == nullptr) { set_error("world > 1 needs the NCCL unique id of rank 0"); delete c; return -1; }
+        if (load_nccl()) { delete c; return -1; }
+        NcclUniqueId id;
+        memcpy(&id, nccl_id128, 128);
+        int r = g_nccl.CommInitRank(&c->comm, c->world, id, rank);
+        if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); delete c; return -1; }
+    }
+    if (cudaMalloc(&c->d_tr, 64) != cudaSuccess) { set_error("cudaMalloc failed"); delete c; return -1; }
+    *out = c;
+    return 0;
+}
+
+static void ctx_free_Y(vbmf_b200_ctx* c) {
+    if (c->Y) cudaFree(c->Y);
+    if (c->rowY2) cudaFree(c->rowY2);
+    if (c->stats_part) cudaFree(c->stats_part);
+    c->Y = nullptr; c->rowY2 = nullptr; c->stats_part = nullptr; c->have_Y = false;
+}
+
+extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    ctx_free_Y(c);
+    if (c->d_tr) cudaFree(c->d_tr);
+    for (auto e : c->ev_k1) cudaEventDestroy(e);
+    for (auto e : c->ev_k2) cudaEventDestroy(e);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->own_stream) cudaStreamDestroy(c->st);
+    delete c;
+    return 0;
+}
+
+extern "C" int vbmf_b200_ctx_sync(vbmf_b200_ctx* c) {
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+static int ctx_alloc_Y(vbmf_b200_ctx* c, int64_t L, int64_t Mloc, int64_t Mglob, int64_t off) {
+    if (L <= 0 || Mloc < 0 || Mglob < Mloc || off < 0 || off + Mloc > Mglob) { set_error("bad Y geometry L=%lld M_local=%lld M_global=%lld offset=%lld", (long long)L, (long long)Mloc, (long long)Mglob, (long long)off); return -1; }
+    if (L > 0x7fffff00LL || Mglob > 0x7fffff00LL) { set_error("L and M must fit in 31 bits"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    ctx_free_Y(c);
+    c->L = (int)L; c->Mloc = (int)Mloc; c->Mglob = (int)Mglob; c->moff = (int)off;
+    c->ldY = (int)((L + 1) & ~1LL);                       // TMA needs a 16-byte pitch
+    const size_t bytes = std::max<size_t>((size_t)c->ldY * (size_t)std::max<int64_t>(Mloc, 1) * 8, 16);
+    VB_CUDA_OK(cudaMalloc(&c->Y, bytes));
+    VB_CUDA_OK(cudaMalloc(&c->rowY2, (size_t)L * 8));
+    VB_CUDA_OK(cudaMalloc(&c->stats_part, (size_t)(MAX_PARTS / 2) * L * 8));
+    if (c->ldY != L) VB_CUDA_OK(cudaMemsetAsync(c->Y, 0, bytes, c->st));
+    return 0;
+}
+
+static int ctx_finish_Y(vbmf_b200_ctx* c) {
+    // tensor maps of the two contractions (K1 box 16 x 128, K2 box 16 x 16)
+    if (c->Mloc > 0) {
+        if (make_tmap_2d(&c->tmY1, c->Y, (uint64_t)c->L, (uint64_t)c->Mloc, (uint64_t)c->ldY * 8, 16, 128)) return -1;
+        if (make_tmap_2d(&c->tmY2, c->Y, (uint64_t)c->L, (uint64_t)c->Mloc, (uint64_t)c->ldY * 8, 16, 16)) return -1;
+    }
+    // K0: row norms and trYTY
+    Dev d;
+    memset(&d, 0, sizeof(d));
+    d.L = c->L; d.Mloc = c->Mloc; d.Y = c->Y; d.ldY = c->ldY; d.rowY2 = c->rowY2; d.part = c->stats_part;
+    if (k_y_stats(c->st, d, c->d_tr)) return -1;
+    if (c->world > 1) {
+        if (ctx_allreduce(c, c->rowY2, (size_t)c->L)) return -1;
+        if (k_total(c->st, c->rowY2, c->L, c->d_tr)) return -1;
+    }
+    VB_CUDA_OK(cudaMemcpyAsync(&c->trYTY, c->d_tr, 8, cudaMemcpyDeviceToHost, c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->have_Y = true;
+    return 0;
+}
+
+extern "C" int vbmf_b200_attach_Y(vbmf_b200_ctx* c, const double* Y, int64_t L, int64_t M_local, int64_t ldY,
+                                  int64_t M_global, int64_t col_offset) {
+    if (!c || (!Y && M_local > 0)) { set_error("attach_Y: NULL argument"); return -1; }
+    if (ldY < L) { set_error("attach_Y: ldY < L"); return -1; }
+    if (ctx_alloc_Y(c, L, M_local, M_global, col_offset)) return -1;
+    if (M_local > 0)
+        VB_CUDA_OK(cudaMemcpy2DAsync(c->Y, (size_t)c->ldY * 8, Y, (size_t)ldY * 8, (size_t)L * 8, (size_t)M_local,
+                                     cudaMemcpyHostToDevice, c->st));
+    return ctx_finish_Y(c);
+}
+
+extern "C" int vbmf_b200_synth_Y(vbmf_b200_ctx* c, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset,
+                                 int rank, double noise, uint64_t seed) {
+    if (!c) { set_error("synth_Y: NULL ctx"); return -1; }
+    if (ctx_alloc_Y(c, L, M_local, M_global, col_offset)) return -1;
+    if (k_synth(c->st, c->Y, c->ldY, c->L, c->Mloc, c->moff, rank, noise, seed)) return -1;
+    return ctx_finish_Y(c);
+}
+
+extern "C" int vbmf_b200_download_Y(vbmf_b200_ctx* c, double* out, int64_t ldY) {
+    if (!c || !c->have_Y) { set_error("download_Y: no Y attached"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    if (c->Mloc > 0)
+        VB_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ldY * 8, c->Y, (size_t)c->ldY * 8, (size_t)c->L * 8, (size_t)c->Mloc,
+                                     cudaMemcpyDeviceToHost, c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int vbmf_b200_trYTY(vbmf_b200_ctx* c, double* out) {
+    if (!c || !c->have_Y) { set_error("trYTY: no Y attached"); return -1; }
+    *out = c->trYTY;
+    return 0;
+}
+
+extern "C" int vbmf_b200_ctx_profile(vbmf_b200_ctx* c, int enable) {
+    c->profile = enable != 0;
+    for (auto e : c->ev_k1) cudaEventDestroy(e);
+    for (auto e : c->ev_k2) cudaEventDestroy(e);
+    c->ev_k1.clear(); c->ev_k2.clear();
+    return 0;
+}
+extern "C" int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* c, double* k1_ms, int64_t* k1_n, double* k2_ms, int64_t* k2_n) {
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    double t1 = 0, t2 = 0;
+    for (size_t i = 0; i + 1 < c->ev_k1.size(); i += 2) { float ms = 0; VB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev_k1[i], c->ev_k1[i + 1])); t1 += ms; }
+    for (size_t i = 0; i + 1 < c->ev_k2.size(); i += 2) { float ms = 0; VB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev_k2[i], c->ev_k2[i + 1])); t2 += ms; }
+    *k1_ms = t1; *k1_n = (int64_t)(c->ev_k1.size() / 2); *k2_ms = t2; *k2_n = (int64_t)(c->ev_k2.size() / 2);
+    return 0;
+}
+static void prof_mark(vbmf_b200_ctx* c, std::vector<cudaEvent_t>& v) {
+    if (!c->profile) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, c->st); v.push_back(e); }
+}
+
+// ------------------------------------------------------------------------------------------- solver
+struct vbmf_b200_solver {
+    vbmf_b200_ctx* c = nullptr;
+    Dev d;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    double* Qpart = nullptr;
+    int S = 1, kchunk = 16;
+    int* d_labels = nullptr;
+    CUtensorMap tmB, tmBs, tmA;
+    bool k2_simt = false;
+    // host-side validity of derived quantities (every enqueued kernel either runs or is skipped as a whole iteration)
+    bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
+    int* h_flag = nullptr;   // pinned, 2 slots
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    Scalars h_sc;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_split, int64_t n_labels,
+                                       const int64_t* labels, int keep_blocks, vbmf_b200_solver** out) {
+    if (out == nullptr) { set_error("solver_create: out is NULL"); return -1; }
+    *out = nullptr;
+    if (!c || !c->have_Y) { set_error("solver_create: attach Y first"); return -1; }
+    if (kind < 0 || kind > 2) { set_error("solver_create: unknown kind %d", kind); return -1; }
+    if (H < 1 || H > 128) { set_error("H = %lld is outside the supported range 1..128", (long long)H); return -1; }
+    if (kind == VBMF_B200_DUAL && (h_split < 0 || h_split > H)) { set_error("H must be at least H0!"); return -1; }  // src/vbmf_dual.jl:126-128
+    if (kind != VBMF_B200_DUAL && (h_split < 0 || h_split > H)) { set_error("H1 must be in 0..H"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    vbmf_b200_solver* s = new vbmf_b200_solver();
+    s->c = c;
+    Dev& d = s->d;
+    memset(&d, 0, sizeof(d));
+    d.kind = kind;
+    d.L = c->L; d.ldB = (c->L + 1) & ~1;
+    d.Mloc = c->Mloc; d.Mglob = c->Mglob; d.moff = c->moff;
+    d.H = (int)H;
+    if (kind == VBMF_B200_DUAL) { d.H0 = (int)h_split; d.H1 = (int)(H - h_split); }
+    else { d.H0 = (int)H; d.H1 = (int)h_split; }
+    d.nlabels = (kind == VBMF_B200_DUAL) ? 0 : (int)n_labels;
+    d.Y = c->Y; d.ldY = c->ldY; d.rowY2 = c->rowY2;
+
+    plan_splitk(d.L, d.Mloc, d.H, c->num_sms, &s->S, &s->kchunk);
+    s->k2_simt = c->simt || (H % 2 != 0);       // the A tensor map needs a 16-byte row pitch
+
+    const size_t MH = (size_t)std::max(d.Mloc, 1) * H, LH = (size_t)H * d.ldB, HH = (size_t)H * H, Lr = (size_t)d.L;
+    const size_t part_elems = std::max<size_t>({(size_t)MAX_PARTS * HH, (size_t)2400 * std::min<size_t>(H, 32) * std::min<size_t>(H, 32),
+                                                (size_t)300 * Lr, (size_t)16384});
+    struct Item { double** p; size_t n; };
+    std::vector<Item> items = {
+        {&d.A, MH}, {&d.P, MH}, {&d.B, LH}, {&d.Bold, LH}, {&d.D, LH}, {&d.Bs, LH}, {&d.packed, LH + 2 * HH + 8},
+        {&d.SigmaA, HH}, {&d.SigmaB, HH}, {&d.BtB, HH}, {&d.BtBw, HH}, {&d.DtD, HH}, {&d.Gm, HH},
+        {&d.sigmaVec, Lr}, {&d.etaVec, Lr}, {&d.zetaVec, Lr}, {&d.part, part_elems}, {&d.lbacc, 32},
+        {&s->Qpart, (size_t)s->S * LH},
+    };
+    if (kind == VBMF_B200_DENSE) { items.push_back({&d.CA, HH}); items.push_back({&d.CB, HH}); items.push_back({&d.invCA, HH}); items.push_back({&d.invCB, HH}); }
+    else {
+        items.push_back({&d.CAv, MH}); items.push_back({&d.beta, MH}); items.push_back({&d.sdiag, MH});
+        items.push_back({&d.CBv, (size_t)H}); items.push_back({&d.deltav, (size_t)H});
+        if (keep_blocks) items.push_back({&d.blocks, MH * H});
+    }
+    size_t total = 256 + align_up(sizeof(Scalars), 256) + align_up((size_t)std::max(d.nlabels, 1) * 4, 256);
+    for (auto& it : items) total += align_up(it.n * 8, 256);
+    if (cudaMalloc(&s->arena, total) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes of solver state failed", total);
+        delete s;
+        return -1;
+    }
+    s->arena_bytes = total;
+    if (cudaMemsetAsync(s->arena, 0, total, c->st) != cudaSuccess) { set_error("cudaMemset failed"); cudaFree(s->arena); delete s; return -1; }
+    char* p = s->arena;
+    d.sc = (Scalars*)p; p += align_up(sizeof(Scalars), 256);
+    s->d_labels = (int*)p; p += align_up((size_t)std::max(d.nlabels, 1) * 4, 256);
+    for (auto& it : items) { *it.p = (double*)p; p += align_up(it.n * 8, 256); }
+    d.labels = s->d_labels;
+    if (d.nlabels > 0) {
+        std::vector<int> lab(d.nlabels);
+        for (int i = 0; i < d.nlabels; ++i) {
+            const int64_t v = labels[i];
+            if (v < 1 || v > d.Mloc) { set_error("label %lld out of range 1..%d", (long long)v, d.Mloc); cudaFree(s->arena); delete s; return -1; }
+            lab[i] = (int)(v - 1);
+        }
+        if (cudaMemcpyAsync(s->d_labels, lab.data(), (size_t)d.nlabels * 4, cudaMemcpyHostToDevice, c->st) != cudaSuccess ||
+            cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("label upload failed"); cudaFree(s->arena); delete s; return -1; }
+    }
+    const GemmGeometry g = gemm_geometry(d.H);
+    int rc = 0;
+    rc |= make_tmap_2d(&s->tmB, d.B, (uint64_t)d.L, (uint64_t)H, (uint64_t)d.ldB * 8, 16, (uint32_t)g.bn);
+    rc |= make_tmap_2d(&s->tmBs, d.Bs, (uint64_t)d.L, (uint64_t)H, (uint64_t)d.ldB * 8, 16, (uint32_t)g.bn);
+    if (!s->k2_simt && d.Mloc > 0) rc |= make_tmap_2d(&s->tmA, d.A, (uint64_t)H, (uint64_t)d.Mloc, (uint64_t)H * 8, 16, 16);
+    if (rc) { cudaFree(s->arena); delete s; return -1; }
+    if (cudaMallocHost(&s->h_flag, 2 * sizeof(int)) != cudaSuccess || cudaEventCreateWithFlags(&s->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        set_error("pinned flag / event allocation failed"); cudaFree(s->arena); delete s; return -1;
+    }
+    memset(&s->h_sc, 0, sizeof(Scalars));
+    *out = s;
+    return 0;
+}
+
+extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->c->device);
+    cudaStreamSynchronize(s->c->st);
+    if (s->arena) cudaFree(s->arena);
+    if (s->h_flag) cudaFreeHost(s->h_flag);
+    for (int i = 0; i < 2; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    delete s;
+    return 0;
+}
+
+// ---- host <-> device marshalling -------------------------------------------------------------------------------------
+static int up(vbmf_b200_solver* s, double* dst, const double* src, size_t n) {
+    if (n == 0) return 0;
+    if (src == nullptr) { set_error("upload: a required array pointer is NULL"); return -1; }
+    VB_CUDA_OK(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, s->c->st));
+    return 0;
+}
+static int down(vbmf_b200_solver* s, double* dst, const double* src, size_t n) {
+    if (n == 0 || dst == nullptr) return 0;
+    VB_CUDA_OK(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, s->c->st));
+    return 0;
+}
+static int up_B(vbmf_b200_solver* s, const double* BHat) {
+    if (BHat == nullptr) { set_error("upload: BHat is NULL"); return -1; }
+    const Dev& d = s->d;
+    VB_CUDA_OK(cudaMemcpy2DAsync(d.B, (size_t)d.ldB * 8, BHat, (size_t)d.L * 8, (size_t)d.L * 8, (size_t)d.H, cudaMemcpyHostToDevice, s->c->st));
+    return 0;
+}
+static int down_B(vbmf_b200_solver* s, double* BHat) {
+    if (BHat == nullptr) return 0;
+    const Dev& d = s->d;
+    VB_CUDA_OK(cudaMemcpy2DAsync(BHat, (size_t)d.L * 8, d.B, (size_t)d.ldB * 8, (size_t)d.L * 8, (size_t)d.H, cudaMemcpyDeviceToHost, s->c->st));
+    return 0;
+}
+// AHat (M x H column-major, Julia) -> A ([M][H] rows); P is the staging buffer
+static int up_A(vbmf_b200_solver* s, const double* AHat, const double* ATVecHat) {
+    const Dev& d = s->d;
+    const size_t n = (size_t)d.Mloc * d.H;
+    if (ATVecHat != nullptr) return up(s, d.A, ATVecHat, n);
+    if (up(s, d.P, AHat, n)) return -1;
+    return k_transpose(s->c->st, d.P, d.A, d.Mloc, d.H);
+}
+static int down_A(vbmf_b200_solver* s, double* AHat, double* ATVecHat) {
+    const Dev& d = s->d;
+    const size_t n = (size_t)d.Mloc * d.H;
+    if (down(s, ATVecHat, d.A, n)) return -1;
+    if (AHat != nullptr) {
+        if (k_transpose(s->c->st, d.A, d.P, d.H, d.Mloc)) return -1;     // A viewed as column-major H x M
+        if (down(s, AHat, d.P, n)) return -1;
+    }
+    return 0;
+}
+static int push_scalars(vbmf_b200_solver* s) {
+    s->h_sc.active = 0;
+    s->h_sc.chol_fail = 0;
+    VB_CUDA_OK(cudaMemcpyAsync(s->d.sc, &s->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, s->c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(s->c->st));
+    s->btb_valid = s->ata_valid = s->q_valid = s->extras_valid = s->mean_valid = false;
+    return 0;
+}
+static int pull_scalars(vbmf_b200_solver* s) {
+    VB_CUDA_OK(cudaMemcpyAsync(&s->h_sc, s->d.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(s->c->st));
+    return 0;
+}
+static int check_dims(vbmf_b200_solver* s, int kind, int64_t L, int64_t M, int64_t H) {
+    const Dev& d = s->d;
+    if (d.kind != kind) { set_error("state struct kind does not match the solver"); return -1; }
+    if (L != d.L || M != d.Mloc || H != d.H) {
+        set_error("state dims (L=%lld, M=%lld, H=%lld) do not match the solver (L=%d, M=%d, H=%d)", (long long)L, (long long)M, (long long)H, d.L, d.Mloc, d.H);
+        return -1;
+    }
+    return 0;
+}
+static int down_yhat(vbmf_b200_solver* s, double* YHat) {
+    if (YHat == nullptr) return 0;
+    return vbmf_b200_solver_yhat(s, YHat, s->d.L);
+}
+
+extern "C" int vbmf_b200_dense_upload(vbmf_b200_solver* s, const vbmf_b200_dense_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_DENSE, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    const Dev& d = s->d;
+    const size_t HH = (size_t)d.H * d.H;
+    if (up_A(s, st->AHat, nullptr) || up_B(s, st->BHat) || up(s, d.SigmaA, st->SigmaA, HH) || up(s, d.SigmaB, st->SigmaB, HH) ||
+        up(s, d.CA, st->CA, HH) || up(s, d.CB, st->CB, HH) || up(s, d.invCA, st->invCA, HH) || up(s, d.invCB, st->invCB, HH)) return -1;
+    memset(&s->h_sc, 0, sizeof(Scalars));
+    s->h_sc.sigma2 = st->sigma2;
+    s->h_sc.trYTY = s->c->trYTY;       // norm2(Y), src/vbmf.jl:154
+    return push_scalars(s);
+}
+extern "C" int vbmf_b200_dense_download(vbmf_b200_solver* s, vbmf_b200_dense_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_DENSE, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    const Dev& d = s->d;
+    const size_t HH = (size_t)d.H * d.H;
+    if (down_A(s, st->AHat, nullptr) || down_B(s, st->BHat) || down(s, st->SigmaA, d.SigmaA, HH) || down(s, st->SigmaB, d.SigmaB, HH) ||
+        down(s, st->CA, d.CA, HH) || down(s, st->CB, d.CB, HH) || down(s, st->invCA, d.invCA, HH) || down(s, st->invCB, d.invCB, HH)) return -1;
+    if (pull_scalars(s)) return -1;
+    st->sigma2 = s->h_sc.sigma2;
+    return down_yhat(s, st->YHat);
+}
+
+template <class ST>
+static int sparse_like_upload(vbmf_b200_solver* s, const ST* st) {
+    const Dev& d = s->d;
+    const size_t HH = (size_t)d.H * d.H, MH = (size_t)d.Mloc * d.H;
+    if (up_A(s, st->AHat, st->ATVecHat) || up_B(s, st->BHat) || up(s, d.SigmaA, st->SigmaA, HH) || up(s, d.SigmaB, st->SigmaB, HH) ||
+        up(s, d.sdiag, st->diagSigmaATVec, MH) || up(s, d.CAv, st->CA, MH) || up(s, d.beta, st->beta, MH) ||
+        up(s, d.CBv, st->CB, (size_t)d.H) || up(s, d.deltav, st->delta, (size_t)d.H) ||
+        up(s, d.sigmaVec, st->sigmaVecHat, (size_t)d.L) || up(s, d.etaVec, st->etaVec, (size_t)d.L) || up(s, d.zetaVec, st->zetaVec, (size_t)d.L)) return -1;
+    if (d.blocks != nullptr && st->SigmaATVec_blocks != nullptr && up(s, d.blocks, st->SigmaATVec_blocks, MH * d.H)) return -1;
+    Scalars& h = s->h_sc;
+    memset(&h, 0, sizeof(Scalars));
+    h.gamma0 = st->gamma0; h.delta0 = st->delta0; h.gamma = st->gamma;
+    h.sigmaHat = st->sigmaHat; h.eta0 = st->eta0; h.zeta0 = st->zeta0; h.eta = st->eta; h.zeta = st->zeta;
+    h.trYTY = st->trYTY;
+    return 0;
+}
+template <class ST>
+static int sparse_like_download(vbmf_b200_solver* s, ST* st) {
+    const Dev& d = s->d;
+    const size_t HH = (size_t)d.H * d.H, MH = (size_t)d.Mloc * d.H;
+    if (down_A(s, st->AHat, st->ATVecHat) || down_B(s, st->BHat) || down(s, st->SigmaA, d.SigmaA, HH) || down(s, st->SigmaB, d.SigmaB, HH) ||
+        down(s, st->diagSigmaATVec, d.sdiag, MH) || down(s, st->CA, d.CAv, MH) || down(s, st->beta, d.beta, MH) ||
+        down(s, st->CB, d.CBv, (size_t)d.H) || down(s, st->delta, d.deltav, (size_t)d.H) ||
+        down(s, st->sigmaVecHat, d.sigmaVec, (size_t)d.L) || down(s, st->etaVec, d.etaVec, (size_t)d.L) || down(s, st->zetaVec, d.zetaVec, (size_t)d.L)) return -1;
+    if (d.blocks != nullptr && st->SigmaATVec_blocks != nullptr && down(s, st->SigmaATVec_blocks, d.blocks, MH * d.H)) return -1;
+    if (pull_scalars(s)) return -1;
+    const Scalars& h = s->h_sc;
+    st->sigmaHat = h.sigmaHat; st->zeta = h.zeta; st->eta = h.eta;
+    return 0;
+}
+
+extern "C" int vbmf_b200_sparse_upload(vbmf_b200_solver* s, const vbmf_b200_sparse_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_SPARSE, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    if (sparse_like_upload(s, st)) return -1;
+    s->h_sc.alpha0p = st->alpha0; s->h_sc.beta0p = st->beta0; s->h_sc.alpha = st->alpha;
+    return push_scalars(s);
+}
+extern "C" int vbmf_b200_sparse_download(vbmf_b200_solver* s, vbmf_b200_sparse_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_SPARSE, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    if (sparse_like_download(s, st)) return -1;
+    return down_yhat(s, st->YHat);
+}
+extern "C" int vbmf_b200_dual_upload(vbmf_b200_solver* s, const vbmf_b200_dual_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_DUAL, st->L, st->M, st->H)) return -1;
+    if (st->H0 != s->d.H0) { set_error("state H0 does not match the solver"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    if (sparse_like_upload(s, st)) return -1;
+    Scalars& h = s->h_sc;
+    h.alpha00 = st->alpha00; h.beta00 = st->beta00; h.alpha01 = st->alpha01; h.beta01 = st->beta01;
+    h.alpha_g0 = st->alpha0; h.alpha_g1 = st->alpha1;
+    return push_scalars(s);
+}
+extern "C" int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_DUAL, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    // the interleaved vectors land in st->CA / st->beta; split them on the host (src/vbmf_dual.jl:340-350 in reverse)
+    std::vector<double> tmpCA, tmpBeta, tmpA;
+    const Dev& d = s->d;
+    const size_t MH = (size_t)d.Mloc * d.H;
+    vbmf_b200_dual_state w = *st;
+    if (w.CA == nullptr) { tmpCA.resize(MH); w.CA = tmpCA.data(); }
+    if (w.beta == nullptr) { tmpBeta.resize(MH); w.beta = tmpBeta.data(); }
+    if (w.AHat == nullptr && (st->A0Hat || st->A1Hat)) { tmpA.resize(MH); w.AHat = tmpA.data(); }
+    if (sparse_like_download(s, &w)) return -1;
+    st->sigmaHat = w.sigmaHat; st->zeta = w.zeta; st->eta = w.eta;
+    const Scalars& h = s->h_sc;
+    st->alpha00 = h.alpha00; st->beta00 = h.beta00; st->alpha01 = h.alpha01; st->beta01 = h.beta01;
+    st->alpha0 = h.alpha_g0; st->alpha1 = h.alpha_g1;
+    if (st->alpha) { st->alpha[0] = h.alpha_g0; st->alpha[1] = h.alpha_g1; }
+    const size_t M = (size_t)d.Mloc, H = (size_t)d.H, H0 = (size_t)d.H0, H1 = (size_t)d.H1;
+    for (size_t m = 0; m < M; ++m) {
+        for (size_t hh = 0; hh < H; ++hh) {
+            const bool g1 = hh >= H0;
+            const size_t k = g1 ? m * H1 + (hh - H0) : m * H0 + hh;
+            double* ca = g1 ? st->CA1 : st->CA0;
+            double* be = g1 ? st->beta1 : st->beta0;
+            if (ca) ca[k] = w.CA[m * H + hh];
+            if (be) be[k] = w.beta[m * H + hh];
+        }
+    }
+    if (st->A0Hat) memcpy(st->A0Hat, w.AHat, M * H0 * 8);               // AHat[:, 1:H0], src/vbmf_dual.jl:283
+    if (st->A1Hat) memcpy(st->A1Hat, w.AHat + M * H0, M * H1 * 8);      // AHat[:, H0+1:end]
+    return down_yhat(s, st->YHat);
+}
+
+// ---- enqueue helpers ---------------------------------------------------------------------------------------------------
+static int enq_k1(vbmf_b200_solver* s, bool scaledB) {
+    vbmf_b200_ctx* c = s->c;
+    const Dev& d = s->d;
+    prof_mark(c, c->ev_k1);
+    int rc;
+    if (c->simt) rc = launch_gemm_ytb_simt(c->st, d.Y, d.ldY, scaledB ? d.Bs : d.B, d.ldB, d.P, d.Mloc, d.L, d.H, d.H, d.sc);
+    else rc = launch_gemm_ytb(c->st, &c->tmY1, scaledB ? &s->tmBs : &s->tmB, d.P, d.Mloc, d.L, d.H, d.H, d.sc, c->num_sms);
+    prof_mark(c, c->ev_k1);
+    return rc;
+}
+static int enq_k2(vbmf_b200_solver* s) {
+    vbmf_b200_ctx* c = s->c;
+    const Dev& d = s->d;
+    prof_mark(c, c->ev_k2);
+    int rc;
+    if (s->k2_simt) rc = launch_gemm_ya_simt(c->st, d.Y, d.ldY, d.A, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc);
+    else rc = launch_gemm_ya(c->st, &c->tmY2, &s->tmA, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc, c->num_sms);
+    prof_mark(c, c->ev_k2);
+    if (rc) return rc;
+    return k_reduce_q(c->st, d, s->Qpart, s->S);
+}
+// Grams of the current BHat that the A update / CB / sigma need
+static int enq_gram_B(vbmf_b200_solver* s, int flags) {
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (k_gram(st, d, d.B, false, d.L, nullptr, d.BtB)) return -1;
+    if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) {
+        if (!s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
+        if (flags & F_FULL_COV) { if (k_gram(st, d, d.B, false, d.L, d.sigmaVec, d.BtBw)) return -1; }   // B'diag(sv)B, src/vbmf_sparse.jl:182
+        else { if (k_gram_w2(st, d, d.B, d.L, d.sigmaVec, d.BtBw)) return -1; }                            // norm2(B[:,h].*sv), :211 (Q4)
+        if (k_scale_B(st, d)) return -1;
+    }
+    s->btb_valid = true;
+    return 0;
+}
+static int copy_sa(vbmf_b200_solver* s) {   // step-level: SigmaA <- all-reduced sum of blocks right away
+    const Dev& d = s->d;
+    if (ctx_allreduce(s->c, d.packed + packed_sa(d), (size_t)d.H * d.H)) return -1;
+    VB_CUDA_OK(cudaMemcpyAsync(d.SigmaA, d.packed + packed_sa(d), (size_t)d.H * d.H * 8, cudaMemcpyDeviceToDevice, s->c->st));
+    return 0;
+}
+static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (!s->btb_valid && enq_gram_B(s, flags)) return -1;
+    if (d.kind == KIND_DENSE) {
+        if (k_dense_sigmaA(st, d) || enq_k1(s, false) || k_dense_A_epilogue(st, d) || k_mask(st, d)) return -1;
+    } else {
+        const bool dv = (flags & F_DIAG_VAR) != 0;
+        if (enq_k1(s, dv)) return -1;
+        if (flags & F_FULL_COV) { if (k_sparse_A_full(st, d, flags)) return -1; }
+        else { if (k_sparse_A_diag(st, d, flags)) return -1; }
+        if (k_mask(st, d)) return -1;
+        if (!fused && copy_sa(s)) return -1;
+    }
+    s->ata_valid = false; s->q_valid = false;
+    return 0;
+}
+static int enq_gram_A(vbmf_b200_solver* s) {
+    const Dev& d = s->d;
+    return k_gram(s->c->st, d, d.A, true, d.Mloc, nullptr, d.packed + packed_ata(d));
+}
+// Q = Y*AHat and AHat'AHat, all-reduced across shards.  fused: the payload also carries SigmaA blocks and dual sums.
+static int enq_q_ata(vbmf_b200_solver* s, bool fused) {
+    const Dev& d = s->d;
+    if (enq_gram_A(s) || enq_k2(s)) return -1;
+    const size_t n = fused ? packed_len(d) : packed_sa(d);
+    if (ctx_allreduce(s->c, d.packed, n)) return -1;
+    s->ata_valid = true; s->q_valid = true;
+    if (fused) s->extras_valid = true;
+    return 0;
+}
+static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (!fused && d.kind != KIND_DENSE) {
+        // step-level: packed.SA must hold the (global) SigmaA the state carries
+        VB_CUDA_OK(cudaMemcpyAsync(d.packed + packed_sa(d), d.SigmaA, (size_t)d.H * d.H * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR) && !s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
+    if (enq_q_ata(s, fused)) return -1;
+    if (k_sigmaB(st, d, flags) || k_B_epilogue(st, d, flags)) return -1;
+    s->btb_valid = false;
+    return 0;
+}
+static int enq_updateCA(vbmf_b200_solver* s, int flags, bool fused) {
+    const Dev& d = s->d;
+    if (d.kind == KIND_DENSE) {
+        if (!s->ata_valid) { if (enq_gram_A(s) || ctx_allreduce(s->c, d.packed + packed_ata(d), (size_t)d.H * d.H)) return -1; s->ata_valid = true; }
+        return k_dense_cov_only(s->c->st, d, 0);
+    }
+    if (k_update_CA(s->c->st, d)) return -1;
+    if (d.kind == KIND_DUAL && !fused) { if (ctx_allreduce(s->c, d.packed + packed_ex(d), 8)) return -1; s->extras_valid = true; }
+    return 0;
+}
+
+extern "C" int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags) {
+    if (!s) { set_error("NULL solver"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (k_set_control(st, d, 1, 0.0, 0, 1)) return -1;
+    int rc = 0;
+    switch (step) {
+        case VBMF_B200_STEP_UPDATE_A: rc = enq_updateA(s, flags, false); break;
+        case VBMF_B200_STEP_UPDATE_B: rc = enq_updateB(s, flags, false); break;
+        case VBMF_B200_STEP_UPDATE_CA: rc = enq_updateCA(s, flags, false); break;
+        case VBMF_B200_STEP_UPDATE_CB:
+            if (!s->btb_valid) rc = enq_gram_B(s, flags);
+            if (!rc) rc = (d.kind == KIND_DENSE) ? k_dense_cov_only(st, d, 1) : k_updateCB_only(st, d);
+            break;
+        case VBMF_B200_STEP_UPDATE_SIGMA:
+            if (!s->btb_valid) rc = enq_gram_B(s, flags);
+            if (!rc && !s->q_valid) rc = enq_q_ata(s, false);
+            if (!rc) rc = k_trbq(st, d);
+            if (!rc) {
+                if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) { rc = k_sigma_rows(st, d); s->mean_valid = true; s->btb_valid = false; }
+                else rc = k_sigma_only(st, d, flags);
+            }
+            break;
+        case VBMF_B200_STEP_UPDATE_ALPHA00: case VBMF_B200_STEP_UPDATE_ALPHA01:
+        case VBMF_B200_STEP_UPDATE_BETA00: case VBMF_B200_STEP_UPDATE_BETA01:
+            if (d.kind != KIND_DUAL) { set_error("hyper-prior steps exist for vbmf_dual only"); return -1; }
+            if (!s->extras_valid) { set_error("call updateCA! before the hyper-prior updates (they need sum(CA_g), sum(log(beta_g)))"); return -1; }
+            rc = k_prior_only(st, d, step - VBMF_B200_STEP_UPDATE_ALPHA00);
+            break;
+        default: set_error("unknown step %d", step); return -1;
+    }
+    if (rc) return -1;
+    VB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int enq_iteration(vbmf_b200_solver* s, int flags) {
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (enq_updateA(s, flags, true)) return -1;                       // updateA!
+    if (d.kind != KIND_DENSE && enq_updateCA(s, flags, true)) return -1;   // updateCA! (local; hoisted before the all-reduce)
+    if (enq_updateB(s, flags, true)) return -1;                       // updateB!
+    if (k_gram(st, d, d.B, false, d.L, nullptr, d.BtB) || k_gram(st, d, d.D, false, d.L, nullptr, d.DtD)) return -1;
+    if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) {
+        if (k_sigma_rows(st, d)) return -1;                           // updateSigma! (per-row)
+        if (flags & F_FULL_COV) { if (k_gram(st, d, d.B, false, d.L, d.sigmaVec, d.BtBw)) return -1; }
+        else { if (k_gram_w2(st, d, d.B, d.L, d.sigmaVec, d.BtBw)) return -1; }
+        if (k_scale_B(st, d)) return -1;
+    }
+    s->btb_valid = true;
+    return k_post(st, d, flags, true);                                // updateCA!/CB! (dense), updateCB!, updateSigma*!, priors, delta
+}
+
+extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode,
+                                    int64_t* iters, double* dout) {
+    if (!s) { set_error("NULL solver"); return -1; }
+    if (niter > 0x7fffffff) niter = 0x7fffffff;
+    if (niter < 0) niter = 0;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    const Dev& d = s->d;
+    cudaStream_t st = s->c->st;
+    if (d.kind == KIND_DENSE) flags &= (F_EST_COVS | F_EST_VAR);
+    if (k_set_control(st, d, (int)niter, eps, norm_mode, 0)) return -1;
+    s->btb_valid = false;
+    if (enq_gram_B(s, flags) || k_norms_init(st, d)) return -1;      // old = BHat, src/vbmf.jl:188
+    const int CHUNK = 4;
+    int64_t enq = 0;
+    int slot = 0;
+    bool pending = false;
+    while (enq < niter) {
+        const int64_t c = std::min<int64_t>(CHUNK, niter - enq);
+        for (int64_t i = 0; i < c; ++i) if (enq_iteration(s, flags)) return -1;
+        enq += c;
+        VB_CUDA_OK(cudaMemcpyAsync(&s->h_flag[slot], &d.sc->active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CUDA_OK(cudaEventRecord(s->ev[slot], st));
+        if (pending) {
+            VB_CUDA_OK(cudaEventSynchronize(s->ev[slot ^ 1]));
+            if (s->h_flag[slot ^ 1] == 0) break;
+        }
+        pending = true;
+        slot ^= 1;
+    }
+    if (pull_scalars(s)) return -1;
+    if (iters) *iters = s->h_sc.iter;
+    if (dout) *dout = s->h_sc.d;
+    if (s->h_sc.chol_fail) { set_error("a posterior precision matrix was not positive definite (NaN written, loop ended)"); return -2; }
+    return 0;
+}
+
+extern "C" int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, int trimmed, double* out) {
+    if (!s || !out) { set_error("NULL argument"); return -1; }
+    const Dev& d = s->d;
+    if (d.kind == KIND_DENSE) { set_error("the dense solver has no lowerBound (the reference defines none)"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    cudaStream_t st = s->c->st;
+    if (k_set_control(st, d, 1, 0.0, 0, 1)) return -1;
+    if (enq_gram_B(s, 0)) return -1;
+    if (!s->q_valid && enq_q_ata(s, false)) return -1;
+    if (k_trbq(st, d)) return -1;
+    if (k_lower_bound(st, d, trim, trimmed, 0)) return -1;
+    if (ctx_allreduce(s->c, d.lbacc, 9)) return -1;
+    if (k_lower_bound(st, d, trim, trimmed, 1)) return -1;
+    if (pull_scalars(s)) return -1;
+    *out = s->h_sc.lb;
+    return 0;
+}
+
+extern "C" int vbmf_b200_solver_yhat(vbmf_b200_solver* s, double* YHat, int64_t ld) {
+    if (!s || !YHat) { set_error("NULL argument"); return -1; }
+    const Dev& d = s->d;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    if (d.Mloc == 0) return 0;
+    double* tmp = nullptr;
+    const size_t bytes = (size_t)d.L * d.Mloc * 8;
+    if (cudaMalloc(&tmp, bytes) != cudaSuccess) { cudaGetLastError(); set_error("YHat needs %zu bytes of device memory", bytes); return -1; }
+    int rc = k_yhat(s->c->st, d, tmp, d.L);
+    if (!rc && cudaMemcpy2DAsync(YHat, (size_t)ld * 8, tmp, (size_t)d.L * 8, (size_t)d.L * 8, (size_t)d.Mloc, cudaMemcpyDeviceToHost, s->c->st) != cudaSuccess) { set_error("YHat download failed"); rc = -1; }
+    cudaStreamSynchronize(s->c->st);
+    cudaFree(tmp);
+    return rc;
+}
+
+// ---- K1 / K2 on their own ------------------------------------------------------------------------------------------------
+extern "C" int vbmf_b200_gemm_YtB(vbmf_b200_ctx* c, const double* B, int64_t H, double* P) {
+    if (!c || !c->have_Y || !B || !P) { set_error("gemm_YtB: bad argument"); return -1; }
+    if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    const int ldB = (c->L + 1) & ~1;
+    const size_t MH = (size_t)std::max(c->Mloc, 1) * H;
+    double *dB = nullptr, *dP = nullptr, *dT = nullptr;
+    VB_CUDA_OK(cudaMalloc(&dB, (size_t)H * ldB * 8));
+    VB_CUDA_OK(cudaMalloc(&dP, MH * 8));
+    VB_CUDA_OK(cudaMalloc(&dT, MH * 8));
+    VB_CUDA_OK(cudaMemsetAsync(dB, 0, (size_t)H * ldB * 8, c->st));
+    VB_CUDA_OK(cudaMemcpy2DAsync(dB, (size_t)ldB * 8, B, (size_t)c->L * 8, (size_t)c->L * 8, (size_t)H, cudaMemcpyHostToDevice, c->st));
+    int rc = 0;
+    if (c->simt) rc = launch_gemm_ytb_simt(c->st, c->Y, c->ldY, dB, ldB, dP, c->Mloc, c->L, (int)H, (int)H, nullptr);
+    else {
+        CUtensorMap tmB;
+        rc = make_tmap_2d(&tmB, dB, (uint64_t)c->L, (uint64_t)H, (uint64_t)ldB * 8, 16, (uint32_t)gemm_geometry((int)H).bn);
+        if (!rc) rc = launch_gemm_ytb(c->st, &c->tmY1, &tmB, dP, c->Mloc, c->L, (int)H, (int)H, nullptr, c->num_sms);
+    }
+    if (!rc) rc = k_transpose(c->st, dP, dT, (int)H, c->Mloc);
+    if (!rc && c->Mloc > 0 && cudaMemcpyAsync(P, dT, (size_t)c->Mloc * H * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) { set_error("copy failed"); rc = -1; }
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    if (e != cudaSuccess) { set_error("gemm_YtB: %s", cudaGetErrorString(e)); rc = -1; }
+    cudaFree(dB); cudaFree(dP); cudaFree(dT);
+    return rc;
+}
+
+extern "C" int vbmf_b200_gemm_YA(vbmf_b200_ctx* c, const double* A, int64_t H, double* Q) {
+    if (!c || !c->have_Y || !A || !Q) { set_error("gemm_YA: bad argument"); return -1; }
+    if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    const int ldQ = (c->L + 1) & ~1;
+    const size_t MH = (size_t)std::max(c->Mloc, 1) * H;
+    int S = 1, kchunk = 16;
+    plan_splitk(c->L, c->Mloc, (int)H, c->num_sms, &S, &kchunk);
+    double *dA = nullptr, *dT = nullptr, *dQp = nullptr, *dQ = nullptr;
+    VB_CUDA_OK(cudaMalloc(&dA, MH * 8));
+    VB_CUDA_OK(cudaMalloc(&dT, MH * 8));
+    VB_CUDA_OK(cudaMalloc(&dQp, (size_t)S * H * ldQ * 8));
+    VB_CUDA_OK(cudaMalloc(&dQ, (size_t)H * ldQ * 8));
+    VB_CUDA_OK(cudaMemsetAsync(dQp, 0, (size_t)S * H * ldQ * 8, c->st));
+    if (c->Mloc > 0) VB_CUDA_OK(cudaMemcpyAsync(dT, A, (size_t)c->Mloc * H * 8, cudaMemcpyHostToDevice, c->st));
+    int rc = k_transpose(c->st, dT, dA, c->Mloc, (int)H);
+    const bool simt = c->simt || (H % 2 != 0);
+    if (!rc) {
+        if (simt) rc = launch_gemm_ya_simt(c->st, c->Y, c->ldY, dA, dQp, c->L, c->Mloc, (int)H, ldQ, kchunk, S, nullptr);
+        else {
+            CUtensorMap tmA;
+            if (c->Mloc > 0) rc = make_tmap_2d(&tmA, dA, (uint64_t)H, (uint64_t)c->Mloc, (uint64_t)H * 8, 16, 16);
+            if (!rc) rc = launch_gemm_ya(c->st, &c->tmY2, &tmA, dQp, c->L, c->Mloc, (int)H, ldQ, kchunk, S, nullptr, c->num_sms);
+        }
+    }
+    if (!rc) {
+        Dev d; memset(&d, 0, sizeof(d));
+        d.H = (int)H; d.ldB = ldQ; d.L = c->L; d.packed = dQ;
+        Scalars* none = nullptr; d.sc = none;
+        // fixed-order slab reduction (same kernel as the solver path, unpredicated)
+        rc = k_reduce_q(c->st, d, dQp, S);
+    }
+    if (!rc && cudaMemcpy2DAsync(Q, (size_t)c->L * 8, dQ, (size_t)ldQ * 8, (size_t)c->L * 8, (size_t)H, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) { set_error("copy failed"); rc = -1; }
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    if (e != cudaSuccess) { set_error("gemm_YA: %s", cudaGetErrorString(e)); rc = -1; }
+    cudaFree(dA); cudaFree(dT); cudaFree(dQp); cudaFree(dQ);
+    return rc;
+}
+
+// ---- one-call drop-ins ---------------------------------------------------------------------------------------------------
+extern "C" int vbmf_b200_dense_run(vbmf_b200_ctx* c, vbmf_b200_dense_state* st, int64_t niter, double eps, int est_covs,
+                                   int est_var, int norm_mode, int64_t* iters, double* d) {
+    if (!c || !st) { set_error("NULL argument"); return -1; }
+    vbmf_b200_solver* s = nullptr;
+    if (vbmf_b200_solver_create(c, VBMF_B200_DENSE, st->H, st->H1, st->n_labels, st->labels, 0, &s)) return -1;
+    int rc = vbmf_b200_dense_upload(s, st);
+    if (!rc) rc = vbmf_b200_solver_run(s, niter, eps, (est_covs ? F_EST_COVS : 0) | (est_var ? F_EST_VAR : 0), norm_mode, iters, d);
+    if (rc == 0 || rc == -2) { int r2 = vbmf_b200_dense_download(s, st); if (r2) rc = r2; }
+    vbmf_b200_solver_destroy(s);
+    return rc;
+}
+extern "C" int vbmf_b200_sparse_run(vbmf_b200_ctx* c, vbmf_b200_sparse_state* st, int64_t niter, double eps, int diag_var,
+                                    int full_cov, int est_cb, int norm_mode, int64_t* iters, double* d) {
+    if (!c || !st) { set_error("NULL argument"); return -1; }
+    vbmf_b200_solver* s = nullptr;
+    if (vbmf_b200_solver_create(c, VBMF_B200_SPARSE, st->H, st->H1, st->n_labels, st->labels, st->SigmaATVec_blocks != nullptr, &s)) return -1;
+    int rc = vbmf_b200_sparse_upload(s, st);
+    const int flags = (diag_var ? F_DIAG_VAR : 0) | (full_cov ? F_FULL_COV : 0) | (est_cb ? F_EST_CB : 0);
+    if (!rc) rc = vbmf_b200_solver_run(s, niter, eps, flags, norm_mode, iters, d);
+    if (rc == 0 || rc == -2) { int r2 = vbmf_b200_sparse_download(s, st); if (r2) rc = r2; }
+    vbmf_b200_solver_destroy(s);
+    return rc;
+}
+extern "C" int vbmf_b200_dual_run(vbmf_b200_ctx* c, vbmf_b200_dual_state* st, int64_t niter, double eps, int diag_var,
+                                  int full_cov, int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d) {
+    if (!c || !st) { set_error("NULL argument"); return -1; }
+    if (st->H < st->H0) { set_error("H must be at least H0!"); return -1; }
+    vbmf_b200_solver* s = nullptr;
+    if (vbmf_b200_solver_create(c, VBMF_B200_DUAL, st->H, st->H0, 0, nullptr, st->SigmaATVec_blocks != nullptr, &s)) return -1;
+    int rc = vbmf_b200_dual_upload(s, st);
+    const int flags = (diag_var ? F_DIAG_VAR : 0) | (full_cov ? F_FULL_COV : 0) | (est_cb ? F_EST_CB : 0) | (est_priors ? F_EST_PRIORS : 0);
+    if (!rc) rc = vbmf_b200_solver_run(s, niter, eps, flags, norm_mode, iters, d);
+    if (rc == 0 || rc == -2) { int r2 = vbmf_b200_dual_download(s, st); if (r2) rc = r2; }
+    vbmf_b200_solver_destroy(s);
+    return rc;
+}

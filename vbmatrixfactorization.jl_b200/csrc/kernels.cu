@@ -1,0 +1,1135 @@
+// Fused small kernels of the VB update loop: everything that is not one of the two contractions over Y.
+// Every kernel is predicated on the device-side loop flag (Scalars::active) so iterations can be enqueued ahead of
+// the device-side convergence test; every reduction uses a fixed order (per-CTA partials + ordered final sum).
+// Reference formulas are cited per kernel (paths relative to /root/reference).
+#include "kernels.cuh"
+#include "linalg.cuh"
+#include <algorithm>
+
+namespace vb {
+
+#define ACTIVE_OR_RETURN(d) if (!(d).sc->active) return
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------- generic helpers
+__global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, size_t stride, size_t n,
+                                    double* __restrict__ out, const Scalars* sc) {
+    if (sc != nullptr && !sc->active) return;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + e];
+        out[e] = s;
+    }
+}
+static int sum_partials(cudaStream_t st, const double* part, int nparts, size_t stride, size_t n, double* out,
+                        const Scalars* sc) {
+    if (n == 0) return 0;
+    int grid = std::max(1, std::min(cdiv((long)n, 256), 1184));
+    sum_partials_kernel<<<grid, 256, 0, st>>>(part, nparts, stride, n, out, sc);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void set_control_kernel(Scalars* sc, int niter, double eps, int norm_mode, int force_active) {
+    sc->niter = niter;
+    sc->eps = eps;
+    sc->norm_mode = norm_mode;
+    sc->iter = 0;
+    sc->d = eps + 1.0;                                  // src/vbmf.jl:189  d = eps + 1.0
+    sc->active = force_active ? 1 : ((1 <= niter) && (sc->d > eps)) ? 1 : 0;   // while (i <= niter) && (d > eps)
+}
+int k_set_control(cudaStream_t st, const Dev& d, int niter, double eps, int norm_mode, int force_active) {
+    set_control_kernel<<<1, 1, 0, st>>>(d.sc, niter, eps, norm_mode, force_active);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// col-major (rows x cols, ld = rows) -> row-major [rows][cols]
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int cols) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + threadIdx.x, c = c0 + i;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)c * rows + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)r * cols + c] = tile[threadIdx.x][i];
+    }
+}
+int k_transpose(cudaStream_t st, const double* src, double* dst, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(cdiv(rows, 32), cdiv(cols, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K0: Y statistics
+// trYTY = sum(Y.^2) (src/vbmf_sparse.jl:150; dense recomputes norm2(Y) every iteration, src/vbmf.jl:154) and the
+// per-row ||Y[l,:]||^2 of the heteroscedastic update (src/vbmf_sparse.jl:310).
+__global__ void y_stats_kernel(const double* __restrict__ Y, int ldY, int L, int M, int cols_per_blk, double* __restrict__ part) {
+    const int m0 = blockIdx.y * cols_per_blk, m1 = min(M, m0 + cols_per_blk);
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double s = 0.0;
+    for (int m = m0; m < m1; ++m) { const double v = Y[(size_t)m * ldY + l]; s = fma(v, v, s); }
+    part[(size_t)blockIdx.y * L + l] = s;
+}
+__global__ void total_kernel(const double* __restrict__ x, int n, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+int k_total(cudaStream_t st, const double* x, int n, double* out) {
+    total_kernel<<<1, 1024, 0, st>>>(x, n, out);
+    VB_LAUNCH_OK();
+    return 0;
+}
+int k_y_stats(cudaStream_t st, const Dev& d, double* out_tr) {
+    const int nby = std::max(1, std::min(MAX_PARTS / 2, cdiv(d.Mloc, 64)));
+    const int cpb = cdiv(std::max(d.Mloc, 1), nby);
+    dim3 grid(cdiv(d.L, 128), nby);
+    y_stats_kernel<<<grid, 128, 0, st>>>(d.Y, d.ldY, d.L, d.Mloc, cpb, d.part);
+    VB_LAUNCH_OK();
+    // rowY2 (local); the caller all-reduces it across shards and totals again
+    int g = std::max(1, std::min(cdiv(d.L, 256), 1184));
+    sum_partials_kernel<<<g, 256, 0, st>>>(d.part, nby, (size_t)d.L, (size_t)d.L, d.rowY2, nullptr);
+    VB_LAUNCH_OK();
+    total_kernel<<<1, 1024, 0, st>>>(d.rowY2, d.L, out_tr);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- Gram matrices
+// G[a][b] = sum_i w_i^wpow X(i,a) X(i,b).  AMAT: X is [n][H] row-major (AHat rows); else X is [H][ld] (BHat-like).
+// Used for BHat'BHat, AHat'AHat (src/vbmf.jl:96,110), B'diag(sv)B (src/vbmf_sparse.jl:182), norm2(B[:,h].*sv) (:211),
+// D'D and Bold'Bold of the convergence test (src/util.jl:28).
+template <int R, bool AMAT>
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restrict__ X, int n, int H, int ld,
+                                                           const double* __restrict__ w, int wpow, int rows_per_blk,
+                                                           double* __restrict__ part, const Scalars* sc) {
+    if (!sc->active) return;
+    extern __shared__ double sm[];
+    const int TS = H + 1;
+    double* tile = sm;             // [32][TS]
+    double* wt = sm + 32 * TS;     // [32]
+    const int ta = threadIdx.x & 15, tb = threadIdx.x >> 4;
+    double acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    const int r0 = blockIdx.x * rows_per_blk, r1 = min(n, r0 + rows_per_blk);
+    for (int rt = r0; rt < r1; rt += 32) {
+        const int nr = min(32, r1 - rt);
+        __syncthreads();
+        if (AMAT) {
+            for (int e = threadIdx.x; e < 32 * H; e += 256) {
+                const int i = e / H, a = e - i * H;
+                tile[i * TS + a] = (i < nr) ? X[(size_t)(rt + i) * H + a] : 0.0;
+            }
+        } else {
+            for (int e = threadIdx.x; e < 32 * H; e += 256) {
+                const int a = e >> 5, i = e & 31;
+                tile[i * TS + a] = (i < nr) ? X[(size_t)a * ld + rt + i] : 0.0;
+            }
+        }
+        if (threadIdx.x < 32) {
+            double wv = 1.0;
+            if (w != nullptr && threadIdx.x < nr) { wv = w[rt + threadIdx.x]; if (wpow == 2) wv *= wv; }
+            wt[threadIdx.x] = wv;
+        }
+        __syncthreads();
+        for (int i = 0; i < 32; ++i) {
+            double xa[R], xb[R];
+            const double wv = wt[i];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int a = ta + 16 * q, b = tb + 16 * q;
+                xa[q] = (a < H) ? tile[i * TS + a] * wv : 0.0;
+                xb[q] = (b < H) ? tile[i * TS + b] : 0.0;
+            }
+#pragma unroll
+            for (int p = 0; p < R; ++p)
+#pragma unroll
+                for (int q = 0; q < R; ++q) acc[p][q] = fma(xa[p], xb[q], acc[p][q]);
+        }
+    }
+    double* out = part + (size_t)blockIdx.x * H * H;
+#pragma unroll
+    for (int p = 0; p < R; ++p)
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int a = ta + 16 * p, b = tb + 16 * q;
+            if (a < H && b < H) out[a * H + b] = acc[p][q];
+        }
+}
+
+static int gram_impl(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, const double* w, int wpow, double* out) {
+    const int H = d.H;
+    const int nblk = std::max(1, std::min(296, cdiv(std::max(n, 1), 256)));
+    const int rpb = cdiv(cdiv(std::max(n, 1), nblk), 32) * 32;
+    const size_t smem = (size_t)(32 * (H + 1) + 32) * sizeof(double);
+    const int R = cdiv(H, 16);
+#define GRAM_LAUNCH(RR)                                                                                              \
+    if (amat) gram_partial_kernel<RR, true><<<nblk, 256, smem, st>>>(X, n, H, d.ldB, w, wpow, rpb, d.part, d.sc);     \
+    else gram_partial_kernel<RR, false><<<nblk, 256, smem, st>>>(X, n, H, d.ldB, w, wpow, rpb, d.part, d.sc);
+    if (R <= 1) { GRAM_LAUNCH(1) } else if (R <= 2) { GRAM_LAUNCH(2) } else if (R <= 4) { GRAM_LAUNCH(4) } else { GRAM_LAUNCH(8) }
+#undef GRAM_LAUNCH
+    VB_LAUNCH_OK();
+    return sum_partials(st, d.part, nblk, (size_t)H * H, (size_t)H * H, out, d.sc);
+}
+int k_gram(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, const double* w, double* out) {
+    return gram_impl(st, d, X, amat, n, w, 1, out);
+}
+int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const double* w, double* out) {
+    return gram_impl(st, d, X, false, n, w, 2, out);
+}
+
+// ------------------------------------------------------------------------------------------- H x H posterior covariances
+// mode 0: SigmaA = sigma2*inv(B'B + L*SigmaB + sigma2*invCA)            src/vbmf.jl:96-97
+// mode 1: SigmaB = sigma2*inv(A'A + M*SigmaA + sigma2*invCB)            src/vbmf.jl:110-111
+// mode 2: SigmaA <- all-reduced sum of per-column blocks; SigmaB = inv(diag(CB) + c*(A'A + SigmaA)),
+//         c = sigmaHat or mean(sigmaVecHat)                             src/vbmf_sparse.jl:256-265, src/vbmf_dual.jl:294-303
+__global__ void __launch_bounds__(256) hxh_kernel(Dev d, int mode, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    const int H = d.H, ld = H + 1;
+    double* Mx = sm;
+    double* vec = sm + H * ld;
+    Scalars* sc = d.sc;
+    const double* AtA = d.packed + packed_ata(d);
+    const double* SA = d.packed + packed_sa(d);
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        const int i = e / H, j = e - i * H;
+        double v;
+        if (mode == 0) v = d.BtB[e] + (double)d.L * d.SigmaB[e] + sc->sigma2 * d.invCA[e];
+        else if (mode == 1) v = AtA[e] + (double)d.Mglob * d.SigmaA[e] + sc->sigma2 * d.invCB[e];
+        else {
+            const double sa = SA[e];
+            d.SigmaA[e] = sa;
+            const double c = diag_var ? sc->meanSigmaVec : sc->sigmaHat;
+            v = ((i == j) ? d.CBv[i] : 0.0) + c * (AtA[e] + sa);
+        }
+        Mx[i * ld + j] = v;
+    }
+    __syncthreads();
+    BlockGroup g;
+    const bool ok = spd_inverse(g, Mx, ld, H, vec);
+    if (!ok && threadIdx.x == 0) sc->chol_fail = 1;
+    double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
+    const double scale = (mode == 2) ? 1.0 : sc->sigma2;
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        const int i = e / H, j = e - i * H;
+        out[e] = ok ? scale * Mx[i * ld + j] : nan("");
+    }
+}
+static size_t hxh_smem(int H) { return (size_t)(H * (H + 1) + 8 * H + 64) * sizeof(double); }
+static int hxh_attr() {
+    static bool done = false;
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(hxh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hxh_smem(128))); done = true; }
+    return 0;
+}
+int k_dense_sigmaA(cudaStream_t st, const Dev& d) {
+    if (hxh_attr()) return -1;
+    hxh_kernel<<<1, 256, hxh_smem(d.H), st>>>(d, 0, 0);
+    VB_LAUNCH_OK();
+    return 0;
+}
+int k_sigmaB(cudaStream_t st, const Dev& d, int flags) {
+    if (hxh_attr()) return -1;
+    hxh_kernel<<<1, 256, hxh_smem(d.H), st>>>(d, d.kind == KIND_DENSE ? 1 : 2, (flags & F_DIAG_VAR) ? 1 : 0);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- dense A epilogue
+// AHat = ((Y'*BHat)*SigmaA)/sigma2   src/vbmf.jl:98  (P = Y'*BHat from K1; left-to-right association, Q12)
+__global__ void __launch_bounds__(256) dense_A_epilogue_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    const int H = d.H, ld = H + 1;
+    double* S = sm;                 // [H][ld]
+    double* T = sm + H * ld;        // [32][ld]
+    for (int e = threadIdx.x; e < H * H; e += 256) S[(e / H) * ld + (e % H)] = d.SigmaA[e];
+    const double s2 = d.sc->sigma2;
+    const int ntiles = (d.Mloc + 31) / 32;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * H; e += 256) T[(e / H) * ld + (e % H)] = d.P[(size_t)m0 * H + e];
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * H; e += 256) {
+            const int r = e / H, h = e - r * H;
+            double s = 0.0;
+            for (int k = 0; k < H; ++k) s = fma(T[r * ld + k], S[k * ld + h], s);
+            d.A[(size_t)m0 * H + e] = s / s2;
+        }
+    }
+}
+int k_dense_A_epilogue(cudaStream_t st, const Dev& d) {
+    static bool done = false;
+    const size_t smem = (size_t)((d.H + 32) * (d.H + 1)) * sizeof(double);
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(dense_A_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * 129 * 8))); done = true; }
+    if (d.Mloc <= 0) return 0;
+    const int grid = std::max(1, std::min(cdiv(d.Mloc, 32), 148 * 4));
+    dense_A_epilogue_kernel<<<grid, 256, smem, st>>>(d);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// AHat[labels, end-H1+1:end] = 0.0     src/vbmf.jl:101, src/vbmf_sparse.jl:245
+__global__ void mask_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    const int n = d.nlabels * d.H1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int li = e / d.H1, c = e - li * d.H1;
+        d.A[(size_t)d.labels[li] * d.H + (d.H - d.H1 + c)] = 0.0;
+    }
+}
+int k_mask(cudaStream_t st, const Dev& d) {
+    if (d.kind == KIND_DUAL || d.nlabels <= 0 || d.H1 <= 0) return 0;
+    const int n = d.nlabels * d.H1;
+    mask_kernel<<<std::max(1, std::min(cdiv(n, 256), 592)), 256, 0, st>>>(d);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- sparse / dual A update, diagonal path
+// src/vbmf_sparse.jl:204-240 == src/vbmf_dual.jl:244-280.
+//   d_h   = sigmaHat*||B[:,h]||^2 + L*SigmaB[h,h]                       (Q3)   [diag_var: sum_l (B[l,h]*sv_l)^2 + L*mean(sv)*SigmaB[h,h], Q4]
+//   prec  = [d ; repeat(d, inner = M-1)] + CA                           (Q2: element j>H reads d[ceil((j-H)/(M-1))], global j and M)
+//   s     = 1 ./ prec ;  vec(A') = (sigmaHat*s) .* vec(B'Y)             [diag_var: s .* vec(B' diag(sv) Y)]
+//   SigmaA = diag(sum_m s[m,:])  -> per-CTA partial column sums, fixed-order reduction into packed.SA
+__global__ void __launch_bounds__(256) sparse_A_diag_kernel(Dev d, int diag_var, int rows_per_blk) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ double dv[128];
+    __shared__ double cs[256];
+    const int H = d.H;
+    const Scalars* sc = d.sc;
+    const int nthr = (256 / H) * H;          // every active thread keeps a fixed column h
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        dv[h] = diag_var ? d.BtBw[h * H + h] + (double)d.L * sc->meanSigmaVec * d.SigmaB[h * H + h]
+                         : sc->sigmaHat * d.BtB[h * H + h] + (double)d.L * d.SigmaB[h * H + h];
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    double colsum = 0.0;
+    if (t < nthr) {
+        const int m0 = blockIdx.x * rows_per_blk, m1 = min(d.Mloc, m0 + rows_per_blk);
+        const double sh = sc->sigmaHat;
+        const long long Mg1 = (long long)d.Mglob - 1;
+        for (long long e = (long long)m0 * H + t; e < (long long)m1 * H; e += nthr) {
+            const long long j0 = (long long)d.moff * H + e;                 // global 0-based index into vec(A')
+            const int src = (j0 < H) ? (int)j0 : (int)((j0 - H) / Mg1);
+            const double s = 1.0 / (dv[src] + d.CAv[e]);
+            const double p = d.P[e];
+            d.sdiag[e] = s;
+            d.A[e] = diag_var ? s * p : (sh * s) * p;
+            colsum += s;
+        }
+    }
+    cs[threadIdx.x] = (t < nthr) ? colsum : 0.0;
+    __syncthreads();
+    if (t < H) {
+        double s = 0.0;
+        for (int q = t; q < nthr; q += H) s += cs[q];
+        d.part[(size_t)blockIdx.x * H + t] = s;
+    }
+}
+__global__ void diag_to_sa_kernel(Dev d, int nparts) {   // packed.SA = diag(sum of partial column sums)
+    ACTIVE_OR_RETURN(d);
+    const int H = d.H;
+    double* SA = d.packed + packed_sa(d);
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        const int i = e / H, j = e - i * H;
+        double s = 0.0;
+        if (i == j) for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * H + i];
+        SA[e] = s;
+    }
+}
+int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags) {
+    const int nblk = std::max(1, std::min(MAX_PARTS, cdiv(std::max(d.Mloc, 1), 64)));
+    const int rpb = cdiv(std::max(d.Mloc, 1), nblk);
+    sparse_A_diag_kernel<<<nblk, 256, 0, st>>>(d, (flags & F_DIAG_VAR) ? 1 : 0, rpb);
+    VB_LAUNCH_OK();
+    diag_to_sa_kernel<<<1, 256, 0, st>>>(d, nblk);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K4: sparse / dual A update, full covariance
+// src/vbmf_sparse.jl:178-202 == src/vbmf_dual.jl:218-242.  inv(sigmaHat*kron(I_M, G0) + diagm(CA)) is block diagonal, so per
+// column m:  Sigma_m = inv(G + diag(CA_m)),  G = sigmaHat*(B'B + L*SigmaB)  [diag_var: B'diag(sv)B + L*mean(sv)*SigmaB],
+//            a_m = (sigmaHat*Sigma_m)*p_m  [diag_var: Sigma_m*p_m],  diag, SigmaA = sum_m Sigma_m.
+// One thread group (warp for H <= 32, CTA otherwise) per matrix, factor held in shared memory.
+__global__ void build_G_kernel(Dev d, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    const Scalars* sc = d.sc;
+    for (int e = threadIdx.x; e < d.H * d.H; e += blockDim.x) {
+        d.Gm[e] = diag_var ? d.BtBw[e] + (double)d.L * sc->meanSigmaVec * d.SigmaB[e]
+                           : sc->sigmaHat * (d.BtB[e] + (double)d.L * d.SigmaB[e]);
+    }
+}
+template <class G, int QMAX>
+__global__ void __launch_bounds__(256) sparse_A_full_kernel(Dev d, int diag_var, int ngroups_total) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    const int H = d.H, ld = H + 1;
+    const Scalars* sc = d.sc;
+    G g;
+    const int groups_per_cta = blockDim.x / g.size();
+    const int gid_in_cta = threadIdx.x / g.size();
+    const int gid = blockIdx.x * groups_per_cta + gid_in_cta;
+    double* Mx = sm + (size_t)gid_in_cta * (H * ld + 3 * H);
+    double* vec = Mx + H * ld;                              // 2H scratch + H for p
+    double* pv = vec + 2 * H;
+    const double* __restrict__ Gs = d.Gm;                   // H x H, L1/L2 resident
+    double acc[QMAX];
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) acc[q] = 0.0;
+    const int t = g.tid(), n = g.size();
+    const double sh = sc->sigmaHat;
+    bool all_ok = true;
+    for (int m = gid; m < d.Mloc; m += ngroups_total) {
+        const double* ca = d.CAv + (size_t)m * H;
+        for (int e = t; e < H * H; e += n) {
+            const int i = e / H, j = e - i * H;
+            Mx[i * ld + j] = Gs[e] + ((i == j) ? ca[i] : 0.0);
+        }
+        for (int h = t; h < H; h += n) pv[h] = d.P[(size_t)m * H + h];
+        g.sync();
+        const bool ok = spd_inverse(g, Mx, ld, H, vec);
+        all_ok = all_ok && ok;
+        for (int h = t; h < H; h += n) {
+            double s = 0.0;
+            if (diag_var) { for (int k = 0; k < H; ++k) s = fma(Mx[h * ld + k], pv[k], s); }
+            else { for (int k = 0; k < H; ++k) s = fma(sh * Mx[h * ld + k], pv[k], s); }
+            d.A[(size_t)m * H + h] = ok ? s : nan("");
+            d.sdiag[(size_t)m * H + h] = ok ? Mx[h * ld + h] : nan("");
+        }
+        if (d.blocks != nullptr)
+            for (int e = t; e < H * H; e += n) d.blocks[(size_t)m * H * H + e] = Mx[(e / H) * ld + (e % H)];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            const int e = t + q * n;
+            if (e < H * H) acc[q] += Mx[(e / H) * ld + (e % H)];
+        }
+        g.sync();
+    }
+    if (!all_ok && t == 0) d.sc->chol_fail = 1;
+    double* out = d.part + (size_t)gid * H * H;
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) {
+        const int e = t + q * n;
+        if (e < H * H) out[e] = acc[q];
+    }
+}
+int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
+    const int H = d.H;
+    const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
+    build_G_kernel<<<1, 256, 0, st>>>(d, dv);
+    VB_LAUNCH_OK();
+    int ngroups;
+    if (H <= 32) {
+        const int gpc = 8;                                           // 8 warps (matrices) per CTA
+        const size_t smem = (size_t)(gpc * (H * (H + 1) + 3 * H)) * sizeof(double);
+        static bool done = false;
+        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_kernel<WarpGroup, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((8 * (32 * 33 + 96)) * 8))); done = true; }
+        const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), gpc), 296));
+        ngroups = grid * gpc;
+        sparse_A_full_kernel<WarpGroup, 32><<<grid, 256, smem, st>>>(d, dv, ngroups);
+    } else {
+        const size_t smem = (size_t)(H * (H + 1) + 3 * H) * sizeof(double);
+        static bool done = false;
+        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_kernel<BlockGroup, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * 129 + 384) * 8))); done = true; }
+        const int grid = std::max(1, std::min(std::max(d.Mloc, 1), 148));
+        ngroups = grid;
+        sparse_A_full_kernel<BlockGroup, 64><<<grid, 256, smem, st>>>(d, dv, ngroups);
+    }
+    VB_LAUNCH_OK();
+    return sum_partials(st, d.part, ngroups, (size_t)H * H, (size_t)H * H, d.packed + packed_sa(d), d.sc);
+}
+
+// ------------------------------------------------------------------------------------------- element-wise ARD update of vec(A')
+// sparse: beta = beta0 + 1/2*(a.^2 + s);  CA = alpha ./ beta                        src/vbmf_sparse.jl:284-288
+// dual  : alpha_g = alpha0g + 1/2; beta_g = beta0g + 1/2*(a_g.^2 + s_g); CA_g = alpha_g ./ beta_g, group g = (h > H0)
+//         plus the sums the hyper-prior updates need: sum(CA_g), sum(log(beta_g))   src/vbmf_dual.jl:322-351,393-434
+__global__ void __launch_bounds__(256) update_CA_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ double red[32];
+    Scalars* sc = d.sc;
+    const int H = d.H;
+    const bool dual = d.kind == KIND_DUAL;
+    const double a0 = dual ? sc->alpha00 + 0.5 : sc->alpha;
+    const double a1 = dual ? sc->alpha01 + 0.5 : sc->alpha;
+    const double b0 = dual ? sc->beta00 : sc->beta0p;
+    const double b1 = dual ? sc->beta01 : sc->beta0p;
+    double sca0 = 0.0, sca1 = 0.0, slb0 = 0.0, slb1 = 0.0;
+    const long long n = (long long)d.Mloc * H;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(e % H);
+        const bool g1 = dual && h >= d.H0;
+        const double a = d.A[e];
+        const double beta = (g1 ? b1 : b0) + 0.5 * (a * a + d.sdiag[e]);
+        const double ca = (g1 ? a1 : a0) / beta;
+        d.beta[e] = beta;
+        d.CAv[e] = ca;
+        if (dual) {
+            if (g1) { sca1 += ca; slb1 += log(beta); } else { sca0 += ca; slb0 += log(beta); }
+        }
+    }
+    if (dual) {
+        sca0 = block_sum(sca0, red); sca1 = block_sum(sca1, red);
+        slb0 = block_sum(slb0, red); slb1 = block_sum(slb1, red);
+        if (threadIdx.x == 0) {
+            double* p = d.part + (size_t)blockIdx.x * 4;
+            p[0] = sca0; p[1] = sca1; p[2] = slb0; p[3] = slb1;
+            if (blockIdx.x == 0) { sc->alpha_g0 = a0; sc->alpha_g1 = a1; }
+        }
+    }
+}
+int k_update_CA(cudaStream_t st, const Dev& d) {
+    const long long n = (long long)d.Mloc * d.H;
+    const int grid = std::max(1, (int)std::min<long long>((n + 1023) / 1024, MAX_PARTS));
+    update_CA_kernel<<<grid, 256, 0, st>>>(d);
+    VB_LAUNCH_OK();
+    if (d.kind == KIND_DUAL) return sum_partials(st, d.part, grid, 4, 4, d.packed + packed_ex(d), d.sc);
+    return 0;
+}
+
+// fixed-order reduction of the split-K slabs of K2 into the all-reduce payload
+int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
+    const size_t n = (size_t)d.H * d.ldB;
+    return sum_partials(st, Qpart, S, n, n, d.packed + packed_q(d), d.sc);
+}
+
+// ------------------------------------------------------------------------------------------- B epilogue
+// dense : BHat = ((Y*AHat)*SigmaB)/sigma2                       src/vbmf.jl:112
+// sparse: BHat = ((sigmaHat*Y)*AHat)*SigmaB                     src/vbmf_sparse.jl:266   (diag_var: diagm(sv)*Y*AHat*SigmaB, :261)
+// also keeps Bold, D = BHat - Bold (convergence test, src/util.jl:27-29) and partial sums of tr(BHat'*(Y*AHat))
+__global__ void __launch_bounds__(256) B_epilogue_kernel(Dev d, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const int H = d.H, ld = H + 1;
+    double* S = sm;              // [H][ld]   SigmaB
+    double* T = sm + H * ld;     // [32][ld]  scaled Q tile
+    const Scalars* sc = d.sc;
+    const double* Q = d.packed + packed_q(d);
+    for (int e = threadIdx.x; e < H * H; e += 256) S[(e / H) * ld + (e % H)] = d.SigmaB[e];
+    const bool dense = d.kind == KIND_DENSE;
+    const double s2 = sc->sigma2, sh = sc->sigmaHat;
+    double tr = 0.0;
+    const int ntiles = (d.L + 31) / 32;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int l0 = tile * 32, nr = min(32, d.L - l0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * H; e += 256) {
+            const int h = e >> 5, i = e & 31;
+            double q = 0.0;
+            if (i < nr) {
+                q = Q[(size_t)h * d.ldB + l0 + i];
+                if (!dense) q *= diag_var ? d.sigmaVec[l0 + i] : sh;
+            }
+            T[i * ld + h] = q;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * H; e += 256) {
+            const int h = e >> 5, i = e & 31;
+            if (i < nr) {
+                double s = 0.0;
+                for (int k = 0; k < H; ++k) s = fma(T[i * ld + k], S[k * ld + h], s);
+                if (dense) s /= s2;
+                const size_t idx = (size_t)h * d.ldB + l0 + i;
+                const double old = d.B[idx];
+                d.Bold[idx] = old;
+                d.D[idx] = s - old;
+                d.B[idx] = s;
+                tr = fma(s, Q[idx], tr);
+            }
+        }
+    }
+    tr = block_sum(tr, red);
+    if (threadIdx.x == 0) d.part[blockIdx.x] = tr;
+}
+__global__ void trbq_kernel(Dev d, int nparts) {
+    ACTIVE_OR_RETURN(d);
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += d.part[p];
+    d.sc->trBQ = s;
+}
+int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
+    static bool done = false;
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * 129 * 8))); done = true; }
+    const size_t smem = (size_t)((d.H + 32) * (d.H + 1)) * sizeof(double);
+    const int grid = std::max(1, std::min(cdiv(d.L, 32), MAX_PARTS));
+    B_epilogue_kernel<<<grid, 256, smem, st>>>(d, (flags & F_DIAG_VAR) ? 1 : 0);
+    VB_LAUNCH_OK();
+    trbq_kernel<<<1, 1, 0, st>>>(d, grid);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// tr(BHat' * Q) only (step-level updateSigma / lowerBound when BHat was not just produced by the epilogue)
+__global__ void __launch_bounds__(256) trbq_partial_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ double red[32];
+    const double* Q = d.packed + packed_q(d);
+    double tr = 0.0;
+    const long long n = (long long)d.H * d.ldB;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+        const int l = (int)(e % d.ldB);
+        if (l < d.L) tr = fma(d.B[e], Q[e], tr);
+    }
+    tr = block_sum(tr, red);
+    if (threadIdx.x == 0) d.part[blockIdx.x] = tr;
+}
+int k_trbq(cudaStream_t st, const Dev& d) {
+    const int grid = std::max(1, std::min(cdiv((long)d.H * d.ldB, 1024), MAX_PARTS));
+    trbq_partial_kernel<<<grid, 256, 0, st>>>(d);
+    VB_LAUNCH_OK();
+    trbq_kernel<<<1, 1, 0, st>>>(d, grid);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- heteroscedastic noise rows
+// zetaVec[l] = zeta0 + 1/2*||Y[l,:]||^2 - Y[l,:]*(AHat*BHat[l,:]) + 1/2*traceXTY(A'A + SigmaA, b_l b_l' + SigmaB)
+// sigmaVecHat[l] = etaVec[l]/zetaVec[l]                         src/vbmf_sparse.jl:309-316 == src/vbmf_dual.jl:372-379
+// Y[l,:]*(AHat*b_l) = Q[l,:]*b_l with Q = Y*AHat already reduced.
+__global__ void __launch_bounds__(128) sigma_rows_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ double s_trc;
+    const int H = d.H;
+    double* GA = sm;   // [H][H]
+    const double* AtA = d.packed + packed_ata(d);
+    const double* Q = d.packed + packed_q(d);
+    double trc = 0.0;
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        const double ga = AtA[e] + d.SigmaA[e];
+        GA[e] = ga;
+        trc = fma(ga, d.SigmaB[e], trc);
+    }
+    trc = block_sum(trc, red);
+    if (threadIdx.x == 0) s_trc = trc;
+    __syncthreads();
+    double part = 0.0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < d.L; l += gridDim.x * blockDim.x) {
+        double qb = 0.0, quad = 0.0;
+        for (int a = 0; a < H; ++a) {
+            const double ba = d.B[(size_t)a * d.ldB + l];
+            qb = fma(Q[(size_t)a * d.ldB + l], ba, qb);
+            double row = 0.0;
+            for (int b = 0; b < H; ++b) row = fma(GA[a * H + b], d.B[(size_t)b * d.ldB + l], row);
+            quad = fma(ba, row, quad);
+        }
+        const double z = d.sc->zeta0 + 0.5 * d.rowY2[l] - qb + 0.5 * (quad + s_trc);
+        d.zetaVec[l] = z;
+        const double sv = d.etaVec[l] / z;
+        d.sigmaVec[l] = sv;
+        part += sv;
+    }
+    part = block_sum(part, red);
+    if (threadIdx.x == 0) d.part[blockIdx.x] = part;
+}
+__global__ void mean_sigma_kernel(Dev d, int nparts) {
+    ACTIVE_OR_RETURN(d);
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += d.part[p];
+    d.sc->meanSigmaVec = s / (double)d.L;
+}
+int k_sigma_rows(cudaStream_t st, const Dev& d) {
+    static bool done = false;
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sigma_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8)); done = true; }
+    const int grid = std::max(1, std::min(cdiv(d.L, 128), MAX_PARTS));
+    sigma_rows_kernel<<<grid, 128, (size_t)d.H * d.H * 8, st>>>(d);
+    VB_LAUNCH_OK();
+    mean_sigma_kernel<<<1, 1, 0, st>>>(d, grid);
+    VB_LAUNCH_OK();
+    return 0;
+}
+// mean(sigmaVecHat) from the current vector (after an upload)
+__global__ void __launch_bounds__(256) mean_only_kernel(Dev d) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int l = threadIdx.x; l < d.L; l += blockDim.x) s += d.sigmaVec[l];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) d.sc->meanSigmaVec = s / (double)d.L;
+}
+int k_mean_sigma(cudaStream_t st, const Dev& d) {
+    mean_only_kernel<<<1, 256, 0, st>>>(d);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// Bs = diag(sigmaVecHat)*BHat : B operand of K1 when diag_var (B' diag(sv) Y, src/vbmf_sparse.jl:193,230)
+__global__ void scale_B_kernel(Dev d) {
+    ACTIVE_OR_RETURN(d);
+    const long long n = (long long)d.H * d.ldB;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(e % d.ldB);
+        d.Bs[e] = (l < d.L) ? d.sigmaVec[l] * d.B[e] : 0.0;
+    }
+}
+int k_scale_B(cudaStream_t st, const Dev& d) {
+    scale_B_kernel<<<std::max(1, std::min(cdiv((long)d.H * d.ldB, 256), 1184)), 256, 0, st>>>(d);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- post step (single CTA)
+// Hyper-parameter / noise updates that only need H x H and scalar data, the convergence test and the loop control.
+enum { POST_CA = 1, POST_CB = 2, POST_SIGMA = 4, POST_A00 = 8, POST_A01 = 16, POST_B00 = 32, POST_B01 = 64, POST_DELTA = 128,
+       POST_NORM_INIT = 256 };
+
+// inverse digamma on [1e-10, 1e10] by Newton from the left (psi is increasing and concave, so the iteration is monotone);
+// stands in for Roots.fzero(f, 1e-10, 1e10) of f(x) = N*log(beta0x) - N*digamma(x) + sum(digamma(alpha) - log(beta_i))
+// (src/vbmf_dual.jl:393-401,417-425).  Returns false when there is no sign change in the bracket (Q11: keep the old value).
+__device__ bool solve_alpha(double N, double beta0x, double alpha_g, double sum_log_beta, double* root) {
+    const double S = N * digamma_pos(alpha_g) - sum_log_beta;      // sum_i gammaELn(alpha_g, beta_i)
+    const double c0 = N * log(beta0x);
+    const double fa = c0 - N * digamma_pos(1e-10) + S, fb = c0 - N * digamma_pos(1e10) + S;
+    if (!isfinite(fa) || !isfinite(fb) || fa * fb > 0.0) return false;
+    if (fa == 0.0) { *root = 1e-10; return true; }
+    if (fb == 0.0) { *root = 1e10; return true; }
+    const double c = (c0 + S) / N;                                  // psi(x) = c
+    double x = (c >= -2.22) ? exp(c) + 0.5 : -1.0 / (c + 0.5772156649015329);
+    for (int it = 0; it < 100; ++it) {
+        const double f = digamma_pos(x) - c;
+        double xn = x - f / trigamma_pos(x);
+        if (!(xn > 0.0)) xn = 0.5 * x;
+        if (fabs(xn - x) <= 2e-16 * fabs(xn)) { x = xn; break; }
+        x = xn;
+    }
+    x = fmin(fmax(x, 1e-10), 1e10);
+    *root = x;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
+    if (!d.sc->active) return;
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ double s_val[4];
+    Scalars* sc = d.sc;
+    const int H = d.H, ld = H + 2;       // even padded size for Jacobi needs ld >= H+1
+    double* Mx = sm;                      // [(H+1)][ld]
+    double* vec = sm + (H + 2) * ld;      // 4*(H+2)
+    const double* AtA = d.packed + packed_ata(d);
+    const double* EX = d.packed + packed_ex(d);
+    const int t = threadIdx.x;
+    BlockGroup g;
+
+    if (d.kind == KIND_DENSE) {
+        // updateCA! / updateCB!  src/vbmf.jl:129-146 : C[h,h] = ||X[:,h]||^2/n + Sigma[h,h]; invC = inv(C)
+        for (int which = 0; which < 2; ++which) {
+            if (!(what & (which == 0 ? POST_CA : POST_CB))) continue;
+            double* C = which == 0 ? d.CA : d.CB;
+            double* invC = which == 0 ? d.invCA : d.invCB;
+            const double* Gm = which == 0 ? AtA : d.BtB;
+            const double* Sg = which == 0 ? d.SigmaA : d.SigmaB;
+            const double nn = which == 0 ? (double)d.Mglob : (double)d.L;
+            __syncthreads();
+            for (int h = t; h < H; h += blockDim.x) C[h * H + h] = Gm[h * H + h] / nn + Sg[h * H + h];
+            __syncthreads();
+            int offdiag = 0;
+            for (int e = t; e < H * H; e += blockDim.x) {
+                const int i = e / H, j = e - i * H;
+                Mx[i * ld + j] = C[e];
+                if (i != j && C[e] != 0.0) offdiag = 1;
+            }
+            offdiag = __syncthreads_or(offdiag);
+            if (!offdiag) {
+                for (int e = t; e < H * H; e += blockDim.x) {
+                    const int i = e / H, j = e - i * H;
+                    invC[e] = (i == j) ? 1.0 / C[e] : 0.0;
+                }
+            } else {
+                const bool ok = spd_inverse(g, Mx, ld, H, vec);
+                if (!ok && t == 0) sc->chol_fail = 1;
+                for (int e = t; e < H * H; e += blockDim.x) invC[e] = ok ? Mx[(e / H) * ld + (e % H)] : nan("");
+            }
+            __syncthreads();
+        }
+        if (what & POST_SIGMA) {
+            // updateSigma2!  src/vbmf.jl:153-157 ; tr(2*Y'*B*A') = 2*sum(B .* (Y*A)), tr(X*Z) = sum(X .* Z') (symmetric)
+            double s = 0.0;
+            for (int e = t; e < H * H; e += blockDim.x) {
+                const int i = e / H, j = e - i * H;
+                const double x = AtA[e] + (double)d.Mglob * d.SigmaA[e];
+                const double z = d.BtB[j * H + i] + (double)d.L * d.SigmaB[j * H + i];
+                s = fma(x, z, s);
+            }
+            s = block_sum(s, red);
+            if (t == 0) sc->sigma2 = (sc->trYTY - 2.0 * sc->trBQ + s) / ((double)d.L * (double)d.Mglob);
+            __syncthreads();
+        }
+    } else {
+        if (what & POST_CB) {
+            // updateCB!  src/vbmf_sparse.jl:295-300 (Q6: 1/2*SigmaB[h,h])
+            for (int h = t; h < H; h += blockDim.x) {
+                const double dl = sc->delta0 + 0.5 * d.BtB[h * H + h] + 0.5 * d.SigmaB[h * H + h];
+                d.deltav[h] = dl;
+                d.CBv[h] = sc->gamma / dl;
+            }
+            __syncthreads();
+        }
+        if ((what & POST_SIGMA) && !(flags & F_DIAG_VAR)) {
+            // updateSigma! homoscedastic  src/vbmf_sparse.jl:317-322
+            double s = 0.0;
+            for (int e = t; e < H * H; e += blockDim.x) {
+                const double x = AtA[e] + d.SigmaA[e];
+                const double z = d.BtB[e] + (double)d.L * d.SigmaB[e];
+                s = fma(x, z, s);
+            }
+            s = block_sum(s, red);
+            if (t == 0) {
+                sc->zeta = sc->zeta0 + 0.5 * sc->trYTY - sc->trBQ + 0.5 * s;
+                sc->sigmaHat = sc->eta / sc->zeta;
+            }
+            __syncthreads();
+        }
+        if (d.kind == KIND_DUAL && t == 0) {
+            // updateAlpha00!, updateAlpha01!, updateBeta00!, updateBeta01! in this order  src/vbmf_dual.jl:491-497
+            const double N0 = (double)d.Mglob * d.H0, N1 = (double)d.Mglob * d.H1;
+            double r;
+            if ((what & POST_A00) && solve_alpha(N0, sc->beta00, sc->alpha_g0, EX[2], &r)) sc->alpha00 = r;
+            if ((what & POST_A01) && solve_alpha(N1, sc->beta01, sc->alpha_g1, EX[3], &r)) sc->alpha01 = r;
+            if (what & POST_B00) sc->beta00 = N0 * sc->alpha00 / EX[0];
+            if (what & POST_B01) sc->beta01 = N1 * sc->alpha01 / EX[1];
+        }
+        __syncthreads();
+    }
+
+    if (what & (POST_DELTA | POST_NORM_INIT)) {
+        // delta(new, old) = norm(old - new)/norm(old), src/util.jl:27-29; Julia 0.5 norm(::Matrix) = sigma_max (Q1)
+        const int n = (H + 1) & ~1;
+        for (int pass = (what & POST_DELTA) ? 0 : 1; pass < 2; ++pass) {
+            const double* Gm = pass == 0 ? d.DtD : d.BtB;
+            double val;
+            if (sc->norm_mode == 1) {
+                double s = 0.0;
+                for (int h = t; h < H; h += blockDim.x) s += Gm[h * H + h];
+                s = block_sum(s, red);
+                if (t == 0) s_val[pass] = s;
+                __syncthreads();
+                val = s_val[pass];
+            } else {
+                __syncthreads();
+                for (int e = t; e < n * n; e += blockDim.x) {
+                    const int i = e / n, j = e - i * n;
+                    Mx[i * ld + j] = (i < H && j < H) ? 0.5 * (Gm[i * H + j] + Gm[j * H + i]) : 0.0;
+                }
+                __syncthreads();
+                val = jacobi_lambda_max(Mx, ld, n, vec, red);
+            }
+            if (t == 0) s_val[pass] = sqrt(fmax(val, 0.0)) + (val != val ? val : 0.0);
+            __syncthreads();
+        }
+        if (t == 0) {
+            if (what & POST_DELTA) {
+                const double dd = s_val[0] / sc->normBold;
+                sc->d = dd;
+                sc->iter += 1;
+                sc->active = (sc->iter < sc->niter) && (dd > sc->eps) ? 1 : 0;
+            }
+            sc->normBold = s_val[1];
+        }
+    }
+}
+static size_t post_smem(int H) { return (size_t)((H + 2) * (H + 2) + 4 * (H + 2) + 8) * sizeof(double); }
+static int post_launch(cudaStream_t st, const Dev& d, int what, int flags) {
+    static bool done = false;
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128))); done = true; }
+    post_kernel<<<1, 256, post_smem(d.H), st>>>(d, what, flags);
+    VB_LAUNCH_OK();
+    return 0;
+}
+int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta) {
+    int what = with_delta ? POST_DELTA : 0;
+    if (d.kind == KIND_DENSE) {
+        if (flags & F_EST_COVS) what |= POST_CA | POST_CB;
+        if (flags & F_EST_VAR) what |= POST_SIGMA;
+    } else {
+        if (flags & F_EST_CB) what |= POST_CB;
+        what |= POST_SIGMA;
+        if (d.kind == KIND_DUAL && (flags & F_EST_PRIORS)) what |= POST_A00 | POST_A01 | POST_B00 | POST_B01;
+    }
+    return post_launch(st, d, what, flags);
+}
+int k_norms_init(cudaStream_t st, const Dev& d) { return post_launch(st, d, POST_NORM_INIT, 0); }
+int k_updateCB_only(cudaStream_t st, const Dev& d) { return post_launch(st, d, POST_CB, 0); }
+int k_dense_cov_only(cudaStream_t st, const Dev& d, int which) { return post_launch(st, d, which == 0 ? POST_CA : POST_CB, 0); }
+int k_sigma_only(cudaStream_t st, const Dev& d, int flags) { return post_launch(st, d, POST_SIGMA, flags); }
+int k_prior_only(cudaStream_t st, const Dev& d, int which) { return post_launch(st, d, POST_A00 << which, 0); }
+
+// ------------------------------------------------------------------------------------------- K10: YHat = BHat*AHat'
+// src/vbmf.jl:120-122, src/vbmf_sparse.jl:275-277 -- on demand only (L x M output).
+__global__ void __launch_bounds__(256) yhat_kernel(Dev d, double* __restrict__ out, int ldo) {
+    extern __shared__ double sm[];
+    const int H = d.H;
+    double* Bt = sm;            // [64][H+1]
+    double* At = sm + 64 * (H + 1);   // [16][H]
+    const int l0 = blockIdx.x * 64, m0 = blockIdx.y * 16;
+    for (int e = threadIdx.x; e < 64 * H; e += 256) {
+        const int h = e >> 6, i = e & 63;
+        Bt[i * (H + 1) + h] = (l0 + i < d.L) ? d.B[(size_t)h * d.ldB + l0 + i] : 0.0;
+    }
+    for (int e = threadIdx.x; e < 16 * H; e += 256) {
+        const int r = e / H;
+        At[e] = (m0 + r < d.Mloc) ? d.A[(size_t)(m0 + r) * H + (e - r * H)] : 0.0;
+    }
+    __syncthreads();
+    const int i = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+    for (int c = c0; c < 16; c += 4) {
+        double s = 0.0;
+        for (int h = 0; h < H; ++h) s = fma(Bt[i * (H + 1) + h], At[c * H + h], s);
+        if (l0 + i < d.L && m0 + c < d.Mloc) out[(size_t)(m0 + c) * ldo + l0 + i] = s;
+    }
+}
+int k_yhat(cudaStream_t st, const Dev& d, double* out, int ldo) {
+    static bool done = false;
+    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(yhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 129 + 16 * 128) * 8)); done = true; }
+    if (d.L <= 0 || d.Mloc <= 0) return 0;
+    dim3 grid(cdiv(d.L, 64), cdiv(d.Mloc, 16));
+    yhat_kernel<<<grid, 256, (size_t)(64 * (d.H + 1) + 16 * d.H) * 8, st>>>(d, out, ldo);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K7: lower bound
+// lowerBound / lowerBoundTrimmed: src/vbmf_sparse.jl:435-489, src/vbmf_dual.jl:556-617.  Phase 0 streams the local slice of
+// the MH-length vectors into 9 sums (fixed-order), phase 1 (after the cross-shard all-reduce) assembles the scalar.
+//   acc[0..1] sum(log(beta_g)) all elements, group 0/1      acc[2..3] sum(CA_g) all elements
+//   acc[4] sum(log(beta)) kept   acc[5] sum(CA) kept   acc[6] sum(CA.*(a.^2+s)) kept   acc[7] sum(log(s)) kept   acc[8] #kept
+__global__ void __launch_bounds__(256) lb_partial_kernel(Dev d, double trim, int trimmed) {
+    __shared__ double red[32];
+    const int H = d.H;
+    double a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = 0.0;
+    const long long n = (long long)d.Mloc * H;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(e % H);
+        const int g1 = (d.kind == KIND_DUAL && h >= d.H0) ? 1 : 0;
+        const double av = d.A[e], be = d.beta[e], ca = d.CAv[e], s = d.sdiag[e];
+        const double lbv = log(be);
+        a[g1] += lbv;
+        a[2 + g1] += ca;
+        if (!trimmed || fabs(av) > trim) {
+            a[4] += lbv; a[5] += ca; a[6] += ca * (av * av + s); a[7] += log(s); a[8] += 1.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double v = block_sum(a[i], red);
+        if (threadIdx.x == 0) d.part[(size_t)blockIdx.x * 9 + i] = v;
+    }
+}
+__global__ void lb_reduce_kernel(Dev d, int nparts) {
+    const int i = threadIdx.x;
+    if (i < 9) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * 9 + i];
+        d.lbacc[i] = s;
+    }
+}
+
+__device__ inline double gammaELn_d(double a, double logb) { return digamma_pos(a) - logb; }
+
+// normalEntropy(kron(SigmaB, eye(L))) with Julia's left-to-right Float64 determinant product emulated (Q7):
+// LU with partial pivoting of SigmaB, u_aa each repeated L times.  Single thread, H <= 128.
+__device__ double normal_entropy_kron(const double* SigmaB, int H, int L, double* W /* H*H scratch */) {
+    const double LOG_EPS0 = -744.4400719213812;          // log(4.9406564584124654e-324)
+    const double LOG_MIN = LOG_EPS0 - 0.6931471805599453, LOG_MAX = 709.782712893384;
+    for (int e = 0; e < H * H; ++e) W[e] = SigmaB[e];
+    double sign = 1.0, run = 0.0;
+    int state = 0;   // 0 finite, 1 zero, 2 inf
+    for (int k = 0; k < H && state == 0; ++k) {
+        int piv = k; double best = fabs(W[k * H + k]);
+        for (int i = k + 1; i < H; ++i) if (fabs(W[i * H + k]) > best) { best = fabs(W[i * H + k]); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < H; ++j) { const double tmp = W[k * H + j]; W[k * H + j] = W[piv * H + j]; W[piv * H + j] = tmp; }
+            if (L & 1) sign = -sign;
+        }
+        const double u = W[k * H + k];
+        if (u == 0.0) { state = 1; break; }
+        if (u < 0.0 && (L & 1)) sign = -sign;
+        for (int i = k + 1; i < H; ++i) {
+            const double f = W[i * H + k] / u;
+            for (int j = k + 1; j < H; ++j) W[i * H + j] -= f * W[k * H + j];
+        }
+        run += (double)L * log(fabs(u));
+        if (run < LOG_MIN) state = 1; else if (run > LOG_MAX) state = 2;
+    }
+    double logd;
+    if (state == 1) logd = LOG_EPS0;
+    else if (state == 2) logd = sign > 0 ? INFINITY : LOG_EPS0;
+    else { logd = sign > 0 ? run : LOG_EPS0; if (logd < LOG_EPS0) logd = LOG_EPS0; }
+    const double m = (double)L * H;
+    return m / 2 + m / 2 * 1.8378770664093453 + 0.5 * logd;
+}
+
+__global__ void lb_final_kernel(Dev d, int trimmed) {
+    extern __shared__ double W[];
+    if (threadIdx.x != 0) return;
+    Scalars* sc = d.sc;
+    const double ln2pi = 1.8378770664093453;
+    const int H = d.H;
+    const double L = d.L, M = d.Mglob;
+    const double* AtA = d.packed + packed_ata(d);
+    const double* acc = d.lbacc;
+    double tGAGB = 0.0, trCBGB = 0.0, sumCB = 0.0, sumLogDelta = 0.0;
+    for (int e = 0; e < H * H; ++e) tGAGB = fma(AtA[e] + d.SigmaA[e], d.BtB[e] + L * d.SigmaB[e], tGAGB);
+    for (int h = 0; h < H; ++h) {
+        trCBGB = fma(d.CBv[h], d.BtB[h * H + h] + L * d.SigmaB[h * H + h], trCBGB);
+        sumCB += d.CBv[h];
+        sumLogDelta += log(d.deltav[h]);
+    }
+    const double elnS = gammaELn_d(sc->eta, log(sc->zeta));
+    const double psiG = digamma_pos(sc->gamma);
+    const double elnD = H * psiG - sumLogDelta;
+    const double MHk = acc[8];                              // params.MH (kept count when trimmed)
+    double Lb = 0.0;
+    Lb += -L * M / 2 * ln2pi + L * M / 2 * elnS;
+    Lb += -sc->sigmaHat / 2 * (sc->trYTY - 2 * sc->trBQ + tGAGB);
+    if (d.kind == KIND_SPARSE) {
+        const double psiA = digamma_pos(sc->alpha);
+        const double elnB = MHk * psiA - acc[4];
+        Lb += -MHk / 2 * ln2pi + 0.5 * elnB;
+        Lb += -(0.5 * acc[6]);
+        Lb += -L * H / 2 * ln2pi;
+        Lb += L / 2 * elnD;
+        Lb += -0.5 * trCBGB;
+        Lb += sc->eta0 * log(sc->zeta0) - lgamma(sc->eta0);
+        Lb += (sc->eta0 - 1) * elnS - sc->zeta0 * sc->sigmaHat;
+        Lb += MHk * (sc->alpha0p * log(sc->beta0p) - lgamma(sc->alpha0p));
+        Lb += (sc->alpha0p - 1) * elnB;
+        Lb += -sc->beta0p * acc[5];
+        Lb += H * (sc->gamma0 * log(sc->delta0) - lgamma(sc->gamma0));
+        Lb += (sc->gamma0 - 1) * elnD;
+        Lb += -sc->gamma0 * sumCB;                          // Q13
+        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[7];
+        Lb += normal_entropy_kron(d.SigmaB, H, d.L, W);
+        Lb += sc->eta + log(sc->zeta) + lgamma(sc->eta) + (1 - sc->eta) * digamma_pos(sc->eta);
+        Lb += MHk * (sc->alpha + lgamma(sc->alpha) + (1 - sc->alpha) * psiA) + acc[4];
+    } else {
+        const double N0 = M * d.H0, N1 = M * d.H1;
+        const double a0 = sc->alpha_g0, a1 = sc->alpha_g1;
+        const double psi0 = digamma_pos(a0), psi1 = digamma_pos(a1);
+        const double eln0 = N0 * psi0 - acc[0], eln1 = N1 * psi1 - acc[1];
+        Lb += -MHk / 2 * ln2pi + 0.5 * eln0;
+        Lb += 0.5 * eln1;
+        Lb += -(0.5 * acc[6]);
+        Lb += -L * H / 2 * ln2pi;
+        Lb += L / 2 * elnD;
+        Lb += -0.5 * trCBGB;
+        Lb += sc->eta0 * log(sc->zeta0) - lgamma(sc->eta0);
+        Lb += (sc->eta0 - 1) * elnS - sc->zeta0 * sc->sigmaHat;
+        Lb += N0 * (sc->alpha00 * log(sc->beta00) - lgamma(sc->alpha00));
+        Lb += (sc->alpha00 - 1) * eln0;
+        Lb += -sc->beta00 * acc[2];
+        Lb += N1 * (sc->alpha01 * log(sc->beta01) - lgamma(sc->alpha01));
+        Lb += (sc->alpha01 - 1) * eln1;
+        Lb += -sc->beta01 * acc[3];
+        Lb += H * (sc->gamma0 * log(sc->delta0) - lgamma(sc->gamma0));
+        Lb += (sc->gamma0 - 1) * elnD;
+        Lb += -sc->gamma0 * sumCB;
+        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[7];
+        Lb += normal_entropy_kron(d.SigmaB, H, d.L, W);
+        Lb += sc->eta + log(sc->zeta) + lgamma(sc->eta) + (1 - sc->eta) * digamma_pos(sc->eta);
+        Lb += (N0 > 0 ? N0 * (a0 + lgamma(a0) + (1 - a0) * psi0) : 0.0) + acc[0];
+        Lb += (N1 > 0 ? N1 * (a1 + lgamma(a1) + (1 - a1) * psi1) : 0.0) + acc[1];
+    }
+    Lb += H * (sc->gamma + lgamma(sc->gamma) + (1 - sc->gamma) * psiG) + sumLogDelta;
+    sc->lb = Lb;
+}
+int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int phase) {
+    if (phase == 0) {
+        const long long n = (long long)d.Mloc * d.H;
+        const int grid = std::max(1, (int)std::min<long long>((n + 1023) / 1024, MAX_PARTS));
+        lb_partial_kernel<<<grid, 256, 0, st>>>(d, trim, trimmed);
+        VB_LAUNCH_OK();
+        lb_reduce_kernel<<<1, 32, 0, st>>>(d, grid);
+        VB_LAUNCH_OK();
+    } else {
+        static bool done = false;
+        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(lb_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8)); done = true; }
+        lb_final_kernel<<<1, 32, (size_t)d.H * d.H * 8, st>>>(d, trimmed);
+        VB_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K9: synthetic inputs
+// Philox4x32-10 counter-based normals; the stream of Y[:, m] depends only on (seed, global column m), so any sharding of
+// the columns generates the same matrix.
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t stream, uint64_t idx) {
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+__global__ void randn_kernel(double* x, size_t n, uint64_t seed, uint64_t stream, uint64_t offset) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] = philox_normal(seed, stream, offset + i);
+}
+int k_randn(cudaStream_t st, double* x, size_t n, uint64_t seed, uint64_t stream) {
+    if (n == 0) return 0;
+    randn_kernel<<<std::max(1, std::min(cdiv((long)n, 256), 2368)), 256, 0, st>>>(x, n, seed, stream, 0);
+    VB_LAUNCH_OK();
+    return 0;
+}
+// Y[l, m] = sum_r B0[l, r]*A0[mg, r] + noise*E[l, mg],  B0 ~ stream 1, A0 ~ stream 2, E ~ stream 3 (mg = global column)
+__global__ void __launch_bounds__(256) synth_kernel(double* __restrict__ Y, int ldY, int L, int Mloc, int moff, int rank,
+                                                    double noise, uint64_t seed) {
+    extern __shared__ double sm[];
+    double* B0 = sm;                 // [64][rank]
+    double* A0 = sm + 64 * rank;     // [16][rank]
+    const int l0 = blockIdx.x * 64, m0 = blockIdx.y * 16;
+    for (int e = threadIdx.x; e < 64 * rank; e += 256)
+        B0[e] = philox_normal(seed, 1, (uint64_t)(l0 + e / rank) * rank + (e % rank));
+    for (int e = threadIdx.x; e < 16 * rank; e += 256)
+        A0[e] = philox_normal(seed, 2, (uint64_t)(moff + m0 + e / rank) * rank + (e % rank));
+    __syncthreads();
+    const int i = threadIdx.x & 63;
+    for (int c = threadIdx.x >> 6; c < 16; c += 4) {
+        const int l = l0 + i, m = m0 + c;
+        if (l < L && m < Mloc) {
+            double s = 0.0;
+            for (int r = 0; r < rank; ++r) s = fma(B0[i * rank + r], A0[c * rank + r], s);
+            s += noise * philox_normal(seed, 3, (uint64_t)(moff + m) * (uint64_t)L + l);
+            Y[(size_t)m * ldY + l] = s;
+        }
+    }
+}
+int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int rank, double noise, uint64_t seed) {
+    if (L <= 0 || Mloc <= 0) return 0;
+    if (rank > 256) { set_error("synthetic rank %d > 256", rank); return -1; }
+    dim3 grid(cdiv(L, 64), cdiv(Mloc, 16));
+    synth_kernel<<<grid, 256, (size_t)80 * rank * 8, st>>>(Y, ldY, L, Mloc, moff, rank, noise, seed);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace vb

@@ -1,0 +1,83 @@
+// Launcher interface of the fused small kernels of the VB loop (everything that is not one of the two GEMMs).
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+enum Kind { KIND_DENSE = 0, KIND_SPARSE = 1, KIND_DUAL = 2 };
+
+// Plain-old-data view of one solver's device state, passed by value to kernels.
+struct Dev {
+    int kind;
+    int L, ldB;          // rows of Y; leading dimension of the [H][ldB] column-major L x H buffers
+    int Mloc, Mglob, moff;   // columns of Y in this shard / in total / global index of the first local column
+    int H, H0, H1;       // rank; dual: first group width H0, second H1 = H - H0; dense/sparse: H1 masked columns
+    int nlabels;
+    Scalars* sc;
+    const double* Y; int ldY;
+    double* rowY2;       // [L] global sum_m Y[l,m]^2
+    double* A;           // [Mloc][H]   AHat rows (== ATVecHat slice, H fastest)
+    double* P;           // [Mloc][H]   Y' * BHat (raw K1 output / staging)
+    double* B;           // [H][ldB]    BHat
+    double* Bold;        // [H][ldB]    previous BHat
+    double* D;           // [H][ldB]    BHat - Bold
+    double* Bs;          // [H][ldB]    diag(sigmaVecHat) * BHat (diag_var)
+    double* packed;      // [H*ldB | H*H | H*H | 8]  all-reduce payload: Q, A'A, sum of Sigma blocks, dual sums
+    double* SigmaA; double* SigmaB;           // [H][H]
+    double* CA; double* CB; double* invCA; double* invCB;   // dense: [H][H]
+    double* CAv; double* beta; double* sdiag; // sparse/dual: [Mloc*H] prior precision, its rate, diag of Sigma
+    double* blocks;      // optional [Mloc][H][H] full_cov covariance blocks (nullptr unless requested)
+    double* CBv; double* deltav;              // sparse/dual: [H]
+    double* sigmaVec; double* etaVec; double* zetaVec;   // [L]
+    double* BtB; double* BtBw; double* DtD;   // [H][H] Grams: B'B, B'diag(w)B, D'D
+    double* Gm;          // [H][H] likelihood part of the per-column precision (full_cov)
+    double* part;        // partial-sum workspace
+    const int* labels;   // local 0-based rows of A to mask
+    double* lbacc;       // [32] lower-bound accumulators
+};
+
+__host__ __device__ inline size_t packed_q(const Dev& d) { return 0; }
+__host__ __device__ inline size_t packed_ata(const Dev& d) { return (size_t)d.H * d.ldB; }
+__host__ __device__ inline size_t packed_sa(const Dev& d) { return (size_t)d.H * d.ldB + (size_t)d.H * d.H; }
+__host__ __device__ inline size_t packed_ex(const Dev& d) { return (size_t)d.H * d.ldB + 2 * (size_t)d.H * d.H; }
+__host__ __device__ inline size_t packed_len(const Dev& d) { return packed_ex(d) + 8; }
+
+constexpr int MAX_PARTS = 592;   // upper bound on per-kernel partial blocks (4 x 148)
+
+// flags shared by steps
+enum {
+    F_DIAG_VAR = 1, F_FULL_COV = 2, F_EST_CB = 4, F_EST_PRIORS = 8, F_EST_COVS = 16, F_EST_VAR = 32,
+    F_FORCE = 64   // ignore sc->active (step-level API)
+};
+
+int k_set_control(cudaStream_t st, const Dev& d, int niter, double eps, int norm_mode, int force_active);
+int k_y_stats(cudaStream_t st, const Dev& d, double* out_tr /*device, 1*/);
+int k_transpose(cudaStream_t st, const double* src, double* dst, int rows, int cols);  // src col-major rows x cols -> dst row-major
+int k_gram(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, const double* w, double* out);
+int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const double* w, double* out);   // weights squared (Q4)
+int k_trbq(cudaStream_t st, const Dev& d);                       // sc->trBQ = sum(BHat .* Q)
+int k_mean_sigma(cudaStream_t st, const Dev& d);                 // sc->meanSigmaVec = mean(sigmaVecHat)
+int k_total(cudaStream_t st, const double* x, int n, double* out);   // out[0] = sum(x), single CTA, fixed order
+int k_norms_init(cudaStream_t st, const Dev& d);                 // normBold = norm(BHat) from d.BtB
+int k_dense_sigmaA(cudaStream_t st, const Dev& d);               // SigmaA = sigma2*inv(B'B + L*SigmaB + sigma2*invCA)
+int k_dense_A_epilogue(cudaStream_t st, const Dev& d);           // A = (P*SigmaA)/sigma2, mask
+int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags);   // diagonal path incl. Q2 map; partial column sums of s
+int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags);   // batched H x H SPD inverse per column
+int k_mask(cudaStream_t st, const Dev& d);
+int k_update_CA(cudaStream_t st, const Dev& d);                  // sparse / dual element-wise ARD update (+ dual sums)
+int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S);   // fixed-order split-K reduction -> packed.Q
+int k_sigmaB(cudaStream_t st, const Dev& d, int flags);          // SigmaB (dense / sparse), also SigmaA <- packed.SA (sparse)
+int k_B_epilogue(cudaStream_t st, const Dev& d, int flags);      // BHat, Bold, D, partial tr(B.*Q)
+int k_sigma_rows(cudaStream_t st, const Dev& d);                 // diag_var: zetaVec, sigmaVecHat, mean
+int k_scale_B(cudaStream_t st, const Dev& d);                    // Bs = diag(sigmaVecHat) * BHat
+int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta);   // CA/CB/sigma/prior updates (+ delta, loop control)
+int k_updateCB_only(cudaStream_t st, const Dev& d);
+int k_dense_cov_only(cudaStream_t st, const Dev& d, int which);  // 0: CA/invCA  1: CB/invCB
+int k_sigma_only(cudaStream_t st, const Dev& d, int flags);
+int k_prior_only(cudaStream_t st, const Dev& d, int which);      // 0 alpha00, 1 alpha01, 2 beta00, 3 beta01
+int k_yhat(cudaStream_t st, const Dev& d, double* out, int ldo); // YHat = BHat * AHat'
+int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int phase);
+int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int rank, double noise, uint64_t seed);
+int k_randn(cudaStream_t st, double* x, size_t n, uint64_t seed, uint64_t stream);
+
+}  // namespace vb
