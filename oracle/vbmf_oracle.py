@@ -39,7 +39,36 @@ EPS0 = 4.9406564584124654e-324  # Julia eps(0.0), src/util.jl:120-122
 # ----------------------------------------------------------------------------- util.jl
 def norm2(x):
     """src/util.jl:8-19  sum of squares."""
+    if hasattr(x, "norm2"):          # ContractedY (below): sum(Y.^2) supplied by the caller
+        return float(x.norm2())
     return float(np.sum(np.asarray(x) ** 2))
+
+
+class ContractedY:
+    """Stand-in for Y at sizes where the CPU cannot form Y'*B and Y*A in reasonable time: the two contractions (and
+    sum(Y.^2)) are supplied as callables, every other line of the update loop still runs in this oracle.  Used by the
+    full-size GPU tests, where the contractions themselves are validated through size-independent properties."""
+
+    def __init__(self, shape, ytb, ya, trYTY):
+        self.shape = tuple(shape)
+        self._ytb, self._ya, self._tr = ytb, ya, float(trYTY)
+
+    class _T:
+        def __init__(self, outer):
+            self.o = outer
+
+        def __matmul__(self, B):
+            return np.asarray(self.o._ytb(np.asarray(B)))
+
+    @property
+    def T(self):
+        return ContractedY._T(self)
+
+    def __matmul__(self, A):
+        return np.asarray(self._ya(np.asarray(A)))
+
+    def norm2(self):
+        return self._tr
 
 
 def matnorm(X, mode="spectral"):

@@ -30,7 +30,9 @@ def ctx(G):
 
 # ------------------------------------------------------------------------------------------------ K1 / K2
 @pytest.mark.parametrize("L,M,H", [(10, 20, 2), (257, 1000, 64), (1000, 3001, 32), (130, 517, 128), (64, 300, 5),
-                                   (2048, 4096, 64), (33, 7, 16), (16, 16, 1)])
+                                   (2048, 4096, 64), (33, 7, 16), (16, 16, 1),
+                                   # persistent CTAs walking many tiles / split-K slabs (cross-proxy WAR regression)
+                                   (64, 200000, 64), (3000, 50000, 64), (1000, 100000, 32), (40000, 300, 64), (500, 30000, 128)])
 def test_contractions(G, ctx, L, M, H):
     rng = np.random.default_rng(L * 7 + M)
     Y = np.asfortranarray(rng.standard_normal((L, M)))

@@ -56,6 +56,15 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+// Hand a pipeline stage back to the TMA producer.  The stage was read through the generic proxy (LDS) and will be
+// overwritten through the async proxy (TMA): that write-after-read crosses proxies, so every reading lane issues
+// fence.proxy.async before the release.  Without it a persistent CTA sporadically reads rows of the *next* k-block
+// (observed on B200: a few rows per launch wrong once a CTA walks more than one tile; tools/k1race reproduces it).
+__device__ __forceinline__ void consumer_release(uint32_t empty_bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+}
 __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -149,8 +158,7 @@ gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 #pragma unroll
                     for (int b = 0; b < NT; ++b) dmma(acc[a][b], af[a], bf[b]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            consumer_release(empty0 + 8 * s, lane);
         }
         // epilogue: raw P tile, row-major [M][ldP]
         const int m0 = tile * BM + wm0;
@@ -256,8 +264,7 @@ gemm_ya_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
 #pragma unroll
                     for (int b = 0; b < NT; ++b) dmma(acc[a][b], af[a], bf[b]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            consumer_release(empty0 + 8 * s, lane);
         }
         // epilogue: undo the permutation, store the split-K slab column-major [H][ldQ]
         double* slab = Qpart + (size_t)kc * H * ldQ;
