@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- VB iterations/s of the dense `vbmf` update loop on synthetic low-rank-plus-noise Y (BASELINE.json configs[2]).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference --gpus 1 --steps K --warmup W      # CPU arm: the oracle restatement on the host cores
+
+One step = one VB iteration (updateA!, updateB!, updateCA!, updateCB!, updateSigma2!, delta; src/vbmf.jl:193-214) over the
+resident column shard of Y.  Y is column-sharded across ranks (fixed total problem => strong scaling); the per-iteration
+exchange is one packed NCCL all-reduce of [Y*AHat | AHat'AHat | ...].
+
+Timed region: W untimed warm-up iterations, then exactly K iterations between barrier + synchronize, CUDA events on the
+stream the kernels run on, max over ranks.  Y (32 GB at N=1) is far larger than L2, so no explicit L2 flush is needed.
+`value` has Y resident in HBM; `e2e` is the same metric through the public API (`vbmf_`) with every input in pinned HOST
+memory: upload of Y and of the parameter struct, K iterations, download of the results.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (L, M, H, kind, flags, description)
+    "c3": (20000, 200000, 64, "dense", ("est_covs", "est_var"),
+           "configs[2]: synthetic dense Y 20000x200000, rank-32 signal + 0.1 noise, vbmf H=64 with ARD (est_covs, est_var), Float64"),
+    "c4": (10000, 100000, 32, "sparse", ("est_cb",), "configs[3] (diagonal covariance path): vbmf_sparse 10000x100000 H=32"),
+    "c4full": (10000, 100000, 32, "sparse", ("est_cb", "full_cov"), "configs[3]: vbmf_sparse 10000x100000 H=32 full_cov (batched per-row Cholesky)"),
+}
+FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue-rate peak on this pool's B200 (profiles/r01_fp64_peak_microbench.jsonl)
+SEED = 20260101
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                try:
+                    power.append(float(f[2]))
+                except ValueError:
+                    pass
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:   # region shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.lines:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_reference(L, M, H, kind, flags, steps, warmup, budget_s):
+    """The oracle restatement timed on the host cores on a bounded column sample of the workload (same L and H,
+    M_s << M columns; one VB iteration is linear in M, so full-size iterations/s = sample iterations/s * M_s/M)."""
+    from oracle import vbmf_oracle as vo
+    cores = os.cpu_count() or 1
+    # size the sample from a measured GEMM rate so the whole run fits the budget
+    n = 1024
+    a = np.random.default_rng(0).standard_normal((n, n))
+    t = time.perf_counter(); a @ a; a @ a; rate = 4.0 * n ** 3 / (time.perf_counter() - t)
+    per_col = 4.0 * L * H * 1.15
+    Ms = int(budget_s * rate / (per_col * max(steps + warmup, 1)))
+    Ms = max(256, min(M // 10, (Ms // 256) * 256))
+    rng = np.random.default_rng(SEED)
+    r = H // 2
+    Y = rng.standard_normal((L, r)) @ rng.standard_normal((r, Ms)) + 0.1 * rng.standard_normal((L, Ms))
+    if kind == "dense":
+        p = vo.vbmf_init(Y, H, rng=np.random.default_rng(SEED + 1))
+        step = lambda: vo.vbmf_run(Y, p, 1, eps=0.0, est_covs="est_covs" in flags, est_var="est_var" in flags)
+    else:
+        p = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(SEED + 1))
+        step = lambda: vo.vbmf_sparse_run(Y, p, 1, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    sample_its = steps / dt
+    return {"value": sample_its * Ms / M, "unit": "iterations/s", "cores": cores, "kind": "port",
+            "sample": "oracle (NumPy/OpenBLAS restatement of src/vbmf*.jl) on L=%d x M_s=%d of the %d columns, H=%d, %d timed iterations: "
+                      "%.3f it/s on the sample, scaled by M_s/M (an iteration is linear in M)" % (L, Ms, M, H, steps, sample_its),
+            "sample_iterations_per_s": sample_its, "sample_ms_per_iteration": dt / steps * 1e3}
+
+
+def run_reference(args, L, M, H, kind, flags, desc):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cb = cpu_reference(L, M, H, kind, flags, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": "VB iterations/s at %dx%dx%d (dense vbmf, Float64)" % (L, M, H) if kind == "dense" else
+            "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, kind),
+            "value": cb["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": desc, "parallelism": "host cores only"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    L, M, H, kind, flags, desc = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference(args, L, M, H, kind, flags, desc)
+        return
+
+    import torch
+    import vbmf_b200_loader
+    vb = vbmf_b200_loader.load()          # fails loudly if libvbmf_b200.so is missing: no CPU fallback
+    lib = vb._lib.load()
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(vb.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    ctx = vb.Context(device=local_rank, rank=rank, world=world, nccl_id=nccl_id, stream=stream.cuda_stream)
+    off, Mloc = vb.shard_columns(M, world, rank)
+    ctx.synth(L, Mloc, M_global=M, col_offset=off, rank=H // 2, noise=0.1, seed=SEED)
+
+    class Shape:           # the init functions only read Y.shape
+        shape = (L, M)
+    rng = np.random.default_rng(SEED + 1)
+    if kind == "dense":
+        pg = vb.vbmf_init(Shape, H, rng=rng)
+        fl = (vb._lib.EST_COVS if "est_covs" in flags else 0) | (vb._lib.EST_VAR if "est_var" in flags else 0)
+    else:
+        pg = vb.vbmf_sparse_init(Shape, H, rng=rng, trYTY=ctx.trYTY())
+        fl = (vb._lib.EST_CB if "est_cb" in flags else 0) | (vb._lib.FULL_COV if "full_cov" in flags else 0)
+
+    def local_params():
+        p = vb.copy(pg)
+        p.M = Mloc
+        p.AHat = np.asfortranarray(pg.AHat[off:off + Mloc])
+        if kind != "dense":
+            p.MH = Mloc * H
+            sl = slice(off * H, (off + Mloc) * H)
+            for f in ("ATVecHat", "diagSigmaATVec", "CA", "beta"):
+                setattr(p, f, getattr(pg, f)[sl].copy())
+        return p
+
+    p = local_params()
+    solver = vb.Solver(ctx, p)
+    solver.upload(p)
+    it, d = solver.run(args.warmup, eps=0.0, flags=fl)
+    assert it == args.warmup, "warm-up ended early (it=%d, d=%r)" % (it, d)
+
+    # ---- timed region: exactly K iterations, Y resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    barrier()
+    ctx.profile(True)
+    n0 = lib.vbmf_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    it, d = solver.run(args.steps, eps=0.0, flags=fl)
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vbmf_b200_launch_count() - n0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop(t0, t1)
+    if it != args.steps or not np.isfinite(d):
+        raise SystemExit("timed region did not run %d iterations (it=%d, d=%r): result invalid" % (args.steps, it, d))
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the slower of the two contractions), CUDA events on the launching stream
+    k1 = prof["k1_ms"] / max(prof["k1_launches"], 1)
+    k2 = prof["k2_ms"] / max(prof["k2_launches"], 1)
+    flops_per_launch = 2.0 * L * Mloc * H
+    dom, dom_ms = ("K1 gemm_ytb (Y'*BHat)", k1) if k1 >= k2 else ("K2 gemm_ya (Y*AHat)", k2)
+    traffic = None
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(ncu_path):
+        try:
+            traffic = json.load(open(ncu_path)).get(args.workload, {}).get("K1" if k1 >= k2 else "K2", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    achieved = flops_per_launch / (dom_ms * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                "peak_source": "measured FP64 DMMA issue-rate microbenchmark on this pool's B200 (tools/microbench, profiles/"
+                               "r01_fp64_peak_microbench.jsonl); MEASURED_PEAKS.json carries no FP64 figure; cuBLAS DGEMM reaches 35.4",
+                "algorithmic_flops_per_launch": flops_per_launch,
+                "k1_ms": k1, "k2_ms": k2, "k1_tflops": flops_per_launch / k1 * 1e-9 if k1 else None,
+                "k2_tflops": flops_per_launch / k2 * 1e-9 if k2 else None,
+                "iteration_frac_of_peak": 4.0 * L * M * H / (ms / args.steps * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
+                "contraction_share_of_step": (k1 + k2) / (ms / args.steps)}
+
+    # ---- e2e: the public API with every input in pinned host memory (upload Y + params, K iterations, download)
+    e2e = None
+    if not args.no_e2e:
+        solver.close()
+        ybytes = L * Mloc * 8
+        ypin = torch.empty((Mloc, L), dtype=torch.float64, pin_memory=True)     # (M, L) C-order == L x M column-major
+        Yh = ypin.numpy().T
+        vb._lib.check(lib.vbmf_b200_download_Y(ctx.h, Yh.ctypes.data_as(vb._lib.p_f64), L))
+        p2 = local_params()
+        pin = {}
+        for f in ("AHat", "BHat"):        # the big parameter arrays come from pinned memory too
+            a = getattr(p2, f)
+            tpin = torch.empty(a.shape[::-1], dtype=torch.float64, pin_memory=True)
+            tpin.numpy().T[...] = a
+            setattr(p2, f, tpin.numpy().T)
+            pin[f] = tpin
+        barrier()
+        w0 = time.perf_counter()
+        ctx.attach(Yh, M_global=M, col_offset=off, force=True)
+        if kind == "dense":
+            vb.vbmf_(None, p2, args.steps, eps=0.0, est_covs="est_covs" in flags, est_var="est_var" in flags, ctx=ctx, yhat=False)
+            done = p2.iterations
+        else:
+            vb.vbmf_sparse_(None, p2, args.steps, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags, ctx=ctx, yhat=False)
+            done = p2.iterations
+        barrier()
+        w = time.perf_counter() - w0
+        tw = torch.tensor([w], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        w = float(tw.item())
+        state_bytes = (Mloc * H + L * H + 6 * H * H) * 8 if kind == "dense" else (5 * Mloc * H + L * H + 3 * L + 2 * H * H + 2 * H) * 8
+        out_bytes = state_bytes + (0 if kind != "dense" else 0)
+        e2e = {"value": done / w, "unit": "iterations/s", "h2d_bytes_per_step": (ybytes + state_bytes) / args.steps,
+               "d2h_bytes_per_step": out_bytes / args.steps, "seconds": w, "iterations": done,
+               "note": "one vbmf_ call per %d iterations: Y (%.1f GB) and the parameter struct uploaded from pinned host memory, results "
+                       "downloaded; YHat (L x M) not requested" % (args.steps, ybytes / 1e9)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cpu = cpu_reference(L, M, H, kind, flags, steps=3, warmup=1, budget_s=25.0)
+
+    line = {
+        "metric": "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, "dense vbmf" if kind == "dense" else "vbmf_" + kind),
+        "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "global_shape": [L, M, H], "columns_per_gpu": Mloc, "parallelism": "column-sharded Y, dp%d, one packed "
+                   "NCCL all-reduce per iteration" % world if world > 1 else "single GPU", "l2": "inputs larger than L2 (Y shard %.1f GB), no flush"
+                   % (L * Mloc * 8 / 1e9), "norm": "spectral", "eps": 0.0},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "final_delta": d,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

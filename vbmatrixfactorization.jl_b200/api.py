@@ -451,10 +451,10 @@ def _verb(verb, it, d):
 
 
 # ----------------------------------------------------------------------------------------------------------- drivers
-def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False, norm="spectral", ctx=None):
-    """`vbmf!` src/vbmf.jl:175-231: mutates params, returns params."""
+def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False, norm="spectral", ctx=None, yhat=True):
+    """`vbmf!` src/vbmf.jl:175-231: mutates params, returns params.  yhat=False skips the final L x M updateYHat!."""
     ctx = _ctx_for(Y, ctx)
-    st = _dense_struct(params, True)
+    st = _dense_struct(params, yhat)
     it, d = C.c_int64(), C.c_double()
     L_.check(ctx.lib.vbmf_b200_dense_run(ctx.h, C.byref(st), int(niter), float(eps), int(est_covs), int(est_var), _NORMS[norm],
                                          C.byref(it), C.byref(d)), allow=(-2,))
@@ -470,10 +470,10 @@ def vbmf(Y, params_in, niter, **kw):
 
 
 def vbmf_sparse_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_cb=True, norm="spectral",
-                 ctx=None, keep_blocks=False):
+                 ctx=None, keep_blocks=False, yhat=True):
     """`vbmf_sparse!` src/vbmf_sparse.jl:344-410: mutates params, returns d."""
     ctx = _ctx_for(Y, ctx)
-    st = _sparse_struct(params, True, keep_blocks)
+    st = _sparse_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
     L_.check(ctx.lib.vbmf_b200_sparse_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_cb),
                                           _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
@@ -492,10 +492,10 @@ def vbmf_sparse(Y, params_in, niter, **kw):
 
 
 def vbmf_dual_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_priors=True, est_cb=True,
-               norm="spectral", ctx=None, keep_blocks=False):
+               norm="spectral", ctx=None, keep_blocks=False, yhat=True):
     """`vbmf_dual!` src/vbmf_dual.jl:455-530: mutates params, returns d."""
     ctx = _ctx_for(Y, ctx)
-    st = _dual_struct(params, True, keep_blocks)
+    st = _dual_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
     L_.check(ctx.lib.vbmf_b200_dual_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
                                         int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))

@@ -284,6 +284,8 @@ struct vbmf_b200_solver {
     size_t arena_bytes = 0;
     double* Qpart = nullptr;
     int S = 1, kchunk = 16;
+    double* Ppart = nullptr;      // split-K slabs of K1 (nullptr when S1 == 1)
+    int S1 = 1, kbs1 = 1;
     int* d_labels = nullptr;
     CUtensorMap tmB, tmBs, tmA;
     bool k2_simt = false;
@@ -320,6 +322,8 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
     d.Y = c->Y; d.ldY = c->ldY; d.rowY2 = c->rowY2;
 
     plan_splitk(d.L, d.Mloc, d.H, c->num_sms, &s->S, &s->kchunk);
+    plan_splitk_ytb(d.L, d.Mloc, d.H, c->num_sms, &s->S1, &s->kbs1);
+    if (c->simt) s->S1 = 1;
     s->k2_simt = c->simt || (H % 2 != 0);       // the A tensor map needs a 16-byte row pitch
 
     const size_t MH = (size_t)std::max(d.Mloc, 1) * H, LH = (size_t)H * d.ldB, HH = (size_t)H * H, Lr = (size_t)d.L;
@@ -332,6 +336,7 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
         {&d.sigmaVec, Lr}, {&d.etaVec, Lr}, {&d.zetaVec, Lr}, {&d.part, part_elems}, {&d.lbacc, 32},
         {&s->Qpart, (size_t)s->S * LH},
     };
+    if (s->S1 > 1) items.push_back({&s->Ppart, (size_t)s->S1 * MH});
     if (kind == VBMF_B200_DENSE) { items.push_back({&d.CA, HH}); items.push_back({&d.CB, HH}); items.push_back({&d.invCA, HH}); items.push_back({&d.invCB, HH}); }
     else {
         items.push_back({&d.CAv, MH}); items.push_back({&d.beta, MH}); items.push_back({&d.sdiag, MH});
@@ -582,7 +587,12 @@ static int enq_k1(vbmf_b200_solver* s, bool scaledB) {
     prof_mark(c, c->ev_k1);
     int rc;
     if (c->simt) rc = launch_gemm_ytb_simt(c->st, d.Y, d.ldY, scaledB ? d.Bs : d.B, d.ldB, d.P, d.Mloc, d.L, d.H, d.H, d.sc);
-    else rc = launch_gemm_ytb(c->st, &c->tmY1, scaledB ? &s->tmBs : &s->tmB, d.P, d.Mloc, d.L, d.H, d.H, d.sc, c->num_sms);
+    else {
+        const size_t MH = (size_t)d.Mloc * d.H;
+        rc = launch_gemm_ytb(c->st, &c->tmY1, scaledB ? &s->tmBs : &s->tmB, s->S1 > 1 ? s->Ppart : d.P, d.Mloc, d.L, d.H, d.H,
+                             s->S1, s->kbs1, MH, d.sc, c->num_sms);
+        if (!rc && s->S1 > 1) rc = k_sum_slabs(c->st, s->Ppart, s->S1, MH, d.P, d.sc);
+    }
     prof_mark(c, c->ev_k1);
     return rc;
 }
@@ -813,7 +823,13 @@ extern "C" int vbmf_b200_gemm_YtB(vbmf_b200_ctx* c, const double* B, int64_t H, 
     else {
         CUtensorMap tmB;
         rc = make_tmap_2d(&tmB, dB, (uint64_t)c->L, (uint64_t)H, (uint64_t)ldB * 8, 16, (uint32_t)gemm_geometry((int)H).bn);
-        if (!rc) rc = launch_gemm_ytb(c->st, &c->tmY1, &tmB, dP, c->Mloc, c->L, (int)H, (int)H, nullptr, c->num_sms);
+        int S1 = 1, kbs1 = 1;
+        plan_splitk_ytb(c->L, c->Mloc, (int)H, c->num_sms, &S1, &kbs1);
+        double* dPp = nullptr;
+        if (S1 > 1 && cudaMalloc(&dPp, (size_t)S1 * MH * 8) != cudaSuccess) { set_error("cudaMalloc failed"); rc = -1; }
+        if (!rc) rc = launch_gemm_ytb(c->st, &c->tmY1, &tmB, S1 > 1 ? dPp : dP, c->Mloc, c->L, (int)H, (int)H, S1, kbs1, MH, nullptr, c->num_sms);
+        if (!rc && S1 > 1) rc = k_sum_slabs(c->st, dPp, S1, MH, dP, nullptr);
+        if (dPp) { cudaStreamSynchronize(c->st); cudaFree(dPp); }
     }
     if (!rc) rc = k_transpose(c->st, dP, dT, (int)H, c->Mloc);
     if (!rc && c->Mloc > 0 && cudaMemcpyAsync(P, dT, (size_t)c->Mloc * H * 8, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) { set_error("copy failed"); rc = -1; }

@@ -18,8 +18,11 @@ GemmGeometry gemm_geometry(int H);
 // K1: P[m][h] = sum_l Y[l, m] * B[l, h]      (Y' * BHat, src/vbmf.jl:98, src/vbmf_sparse.jl:195,232)
 // tmY : dims {L, M}, box {16, 128};  tmB : dims {L, H} (column h contiguous in l), box {16, bn}
 // P is row-major [M][ldP].
+// With S > 1 the kernel writes S slabs P + s*slab_stride (split over L, kb_per_split 16-row blocks each) that the caller
+// sums in fixed order (deterministic split-K); S == 1 writes P directly.
 int launch_gemm_ytb(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* tmB, double* P,
-                    int M, int L, int H, int ldP, const Scalars* sc, int num_sms);
+                    int M, int L, int H, int ldP, int S, int kb_per_split, size_t slab_stride, const Scalars* sc, int num_sms);
+void plan_splitk_ytb(int L, int M, int H, int num_sms, int* S, int* kb_per_split);
 
 // K2: Qpart[s][h][l] = sum_{m in chunk s} Y[l, m] * A[m][h]   (Y * AHat, src/vbmf.jl:112, src/vbmf_sparse.jl:266)
 // tmY : dims {L, M}, box {16, 16};  tmA : dims {H, M} (row m contiguous in h), box {16, 16}

@@ -89,7 +89,8 @@ template <int BN> struct Sizes {
 template <int BN>
 __global__ void __launch_bounds__((Cfg<BN>::WM * Cfg<BN>::WN + 1) * 32, Cfg<BN>::CPS)
 gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB,
-                double* __restrict__ P, int M, int L, int H, int ldP, const Scalars* __restrict__ sc) {
+                double* __restrict__ P, int M, int L, int H, int ldP, int S, int kb_per_split, size_t slab_stride,
+                const Scalars* __restrict__ sc) {
     if (sc != nullptr && !sc->active) return;
     constexpr int WM = Cfg<BN>::WM, WN = Cfg<BN>::WN, STAGES = Cfg<BN>::STAGES;
     constexpr int NCW = WM * WN;
@@ -108,15 +109,18 @@ gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
     __syncthreads();
 
-    const int ntiles = (M + BM - 1) / BM;
+    // work item w = (m-tile, k-split): split-K over L evens out the tile count over the SMs (196 tiles on 148 SMs at
+    // 25000 columns per GPU would otherwise cost two full rounds); the S slabs are summed in fixed order afterwards.
+    const int nwork = ((M + BM - 1) / BM) * S;
     const int nkb = (L + BK - 1) / BK;
 
     if (warp == NCW) {  // ---------------- producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m0 = tile * BM;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int m0 = (w / S) * BM, ks = w % S;
+                const int kb0 = ks * kb_per_split, kb1 = min(nkb, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     mbar_expect_tx(full0 + 8 * s, SB);
@@ -135,14 +139,16 @@ gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     for (int sp = 0; sp < 4; ++sp) off[sp] = r * 128 + (((sp + 4 * (j >> 1)) ^ r) << 4) + ((j & 1) << 3);
 
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int tile = w / S, ks = w % S;
+        const int kb0 = ks * kb_per_split, kb1 = min(nkb, kb0 + kb_per_split);
         double acc[MT][NT][2];
 #pragma unroll
         for (int a = 0; a < MT; ++a)
 #pragma unroll
             for (int b = 0; b < NT; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full0 + 8 * s, ph);
             const uint32_t ys = base + s * SB + wm0 * 128, bs = base + s * SB + YB + wn0 * 128;
@@ -169,7 +175,7 @@ gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 #pragma unroll
                 for (int b = 0; b < NT; ++b) {
                     const int h = wn0 + b * 8 + 2 * j;
-                    double* p = P + (size_t)m * ldP + h;
+                    double* p = P + (size_t)ks * slab_stride + (size_t)m * ldP + h;
                     if (h < H) p[0] = acc[a][b][0];
                     if (h + 1 < H) p[1] = acc[a][b][1];
                 }
@@ -355,29 +361,50 @@ void plan_splitk(int L, int M, int H, int num_sms, int* S_out, int* kchunk_out) 
     *kchunk_out = (int)kc;
 }
 
+void plan_splitk_ytb(int L, int M, int H, int num_sms, int* S_out, int* kb_per_split) {
+    const GemmGeometry g = gemm_geometry(H);
+    const long cap = (long)num_sms * g.ctas_per_sm;
+    const long ntiles = (M + BM - 1) / BM, nkb = (L + BK - 1) / BK;
+    int best_s = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 16; ++s) {
+        const long kbs = (nkb + s - 1) / s;
+        if (kbs < 48 && s > 1) break;                      // keep >= 48 k-blocks per item (pipeline fill/drain, epilogue)
+        const long s_eff = (nkb + kbs - 1) / kbs;
+        const long work = ntiles * s_eff;
+        // slab traffic (write + read of s partial outputs) relative to the Y bytes of the launch
+        const double extra = s_eff > 1 ? 2.0 * s_eff * H / (double)L : 0.0;
+        const double eff = (double)work / (double)(((work + cap - 1) / cap) * cap) / (1.0 + extra);
+        if (eff > best_eff + 0.005) { best_eff = eff; best_s = (int)s_eff; }
+    }
+    const long kbs = (nkb + best_s - 1) / best_s;
+    *S_out = (int)std::max<long>(1, (nkb + kbs - 1) / std::max<long>(kbs, 1));
+    *kb_per_split = (int)std::max<long>(kbs, 1);
+}
+
 template <int BN>
 static int launch_ytb_t(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* tmB, double* P, int M, int L, int H,
-                        int ldP, const Scalars* sc, int num_sms) {
+                        int ldP, int S, int kbs, size_t slab_stride, const Scalars* sc, int num_sms) {
     static bool attr_set = false;
     if (!attr_set) {
         VB_CUDA_OK(cudaFuncSetAttribute(gemm_ytb_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<BN>::SMEM));
         attr_set = true;
     }
-    const int ntiles = (M + BM - 1) / BM;
-    const int grid = std::max(1, std::min(ntiles, num_sms * Cfg<BN>::CPS));
+    const int nwork = ((M + BM - 1) / BM) * S;
+    const int grid = std::max(1, std::min(nwork, num_sms * Cfg<BN>::CPS));
     const int threads = (Cfg<BN>::WM * Cfg<BN>::WN + 1) * 32;
-    gemm_ytb_kernel<BN><<<grid, threads, Sizes<BN>::SMEM, st>>>(*tmY, *tmB, P, M, L, H, ldP, sc);
+    gemm_ytb_kernel<BN><<<grid, threads, Sizes<BN>::SMEM, st>>>(*tmY, *tmB, P, M, L, H, ldP, S, kbs, slab_stride, sc);
     VB_LAUNCH_OK();
     return 0;
 }
 
 int launch_gemm_ytb(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* tmB, double* P, int M, int L, int H,
-                    int ldP, const Scalars* sc, int num_sms) {
+                    int ldP, int S, int kb_per_split, size_t slab_stride, const Scalars* sc, int num_sms) {
     if (H > 128) { set_error("H = %d > 128 is not supported by the K1 kernel yet", H); return -1; }
     if (M <= 0 || L <= 0 || H <= 0) return 0;
-    if (H <= 32) return launch_ytb_t<32>(st, tmY, tmB, P, M, L, H, ldP, sc, num_sms);
-    if (H <= 64) return launch_ytb_t<64>(st, tmY, tmB, P, M, L, H, ldP, sc, num_sms);
-    return launch_ytb_t<128>(st, tmY, tmB, P, M, L, H, ldP, sc, num_sms);
+    if (H <= 32) return launch_ytb_t<32>(st, tmY, tmB, P, M, L, H, ldP, S, kb_per_split, slab_stride, sc, num_sms);
+    if (H <= 64) return launch_ytb_t<64>(st, tmY, tmB, P, M, L, H, ldP, S, kb_per_split, slab_stride, sc, num_sms);
+    return launch_ytb_t<128>(st, tmY, tmB, P, M, L, H, ldP, S, kb_per_split, slab_stride, sc, num_sms);
 }
 
 template <int BN>

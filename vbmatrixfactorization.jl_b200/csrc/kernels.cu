@@ -503,6 +503,9 @@ int k_update_CA(cudaStream_t st, const Dev& d) {
     return 0;
 }
 
+int k_sum_slabs(cudaStream_t st, const double* slabs, int S, size_t n, double* out, const Scalars* sc) {
+    return sum_partials(st, slabs, S, n, n, out, sc);
+}
 // fixed-order reduction of the split-K slabs of K2 into the all-reduce payload
 int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
     const size_t n = (size_t)d.H * d.ldB;
@@ -811,7 +814,6 @@ __global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
 
     if (what & (POST_DELTA | POST_NORM_INIT)) {
         // delta(new, old) = norm(old - new)/norm(old), src/util.jl:27-29; Julia 0.5 norm(::Matrix) = sigma_max (Q1)
-        const int n = (H + 1) & ~1;
         for (int pass = (what & POST_DELTA) ? 0 : 1; pass < 2; ++pass) {
             const double* Gm = pass == 0 ? d.DtD : d.BtB;
             double val;
@@ -824,12 +826,12 @@ __global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
                 val = s_val[pass];
             } else {
                 __syncthreads();
-                for (int e = t; e < n * n; e += blockDim.x) {
-                    const int i = e / n, j = e - i * n;
-                    Mx[i * ld + j] = (i < H && j < H) ? 0.5 * (Gm[i * H + j] + Gm[j * H + i]) : 0.0;
+                for (int e = t; e < H * H; e += blockDim.x) {
+                    const int i = e / H, j = e - i * H;
+                    Mx[i * ld + j] = 0.5 * (Gm[i * H + j] + Gm[j * H + i]);
                 }
                 __syncthreads();
-                val = jacobi_lambda_max(Mx, ld, n, vec, red);
+                val = sym_lambda_max(Mx, ld, H, vec);
             }
             if (t == 0) s_val[pass] = sqrt(fmax(val, 0.0)) + (val != val ? val : 0.0);
             __syncthreads();

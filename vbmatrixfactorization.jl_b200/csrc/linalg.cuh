@@ -90,78 +90,111 @@ __device__ bool spd_inverse(const G& g, double* A, int ld, int H, double* vec) {
     return ok;
 }
 
-// Largest eigenvalue of the symmetric matrix A (n x n, n even, row stride ld, shared memory; destroyed).
-// rot = 4*(n/2) doubles of scratch, red = 32 doubles.  Whole CTA cooperates.  Result valid in every thread.
-__device__ inline double jacobi_lambda_max(double* A, int ld, int n, double* rot, double* red) {
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int half = n / 2;
-    __shared__ double s_off, s_diag;
-    if (n == 0) return 0.0;
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int e = t; e < n * n; e += nt) {
-            const int i = e / n, j = e - i * n;
-            const double v = A[i * ld + j];
-            if (i == j) dg += v * v; else off += v * v;
-        }
-        off = block_sum(off, red);
-        if (t == 0) s_off = off;
-        dg = block_sum(dg, red);
-        if (t == 0) s_diag = dg;
-        __syncthreads();
-        if (!(s_off > 1e-32 * s_diag)) break;      // also leaves on NaN
-        for (int round = 0; round < n - 1; ++round) {
-            if (t < half) {
-                int p, q;
-                if (t == 0) { p = n - 1; q = round; }
-                else { p = (round + t) % (n - 1); q = (round - t + (n - 1)) % (n - 1); }
-                const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
-                double c = 1.0, s = 0.0;
-                if (apq != 0.0) {
-                    const double tau = (aqq - app) / (2.0 * apq);
-                    const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    c = 1.0 / sqrt(1.0 + tt * tt);
-                    s = tt * c;
-                    if (!isfinite(tau)) { c = 1.0; s = 0.0; }
+// Largest eigenvalue of the symmetric matrix A (n x n, full storage, row stride ld, shared memory; destroyed) by
+// Householder tridiagonalisation followed by parallel multisection on the Sturm sequence: orthogonal similarity +
+// bisection, so lambda_max carries an absolute error of a few ulp of ||A|| (what LAPACK's SVD gives the reference for
+// norm(::Matrix)).  work = 4*n doubles.  Whole CTA (blockDim.x >= 64, multiple of 32); result valid in every thread.
+__device__ inline double sym_lambda_max(double* A, int ld, int n, double* work) {
+    const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5;
+    double* dv = work;            // diagonal of T
+    double* ev = work + n;        // sub-diagonal of T (ev[k] couples k and k+1)
+    double* v = work + 2 * n;     // Householder vector
+    double* p = work + 3 * n;     // p / q vector
+    __shared__ double s_sc[4];    // beta, alpha, K, flag
+    __shared__ double s_lo, s_hi;
+    __shared__ int s_first;
+    if (n <= 0) return 0.0;
+    // NaN / Inf anywhere -> NaN (the reference's norm would propagate it)
+    int bad = 0;
+    for (int e = t; e < n * n; e += nt) { const double x = A[(e / n) * ld + (e % n)]; if (!(fabs(x) <= 1.79e308)) bad = 1; }
+    if (__syncthreads_or(bad)) return nan("");
+    if (n == 1) return A[0];
+    for (int k = 0; k < n - 2; ++k) {
+        const int m = n - k - 1;                  // trailing block is rows/cols k+1 .. n-1
+        double* Asub = A + (k + 1) * ld + (k + 1);
+        if (warp == 0) {                          // x = A[k+1:, k] ; v = x - alpha*e1 ; beta = 2/(v'v)
+            double s = 0.0;
+            for (int i = lane; i < m; i += 32) { const double x = A[(k + 1 + i) * ld + k]; v[i] = x; s = fma(x, x, s); }
+            s = warp_sum(s);
+            __syncwarp();
+            const double x0 = v[0];
+            const double tail = s - x0 * x0;      // sum of squares below the first entry
+            if (lane == 0) {
+                if (!(tail > 0.0)) { s_sc[0] = 0.0; s_sc[1] = x0; }          // already tridiagonal in this column
+                else {
+                    const double alpha = (x0 >= 0.0) ? -sqrt(s) : sqrt(s);
+                    const double v0 = x0 - alpha;
+                    v[0] = v0;
+                    s_sc[0] = 2.0 / (tail + v0 * v0);
+                    s_sc[1] = alpha;
                 }
-                rot[4 * t] = c; rot[4 * t + 1] = s; rot[4 * t + 2] = (double)p; rot[4 * t + 3] = (double)q;
             }
-            __syncthreads();
-            for (int e = t; e < half * n; e += nt) {     // columns p, q of every row
-                const int i = e / n, r = e - i * n;
-                const double c = rot[4 * i], s = rot[4 * i + 1];
-                const int p = (int)rot[4 * i + 2], q = (int)rot[4 * i + 3];
-                const double arp = A[r * ld + p], arq = A[r * ld + q];
-                A[r * ld + p] = c * arp - s * arq;
-                A[r * ld + q] = s * arp + c * arq;
-            }
-            __syncthreads();
-            for (int e = t; e < half * n; e += nt) {     // rows p, q of every column
-                const int i = e / n, r = e - i * n;
-                const double c = rot[4 * i], s = rot[4 * i + 1];
-                const int p = (int)rot[4 * i + 2], q = (int)rot[4 * i + 3];
-                const double apr = A[p * ld + r], aqr = A[q * ld + r];
-                A[p * ld + r] = c * apr - s * aqr;
-                A[q * ld + r] = s * apr + c * aqr;
-            }
-            __syncthreads();
         }
+        __syncthreads();
+        const double beta = s_sc[0];
+        if (beta != 0.0) {
+            if (t < m) {                          // p = beta * Asub * v   (column access: A is symmetric)
+                double s = 0.0;
+                for (int j = 0; j < m; ++j) s = fma(Asub[j * ld + t], v[j], s);
+                p[t] = beta * s;
+            }
+            __syncthreads();
+            if (warp == 0) {                      // K = beta/2 * p'v ; q = p - K v
+                double s = 0.0;
+                for (int i = lane; i < m; i += 32) s = fma(p[i], v[i], s);
+                s = warp_sum(s);
+                const double K = 0.5 * beta * s;
+                for (int i = lane; i < m; i += 32) p[i] -= K * v[i];
+            }
+            __syncthreads();
+            for (int e = t; e < m * m; e += nt) { // Asub -= v q' + q v'
+                const int i = e / m, j = e - i * m;
+                Asub[i * ld + j] -= v[i] * p[j] + p[i] * v[j];
+            }
+        }
+        if (t == 0) { dv[k] = A[k * ld + k]; ev[k] = s_sc[1]; }
+        __syncthreads();
     }
-    double mx = -1e308;
-    for (int i = t; i < n; i += nt) mx = fmax(mx, A[i * ld + i]);
-    // NaN-propagating max reduce
-    bool bad = false;
-    for (int i = t; i < n; i += nt) if (A[i * ld + i] != A[i * ld + i]) bad = true;
+    if (t == 0) {
+        dv[n - 2] = A[(n - 2) * ld + (n - 2)];
+        dv[n - 1] = A[(n - 1) * ld + (n - 1)];
+        ev[n - 2] = A[(n - 1) * ld + (n - 2)];
+        double lo = 1e308, hi = -1e308;           // Gershgorin interval
+        for (int i = 0; i < n; ++i) {
+            const double r = (i > 0 ? fabs(ev[i - 1]) : 0.0) + (i < n - 1 ? fabs(ev[i]) : 0.0);
+            lo = fmin(lo, dv[i] - r); hi = fmax(hi, dv[i] + r);
+        }
+        const double pad = 4e-16 * fmax(fabs(lo), fabs(hi)) + 1e-300;
+        s_lo = lo - pad; s_hi = hi + pad;
+    }
     __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
-    if ((t & 31) == 0) red[t >> 5] = mx;
-    __syncthreads();
-    double r = -1e308;
-    for (int w = 0; w < (nt + 31) / 32; ++w) r = fmax(r, red[w]);
-    __syncthreads();
-    return any_bad ? nan("") : r;
+    // multisection: count(x) = #eigenvalues < x ; lambda_max is where count steps from n-1 to n
+    const double tiny = 1e-300;
+    for (int iter = 0; iter < 16; ++iter) {
+        const double lo = s_lo, hi = s_hi;
+        if (!(hi - lo > 4.5e-16 * fmax(fabs(lo), fabs(hi)))) break;
+        const double x = lo + (hi - lo) * ((double)(t + 1) / (double)(nt + 1));
+        double q = dv[0] - x;
+        int cnt = q < 0.0;
+        for (int i = 1; i < n; ++i) {
+            if (q == 0.0) q = tiny;
+            q = dv[i] - x - ev[i - 1] * ev[i - 1] / q;
+            cnt += q < 0.0;
+        }
+        if (t == 0) s_first = nt;
+        __syncthreads();
+        if (cnt == n) atomicMin(&s_first, t);     // smallest sample point that lies above every eigenvalue
+        __syncthreads();
+        const int f = s_first;
+        __syncthreads();
+        if (t == 0) {
+            const double w = (hi - lo) / (double)(nt + 1);
+            s_hi = (f < nt) ? lo + w * (double)(f + 1) : hi;
+            s_lo = (f > 0) ? lo + w * (double)f : lo;
+        }
+        __syncthreads();
+    }
+    return 0.5 * (s_lo + s_hi);
 }
 
 }  // namespace vb
