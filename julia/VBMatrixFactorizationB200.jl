@@ -1,0 +1,200 @@
+# VBMatrixFactorizationB200.jl -- thin `ccall` shim that routes VBMatrixFactorization.jl's VB update loop to libvbmf_b200.so.
+#
+# Drop-in for the hot path only: `vbmf!`, `vbmf_sparse!`, `vbmf_dual!` (and the non-mutating `vbmf`, `vbmf_sparse`, `vbmf_dual`),
+# `lowerBound`, `lowerBoundTrimmed` keep their reference signatures (src/vbmf.jl:175,238; src/vbmf_sparse.jl:344,418,435,478;
+# src/vbmf_dual.jl:455,538,556,606).  Everything else (init = Julia RNG, preprocessing, logging, MIL scripts) stays in the
+# reference package.  Written in the reference's dialect (Julia 0.5: `type`, `immutable`, `Ptr{Void}`); on Julia >= 1.0
+# replace `immutable` by `struct`, `Void` by `Cvoid`.  NOT EXECUTED in the build container (no Julia toolchain there): the same
+# ABI is exercised by the ctypes binding (vbmatrixfactorization.jl_b200/_lib.py) in tests/.
+#
+# Usage:  include("VBMatrixFactorizationB200.jl"); using VBMatrixFactorizationB200
+#         ctx = b200_context()                          # one GPU; Y is uploaded once per distinct matrix
+#         vbmf!(ctx, Y, params, 100, est_covs = true, est_var = true)
+module VBMatrixFactorizationB200
+
+using VBMatrixFactorization
+import VBMatrixFactorization: vbmf_parameters, vbmf_sparse_parameters, vbmf_dual_parameters
+
+export b200_context, b200_close, vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, lowerBound, lowerBoundTrimmed
+
+const LIB = get(ENV, "VBMF_B200_LIB", "libvbmf_b200.so")
+
+# ---- mirrors of the C structs in include/vbmf_b200.h (all fields 8 bytes, same order) -------------------------------------
+immutable DenseState        # vbmf_b200_dense_state  <->  vbmf_parameters (src/vbmf.jl:22-40)
+    L::Int64; M::Int64; H::Int64; H1::Int64
+    n_labels::Int64; labels::Ptr{Int64}
+    AHat::Ptr{Float64}; BHat::Ptr{Float64}; SigmaA::Ptr{Float64}; SigmaB::Ptr{Float64}
+    CA::Ptr{Float64}; CB::Ptr{Float64}; invCA::Ptr{Float64}; invCB::Ptr{Float64}
+    sigma2::Float64
+    YHat::Ptr{Float64}
+end
+
+immutable SparseState       # vbmf_b200_sparse_state <->  vbmf_sparse_parameters (src/vbmf_sparse.jl:47-90)
+    L::Int64; M::Int64; H::Int64; MH::Int64; H1::Int64
+    n_labels::Int64; labels::Ptr{Int64}
+    AHat::Ptr{Float64}; ATVecHat::Ptr{Float64}; SigmaATVec_blocks::Ptr{Float64}; diagSigmaATVec::Ptr{Float64}
+    SigmaA::Ptr{Float64}; BHat::Ptr{Float64}; SigmaB::Ptr{Float64}; CA::Ptr{Float64}
+    alpha0::Float64; beta0::Float64; alpha::Float64; beta::Ptr{Float64}
+    CB::Ptr{Float64}; gamma0::Float64; delta0::Float64; gamma::Float64; delta::Ptr{Float64}
+    sigmaHat::Float64; eta0::Float64; zeta0::Float64; eta::Float64; zeta::Float64
+    sigmaVecHat::Ptr{Float64}; etaVec::Ptr{Float64}; zetaVec::Ptr{Float64}
+    YHat::Ptr{Float64}; trYTY::Float64
+end
+
+immutable DualState         # vbmf_b200_dual_state   <->  vbmf_dual_parameters (src/vbmf_dual.jl:59-112)
+    L::Int64; M::Int64; MH::Int64; H::Int64; H0::Int64; H1::Int64
+    AHat::Ptr{Float64}; ATVecHat::Ptr{Float64}; SigmaATVec_blocks::Ptr{Float64}; diagSigmaATVec::Ptr{Float64}
+    SigmaA::Ptr{Float64}; A0Hat::Ptr{Float64}; A1Hat::Ptr{Float64}; BHat::Ptr{Float64}; SigmaB::Ptr{Float64}
+    CA::Ptr{Float64}; alpha::Ptr{Float64}; beta::Ptr{Float64}; CA0::Ptr{Float64}
+    alpha00::Float64; beta00::Float64; alpha0::Float64; beta0::Ptr{Float64}; CA1::Ptr{Float64}
+    alpha01::Float64; beta01::Float64; alpha1::Float64; beta1::Ptr{Float64}; CB::Ptr{Float64}
+    gamma0::Float64; delta0::Float64; gamma::Float64; delta::Ptr{Float64}
+    sigmaHat::Float64; eta0::Float64; zeta0::Float64; eta::Float64; zeta::Float64
+    sigmaVecHat::Ptr{Float64}; etaVec::Ptr{Float64}; zetaVec::Ptr{Float64}
+    YHat::Ptr{Float64}; trYTY::Float64
+end
+
+type B200Context
+    handle::Ptr{Void}
+    Yid::UInt            # object id of the matrix currently resident on the device
+end
+
+check(rc) = rc == 0 || rc == -2 || error(unsafe_string(ccall((:vbmf_b200_last_error, LIB), Cstring, ())))
+
+function b200_context(device::Int = 0)
+    h = Ref{Ptr{Void}}(C_NULL)
+    check(ccall((:vbmf_b200_ctx_create, LIB), Cint, (Cint, Cint, Cint, Ptr{Void}, Ptr{Void}, Ptr{Ptr{Void}}),
+                device, 0, 1, C_NULL, C_NULL, h))
+    return B200Context(h[], UInt(0))
+end
+b200_close(ctx::B200Context) = ccall((:vbmf_b200_ctx_destroy, LIB), Cint, (Ptr{Void},), ctx.handle)
+
+# Y is the expensive upload: cached on object identity; call attach!(ctx, Y, force = true) after mutating Y in place
+function attach!(ctx::B200Context, Y::Array{Float64,2}; force = false)
+    if force || ctx.Yid != object_id(Y)
+        L, M = size(Y)
+        check(ccall((:vbmf_b200_attach_Y, LIB), Cint, (Ptr{Void}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64),
+                    ctx.handle, Y, L, M, L, M, 0))
+        ctx.Yid = object_id(Y)
+    end
+end
+
+const NORM = Dict(:spectral => 0, :frobenius => 1)   # :spectral = Julia 0.5 norm(::Matrix), what src/util.jl:28 computes
+
+# ---- vbmf! (src/vbmf.jl:175) ----------------------------------------------------------------------------------------------
+function vbmf!(ctx::B200Context, Y::Array{Float64,2}, p::vbmf_parameters, niter::Int; eps::Float64 = 1e-6,
+               est_covs::Bool = false, est_var::Bool = false, verb = false, norm = :spectral)
+    attach!(ctx, Y)
+    p.YHat = Array{Float64}(p.L, p.M)
+    st = Ref(DenseState(p.L, p.M, p.H, p.H1, length(p.labels), pointer(p.labels), pointer(p.AHat), pointer(p.BHat),
+                        pointer(p.SigmaA), pointer(p.SigmaB), pointer(p.CA), pointer(p.CB), pointer(p.invCA), pointer(p.invCB),
+                        p.sigma2, pointer(p.YHat)))
+    iters = Ref{Int64}(0); d = Ref{Float64}(0.0)
+    check(ccall((:vbmf_b200_dense_run, LIB), Cint,
+                (Ptr{Void}, Ref{DenseState}, Int64, Float64, Cint, Cint, Cint, Ref{Int64}, Ref{Float64}),
+                ctx.handle, st, niter, eps, est_covs, est_var, NORM[norm], iters, d))
+    p.sigma2 = st[].sigma2
+    verb && print("Factorization finished after ", iters[], " iterations, eps = ", d[], "\n")
+    return p
+end
+vbmf(ctx::B200Context, Y, p_in::vbmf_parameters, niter::Int; kw...) = vbmf!(ctx, Y, deepcopy(p_in), niter; kw...)
+
+# ---- vbmf_sparse! (src/vbmf_sparse.jl:344) ----------------------------------------------------------------------------------
+function sparse_state(p::vbmf_sparse_parameters, blocks::Ptr{Float64})
+    SparseState(p.L, p.M, p.H, p.MH, p.H1, length(p.labels), pointer(p.labels), pointer(p.AHat), pointer(p.ATVecHat), blocks,
+                pointer(p.diagSigmaATVec), pointer(p.SigmaA), pointer(p.BHat), pointer(p.SigmaB), pointer(p.CA),
+                p.alpha0, p.beta0, p.alpha, pointer(p.beta), pointer(p.CB), p.gamma0, p.delta0, p.gamma, pointer(p.delta),
+                p.sigmaHat, p.eta0, p.zeta0, p.eta, p.zeta, pointer(p.sigmaVecHat), pointer(p.etaVec), pointer(p.zetaVec),
+                pointer(p.YHat), p.trYTY)
+end
+function vbmf_sparse!(ctx::B200Context, Y::Array{Float64,2}, p::vbmf_sparse_parameters, niter::Int; eps::Float64 = 1e-6,
+                      diag_var::Bool = false, full_cov::Bool = false, verb = false, est_cb::Bool = true, norm = :spectral)
+    attach!(ctx, Y)
+    p.YHat = Array{Float64}(p.L, p.M)
+    # the (MH)x(MH) SigmaATVec / invSigmaATVec of the reference are never materialised; ask for the M diagonal blocks with
+    # blocks = Array{Float64}(p.H, p.H, p.M) and pass pointer(blocks) instead of C_NULL when they are needed.
+    st = Ref(sparse_state(p, convert(Ptr{Float64}, C_NULL)))
+    iters = Ref{Int64}(0); d = Ref{Float64}(0.0)
+    check(ccall((:vbmf_b200_sparse_run, LIB), Cint,
+                (Ptr{Void}, Ref{SparseState}, Int64, Float64, Cint, Cint, Cint, Cint, Ref{Int64}, Ref{Float64}),
+                ctx.handle, st, niter, eps, diag_var, full_cov, est_cb, NORM[norm], iters, d))
+    p.sigmaHat = st[].sigmaHat; p.zeta = st[].zeta
+    verb && print("Factorization finished after ", iters[], " iterations, eps = ", d[], "\n")
+    return d[]
+end
+function vbmf_sparse(ctx::B200Context, Y, p_in::vbmf_sparse_parameters, niter::Int; kw...)
+    p = deepcopy(p_in)
+    d = vbmf_sparse!(ctx, Y, p, niter; kw...)
+    return p, d
+end
+
+# ---- vbmf_dual! (src/vbmf_dual.jl:455) ----------------------------------------------------------------------------------------
+function dual_state(p::vbmf_dual_parameters)
+    DualState(p.L, p.M, p.MH, p.H, p.H0, p.H1, pointer(p.AHat), pointer(p.ATVecHat), convert(Ptr{Float64}, C_NULL),
+              pointer(p.diagSigmaATVec), pointer(p.SigmaA), pointer(p.A0Hat), pointer(p.A1Hat), pointer(p.BHat), pointer(p.SigmaB),
+              pointer(p.CA), pointer(p.alpha), pointer(p.beta), pointer(p.CA0), p.alpha00, p.beta00, p.alpha0, pointer(p.beta0),
+              pointer(p.CA1), p.alpha01, p.beta01, p.alpha1, pointer(p.beta1), pointer(p.CB), p.gamma0, p.delta0, p.gamma,
+              pointer(p.delta), p.sigmaHat, p.eta0, p.zeta0, p.eta, p.zeta, pointer(p.sigmaVecHat), pointer(p.etaVec),
+              pointer(p.zetaVec), pointer(p.YHat), p.trYTY)
+end
+function vbmf_dual!(ctx::B200Context, Y::Array{Float64,2}, p::vbmf_dual_parameters, niter::Int; eps::Float64 = 1e-6,
+                    diag_var::Bool = false, full_cov::Bool = false, verb = false, est_priors = true, est_cb::Bool = true,
+                    norm = :spectral)
+    attach!(ctx, Y)
+    p.YHat = Array{Float64}(p.L, p.M)
+    st = Ref(dual_state(p))
+    iters = Ref{Int64}(0); d = Ref{Float64}(0.0)
+    check(ccall((:vbmf_b200_dual_run, LIB), Cint,
+                (Ptr{Void}, Ref{DualState}, Int64, Float64, Cint, Cint, Cint, Cint, Cint, Ref{Int64}, Ref{Float64}),
+                ctx.handle, st, niter, eps, diag_var, full_cov, est_priors, est_cb, NORM[norm], iters, d))
+    s = st[]
+    p.sigmaHat = s.sigmaHat; p.zeta = s.zeta
+    p.alpha00 = s.alpha00; p.beta00 = s.beta00; p.alpha01 = s.alpha01; p.beta01 = s.beta01
+    p.alpha0 = s.alpha0; p.alpha1 = s.alpha1
+    verb && print("Factorization finished after ", iters[], " iterations, eps = ", d[], "\n")
+    return d[]
+end
+function vbmf_dual(ctx::B200Context, Y, p_in::vbmf_dual_parameters, niter::Int; kw...)
+    p = deepcopy(p_in)
+    d = vbmf_dual!(ctx, Y, p, niter; kw...)
+    return p, d
+end
+
+# ---- lowerBound / lowerBoundTrimmed (src/vbmf_sparse.jl:435,478; src/vbmf_dual.jl:556,606) and the step functions -------------
+# go through the resident-solver entry points: solver_create -> *_upload -> solver_lower_bound / solver_step -> *_download.
+function with_solver(f, ctx::B200Context, kind::Int, H::Int, split::Int, labels::Vector{Int64})
+    h = Ref{Ptr{Void}}(C_NULL)
+    check(ccall((:vbmf_b200_solver_create, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Int64, Ptr{Int64}, Cint, Ptr{Ptr{Void}}),
+                ctx.handle, kind, H, split, length(labels), labels, 0, h))
+    try
+        return f(h[])
+    finally
+        ccall((:vbmf_b200_solver_destroy, LIB), Cint, (Ptr{Void},), h[])
+    end
+end
+function lower_bound(ctx::B200Context, Y, p::vbmf_sparse_parameters, trim::Float64, trimmed::Bool)
+    attach!(ctx, Y)
+    isdefined(p, :YHat) || (p.YHat = Array{Float64}(0, 0))
+    with_solver(ctx, 1, p.H, p.H1, p.labels) do s
+        st = Ref(sparse_state(p, convert(Ptr{Float64}, C_NULL)))
+        check(ccall((:vbmf_b200_sparse_upload, LIB), Cint, (Ptr{Void}, Ref{SparseState}), s, st))
+        out = Ref{Float64}(0.0)
+        check(ccall((:vbmf_b200_solver_lower_bound, LIB), Cint, (Ptr{Void}, Float64, Cint, Ref{Float64}), s, trim, trimmed, out))
+        out[]
+    end
+end
+function lower_bound(ctx::B200Context, Y, p::vbmf_dual_parameters, trim::Float64, trimmed::Bool)
+    attach!(ctx, Y)
+    isdefined(p, :YHat) || (p.YHat = Array{Float64}(0, 0))
+    with_solver(ctx, 2, p.H, p.H0, Int64[]) do s
+        st = Ref(dual_state(p))
+        check(ccall((:vbmf_b200_dual_upload, LIB), Cint, (Ptr{Void}, Ref{DualState}), s, st))
+        out = Ref{Float64}(0.0)
+        check(ccall((:vbmf_b200_solver_lower_bound, LIB), Cint, (Ptr{Void}, Float64, Cint, Ref{Float64}), s, trim, trimmed, out))
+        out[]
+    end
+end
+lowerBound(ctx::B200Context, Y, p) = lower_bound(ctx, Y, p, 0.0, false)
+lowerBoundTrimmed(ctx::B200Context, Y, p, trim = 1e-1) = lower_bound(ctx, Y, p, Float64(trim), true)
+
+end # module

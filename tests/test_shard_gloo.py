@@ -1,0 +1,149 @@
+"""CPU, world_size-2 (gloo) coverage of the N>1 path's host logic and of the sharding decomposition itself:
+
+every rank owns a column shard of Y and the matching rows of AHat / per-element vectors, computes the local partials
+[Y_g*A_g | A_g'A_g | sum of Sigma blocks | dual sums], one all-reduce of that packed buffer per iteration (the same payload
+layout libvbmf_b200 sends through NCCL, csrc/kernels.cuh packed_*), then every rank repeats the replicated B-side update.
+The result must equal the unsharded oracle -- including Quirk Q2, whose source index depends on the GLOBAL column index.
+This is test infrastructure (oracle arithmetic + gloo); the product path has no CPU mode.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import vbmf_oracle as vo  # noqa: E402
+from tests.helpers import synth  # noqa: E402
+
+
+def shard_columns(M, world, rank):
+    import vbmf_b200_loader
+    return vbmf_b200_loader.load().shard_columns(M, world, rank)
+
+
+def _sharded_sparse_iteration(Y, p, off, n, M, full_cov, est_cb, dual, est_priors):
+    """One iteration on the shard [off, off+n): local A side, packed all-reduce, replicated B side."""
+    H, L = p.H, p.L
+    Yg = Y[:, off:off + n]
+    # ---- updateA! on the shard (src/vbmf_sparse.jl:176-247): Q2 uses the global index j = (off+m)*H + h
+    P = Yg.T @ p.BHat
+    CA = p.CA.reshape(n, H)
+    if full_cov:
+        G = p.sigmaHat * (p.BHat.T @ p.BHat + L * p.SigmaB)
+        A = np.empty((n, H)); s = np.empty((n, H)); SA = np.zeros((H, H))
+        for m in range(n):
+            Sm = np.linalg.inv(G + np.diag(CA[m]))
+            A[m] = (p.sigmaHat * Sm) @ P[m]; s[m] = np.diag(Sm); SA += Sm
+    else:
+        d = vo._diag_precision_base(p, False)
+        j0 = (off * H + np.arange(n * H)).astype(np.int64)
+        src = np.where(j0 < H, j0, (j0 - H) // max(M - 1, 1))
+        s = (1.0 / (d[src] + p.CA)).reshape(n, H)
+        A = (p.sigmaHat * s) * P
+        SA = np.diag(s.sum(axis=0))
+    p.AHat, p.ATVecHat, p.diagSigmaATVec = A, A.reshape(-1).copy(), s.reshape(-1).copy()
+    # ---- updateCA! (local; hoisted before the exchange, it does not touch BHat)
+    extras = np.zeros(8)
+    if dual:
+        p.alpha0, p.alpha1 = p.alpha00 + 0.5, p.alpha01 + 0.5
+        g1 = (np.arange(H) >= p.H0)[None, :].repeat(n, 0)
+        beta = np.where(g1, p.beta01, p.beta00) + 0.5 * (A * A + s)
+        ca = np.where(g1, p.alpha1, p.alpha0) / beta
+        extras[:4] = [ca[~g1].sum(), ca[g1].sum(), np.log(beta[~g1]).sum(), np.log(beta[g1]).sum()]
+        p.beta, p.CA = beta.reshape(-1), ca.reshape(-1)
+    else:
+        p.beta = p.beta0 + 0.5 * (p.ATVecHat ** 2 + p.diagSigmaATVec)
+        p.CA = p.alpha / p.beta
+    # ---- packed all-reduce: [Q | A'A | SA | extras]
+    packed = np.concatenate([(Yg @ A).reshape(-1), (A.T @ A).reshape(-1), SA.reshape(-1), extras])
+    t = torch.from_numpy(packed)
+    dist.all_reduce(t)
+    Q = packed[:L * H].reshape(L, H); AtA = packed[L * H:L * H + H * H].reshape(H, H)
+    p.SigmaA = packed[L * H + H * H:L * H + 2 * H * H].reshape(H, H).copy(); ex = packed[-8:]
+    # ---- replicated: updateB!, updateCB!, updateSigma!, priors
+    GA = AtA + p.SigmaA
+    p.SigmaB = np.linalg.inv(np.diag(p.CB) + p.sigmaHat * GA)
+    p.BHat = (p.sigmaHat * Q) @ p.SigmaB
+    if est_cb:
+        vo.sparse_updateCB(p)
+    p.zeta = p.zeta0 + 0.5 * p.trYTY - float(np.sum(p.BHat * Q)) + 0.5 * float(np.sum(GA * (p.BHat.T @ p.BHat + L * p.SigmaB)))
+    p.sigmaHat = p.eta / p.zeta
+    if dual and est_priors:
+        from scipy.special import digamma
+        N0, N1 = M * p.H0, M * p.H1
+        for g, (N, a_g, slb) in enumerate(((N0, p.alpha0, ex[2]), (N1, p.alpha1, ex[3]))):
+            b0x = p.beta00 if g == 0 else p.beta01
+            S = N * digamma(a_g) - slb
+            c = N * np.log(b0x)
+            try:
+                root = vo.fzero_bisect(lambda x: c - N * digamma(x) + S)
+                if g == 0:
+                    p.alpha00 = root
+                else:
+                    p.alpha01 = root
+            except Exception:
+                pass
+        p.beta00 = N0 * p.alpha00 / ex[0]
+        p.beta01 = N1 * p.alpha01 / ex[1]
+
+
+def _worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, M, H = 24, 101, 4
+    Y = synth(L, M, 2, seed=3)
+    off, n = shard_columns(M, world, rank)
+    kind, full_cov = case
+    dual = kind == "dual"
+    pg = vo.vbmf_dual_init(Y, H, 1, rng=np.random.default_rng(7)) if dual else vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(7))
+    p = copy.deepcopy(pg)
+    p.M, p.MH = n, n * H
+    sl = slice(off * H, (off + n) * H)
+    for f in ("ATVecHat", "diagSigmaATVec", "CA", "beta"):
+        setattr(p, f, getattr(pg, f)[sl].copy())
+    p.AHat = pg.AHat[off:off + n].copy()
+    niter = 5
+    for _ in range(niter):
+        _sharded_sparse_iteration(Y, p, off, n, M, full_cov, True, dual, True)
+    if dual:
+        vo.vbmf_dual_run(Y, pg, niter, eps=0.0, full_cov=full_cov, est_priors=True, est_cb=True)
+    else:
+        vo.vbmf_sparse_run(Y, pg, niter, eps=0.0, full_cov=full_cov, est_cb=True)
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    errs = [rel(p.BHat, pg.BHat), rel(p.SigmaB, pg.SigmaB), rel(p.SigmaA, pg.SigmaA), rel(p.AHat, pg.AHat[off:off + n]),
+            rel(p.CA, pg.CA[sl]), abs(p.sigmaHat - pg.sigmaHat) / pg.sigmaHat, rel(p.CB, pg.CB)]
+    if dual:
+        errs += [abs(p.alpha00 - pg.alpha00) / pg.alpha00, abs(p.beta01 - pg.beta01) / pg.beta01]
+    t = torch.tensor([max(errs)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        with open(out, "w") as f:
+            f.write(repr(float(t.item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("sparse", False), ("sparse", True), ("dual", False), ("dual", True)])
+def test_world2_sharding_matches_unsharded(case, tmp_path):
+    out = str(tmp_path / "err.txt")
+    port = 29600 + abs(hash(case)) % 300
+    mp.spawn(_worker, args=(2, port, case, out), nprocs=2, join=True)
+    assert float(open(out).read()) < 1e-11
+
+
+def test_shard_columns_partition():
+    for M in (1, 7, 100, 200000):
+        for w in (1, 2, 3, 8):
+            parts = [shard_columns(M, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == M
+            for (o1, n1), (o2, _) in zip(parts, parts[1:]):
+                assert o1 + n1 == o2
