@@ -667,8 +667,8 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
     }
     if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR) && !s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
     if (enq_q_ata(s, fused)) return -1;
-    if (k_sigmaB(st, d, flags) || k_B_epilogue(st, d, flags)) return -1;
-    s->btb_valid = false;
+    if (k_sigmaB(st, d, flags) || k_B_epilogue(st, d, flags)) return -1;     // also BtB, DtD, tr(B'Q) of the new BHat
+    s->btb_valid = !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR));           // weighted Grams / Bs still stale with diag_var
     return 0;
 }
 static int enq_updateCA(vbmf_b200_solver* s, int flags, bool fused) {
@@ -724,8 +724,7 @@ static int enq_iteration(vbmf_b200_solver* s, int flags) {
     cudaStream_t st = s->c->st;
     if (enq_updateA(s, flags, true)) return -1;                       // updateA!
     if (d.kind != KIND_DENSE && enq_updateCA(s, flags, true)) return -1;   // updateCA! (local; hoisted before the all-reduce)
-    if (enq_updateB(s, flags, true)) return -1;                       // updateB!
-    if (k_gram(st, d, d.B, false, d.L, nullptr, d.BtB) || k_gram(st, d, d.D, false, d.L, nullptr, d.DtD)) return -1;
+    if (enq_updateB(s, flags, true)) return -1;                       // updateB! (+ Grams of BHat and of BHat - Bold)
     if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) {
         if (k_sigma_rows(st, d)) return -1;                           // updateSigma! (per-row)
         if (flags & F_FULL_COV) { if (k_gram(st, d, d.B, false, d.L, d.sigmaVec, d.BtBw)) return -1; }

@@ -21,6 +21,7 @@ struct Scalars {
     double eps;
     double d;         // last delta
     double normBold;  // norm(old) carried between iterations
+    double normD, normBnew;   // norm(BHat - old), norm(BHat) of the current iteration (norms_kernel)
     // model scalars
     double sigma2;                     // dense: noise variance
     double sigmaHat, eta, zeta;        // sparse/dual: noise precision posterior

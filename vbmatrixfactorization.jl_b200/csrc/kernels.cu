@@ -196,56 +196,55 @@ int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const doubl
 // mode 1: SigmaB = sigma2*inv(A'A + M*SigmaA + sigma2*invCB)            src/vbmf.jl:110-111
 // mode 2: SigmaA <- all-reduced sum of per-column blocks; SigmaB = inv(diag(CB) + c*(A'A + SigmaA)),
 //         c = sigmaHat or mean(sigmaVecHat)                             src/vbmf_sparse.jl:256-265, src/vbmf_dual.jl:294-303
-__global__ void __launch_bounds__(256) hxh_kernel(Dev d, int mode, int diag_var) {
+template <int Q>   // Q * 1024 >= H * H
+__global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_var) {
     ACTIVE_OR_RETURN(d);
-    extern __shared__ double sm[];
-    const int H = d.H, ld = H + 1;
-    double* Mx = sm;
-    double* vec = sm + H * ld;
+    __shared__ double cbuf[2 * 128], sbuf[128];
+    const int H = d.H;
     Scalars* sc = d.sc;
     const double* AtA = d.packed + packed_ata(d);
     const double* SA = d.packed + packed_sa(d);
-    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
-        const int i = e / H, j = e - i * H;
-        double v;
-        if (mode == 0) v = d.BtB[e] + (double)d.L * d.SigmaB[e] + sc->sigma2 * d.invCA[e];
-        else if (mode == 1) v = AtA[e] + (double)d.Mglob * d.SigmaA[e] + sc->sigma2 * d.invCB[e];
-        else {
-            const double sa = SA[e];
-            d.SigmaA[e] = sa;
-            const double c = diag_var ? sc->meanSigmaVec : sc->sigmaHat;
-            v = ((i == j) ? d.CBv[i] : 0.0) + c * (AtA[e] + sa);
-        }
-        Mx[i * ld + j] = v;
+    double a[Q];
+    int eij[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * 1024;
+        if (e < H * H) {
+            const int i = e / H, j = e - i * H;
+            eij[q] = i | (j << 8);
+            double v;
+            if (mode == 0) v = d.BtB[e] + (double)d.L * d.SigmaB[e] + sc->sigma2 * d.invCA[e];
+            else if (mode == 1) v = AtA[e] + (double)d.Mglob * d.SigmaA[e] + sc->sigma2 * d.invCB[e];
+            else {
+                const double sa = SA[e];
+                d.SigmaA[e] = sa;
+                const double c = diag_var ? sc->meanSigmaVec : sc->sigmaHat;
+                v = ((i == j) ? d.CBv[i] : 0.0) + c * (AtA[e] + sa);
+            }
+            a[q] = v;
+        } else { eij[q] = -1; a[q] = 0.0; }
     }
-    __syncthreads();
-    BlockGroup g;
-    const bool ok = spd_inverse(g, Mx, ld, H, vec);
+    const bool ok = block_spd_inverse_reg<Q>(a, eij, H, cbuf, sbuf);
     if (!ok && threadIdx.x == 0) sc->chol_fail = 1;
     double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
     const double scale = (mode == 2) ? 1.0 : sc->sigma2;
-    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
-        const int i = e / H, j = e - i * H;
-        out[e] = ok ? scale * Mx[i * ld + j] : nan("");
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * 1024;
+        if (e < H * H) out[e] = ok ? scale * a[q] : nan("");
     }
 }
-static size_t hxh_smem(int H) { return (size_t)(H * (H + 1) + 8 * H + 64) * sizeof(double); }
-static int hxh_attr() {
-    static bool done = false;
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(hxh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hxh_smem(128))); done = true; }
-    return 0;
-}
-int k_dense_sigmaA(cudaStream_t st, const Dev& d) {
-    if (hxh_attr()) return -1;
-    hxh_kernel<<<1, 256, hxh_smem(d.H), st>>>(d, 0, 0);
+static int hxh_launch(cudaStream_t st, const Dev& d, int mode, int dv) {
+    const int hh = d.H * d.H;
+    if (hh <= 1024) hxh_kernel<1><<<1, 1024, 0, st>>>(d, mode, dv);
+    else if (hh <= 4096) hxh_kernel<4><<<1, 1024, 0, st>>>(d, mode, dv);
+    else hxh_kernel<16><<<1, 1024, 0, st>>>(d, mode, dv);
     VB_LAUNCH_OK();
     return 0;
 }
+int k_dense_sigmaA(cudaStream_t st, const Dev& d) { return hxh_launch(st, d, 0, 0); }
 int k_sigmaB(cudaStream_t st, const Dev& d, int flags) {
-    if (hxh_attr()) return -1;
-    hxh_kernel<<<1, 256, hxh_smem(d.H), st>>>(d, d.kind == KIND_DENSE ? 1 : 2, (flags & F_DIAG_VAR) ? 1 : 0);
-    VB_LAUNCH_OK();
-    return 0;
+    return hxh_launch(st, d, d.kind == KIND_DENSE ? 1 : 2, (flags & F_DIAG_VAR) ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------- dense A epilogue
@@ -430,6 +429,66 @@ __global__ void __launch_bounds__(256) sparse_A_full_kernel(Dev d, int diag_var,
         if (e < H * H) out[e] = acc[q];
     }
 }
+// H <= 32: one warp per matrix, the matrix lives in registers (lane l owns column l), see warp_spd_inverse_reg.
+template <int HP>
+__global__ void __launch_bounds__(256) sparse_A_full_warp_kernel(Dev d, int diag_var, int nwarps_total) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ __align__(16) double s_col[8][64];
+    __shared__ __align__(16) double s_p[8][32];
+    const int H = d.H;
+    const Scalars* sc = d.sc;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wic;
+    double* col = s_col[wic];
+    double* pv = s_p[wic];
+    const double sh = sc->sigmaHat;
+    const bool live = lane < H;
+    constexpr bool KEEP_G = HP <= 16;          // column `lane` of G in registers when they are not needed elsewhere
+    const double* __restrict__ Gm = d.Gm;
+    double g[KEEP_G ? HP : 1], acc[HP];
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+        if (KEEP_G) g[q] = (q < H && live) ? Gm[q * H + lane] : 0.0;
+        acc[q] = 0.0;
+    }
+    const double gll = live ? d.Gm[lane * H + lane] : 0.0;
+    bool all_ok = true;
+    for (int m = gw; m < d.Mloc; m += nwarps_total) {
+        const double ca = live ? d.CAv[(size_t)m * H + lane] : 1.0;     // padded lanes: identity
+        const double p = live ? d.P[(size_t)m * H + lane] : 0.0;
+        double a[HP];
+#pragma unroll
+        for (int q = 0; q < HP; ++q)
+            a[q] = (KEEP_G ? g[q] : ((q < H && live) ? Gm[q * H + lane] : 0.0)) + ((q == lane) ? ca : 0.0);
+        pv[lane] = p;
+        const bool ok = warp_spd_inverse_reg<HP>(a, gll + ca, lane, col);      // ends with __syncwarp (pv visible)
+        all_ok = all_ok && ok;
+        double s = 0.0, dg = 0.0;
+#pragma unroll
+        for (int q = 0; q < HP; ++q) {
+            const double pq = pv[q];
+            s = diag_var ? fma(a[q], pq, s) : fma(sh * a[q], pq, s);     // row `lane` of Sigma_m (symmetric) times p
+            if (q == lane) dg = a[q];
+        }
+        if (live) {
+            d.A[(size_t)m * H + lane] = ok ? s : nan("");
+            d.sdiag[(size_t)m * H + lane] = ok ? dg : nan("");
+            if (d.blocks != nullptr) {
+#pragma unroll
+                for (int q = 0; q < HP; ++q) if (q < H) d.blocks[(size_t)m * H * H + q * H + lane] = a[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < HP; ++q) acc[q] += a[q];
+        __syncwarp();
+    }
+    if (!all_ok && lane == 0) d.sc->chol_fail = 1;
+    if (live) {
+        double* out = d.part + (size_t)gw * H * H;
+#pragma unroll
+        for (int q = 0; q < HP; ++q) if (q < H) out[q * H + lane] = acc[q];
+    }
+}
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
@@ -437,13 +496,13 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     VB_LAUNCH_OK();
     int ngroups;
     if (H <= 32) {
-        const int gpc = 8;                                           // 8 warps (matrices) per CTA
-        const size_t smem = (size_t)(gpc * (H * (H + 1) + 3 * H)) * sizeof(double);
-        static bool done = false;
-        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_kernel<WarpGroup, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((8 * (32 * 33 + 96)) * 8))); done = true; }
-        const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), gpc), 296));
-        ngroups = grid * gpc;
-        sparse_A_full_kernel<WarpGroup, 32><<<grid, 256, smem, st>>>(d, dv, ngroups);
+        const int wpc = 8;
+        const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
+        ngroups = grid * wpc;
+        if (H <= 8) sparse_A_full_warp_kernel<8><<<grid, 256, 0, st>>>(d, dv, ngroups);
+        else if (H <= 16) sparse_A_full_warp_kernel<16><<<grid, 256, 0, st>>>(d, dv, ngroups);
+        else if (H <= 24) sparse_A_full_warp_kernel<24><<<grid, 256, 0, st>>>(d, dv, ngroups);
+        else sparse_A_full_warp_kernel<32><<<grid, 256, 0, st>>>(d, dv, ngroups);
     } else {
         const size_t smem = (size_t)(H * (H + 1) + 3 * H) * sizeof(double);
         static bool done = false;
@@ -515,26 +574,38 @@ int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
 // ------------------------------------------------------------------------------------------- B epilogue
 // dense : BHat = ((Y*AHat)*SigmaB)/sigma2                       src/vbmf.jl:112
 // sparse: BHat = ((sigmaHat*Y)*AHat)*SigmaB                     src/vbmf_sparse.jl:266   (diag_var: diagm(sv)*Y*AHat*SigmaB, :261)
-// also keeps Bold, D = BHat - Bold (convergence test, src/util.jl:27-29) and partial sums of tr(BHat'*(Y*AHat))
-__global__ void __launch_bounds__(256) B_epilogue_kernel(Dev d, int diag_var) {
+// Fused with everything that needs the new rows while they sit in shared memory: Bold, D = BHat - Bold and the Grams
+// BHat'BHat, D'D of the convergence test (src/util.jl:27-29) and of updateCB!/updateSigma*!, and tr(BHat'*(Y*AHat)).
+// TD x TD threads, every thread owns an R x R patch of both Grams; TR rows per tile.
+template <int R, int TD, int TR>
+__global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
     __shared__ double red[32];
+    constexpr int NT = TD * TD;
     const int H = d.H, ld = H + 1;
-    double* S = sm;              // [H][ld]   SigmaB
-    double* T = sm + H * ld;     // [32][ld]  scaled Q tile
+    double* S = sm;                  // [H][ld]   SigmaB
+    double* T = S + H * ld;          // [TR][ld]  scaled Q tile
+    double* Bn = T + TR * ld;        // [TR][ld]  new BHat rows
+    double* Dn = Bn + TR * ld;       // [TR][ld]  BHat - Bold
     const Scalars* sc = d.sc;
     const double* Q = d.packed + packed_q(d);
-    for (int e = threadIdx.x; e < H * H; e += 256) S[(e / H) * ld + (e % H)] = d.SigmaB[e];
+    for (int e = threadIdx.x; e < H * H; e += NT) S[(e / H) * ld + (e % H)] = d.SigmaB[e];
     const bool dense = d.kind == KIND_DENSE;
     const double s2 = sc->sigma2, sh = sc->sigmaHat;
+    const int ta = threadIdx.x % TD, tb = threadIdx.x / TD;
+    double gB[R][R], gD[R][R];
+#pragma unroll
+    for (int p = 0; p < R; ++p)
+#pragma unroll
+        for (int q = 0; q < R; ++q) { gB[p][q] = 0.0; gD[p][q] = 0.0; }
     double tr = 0.0;
-    const int ntiles = (d.L + 31) / 32;
+    const int ntiles = (d.L + TR - 1) / TR;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int l0 = tile * 32, nr = min(32, d.L - l0);
+        const int l0 = tile * TR, nr = min(TR, d.L - l0);
         __syncthreads();
-        for (int e = threadIdx.x; e < 32 * H; e += 256) {
-            const int h = e >> 5, i = e & 31;
+        for (int e = threadIdx.x; e < TR * H; e += NT) {
+            const int h = e / TR, i = e - h * TR;
             double q = 0.0;
             if (i < nr) {
                 q = Q[(size_t)h * d.ldB + l0 + i];
@@ -543,8 +614,9 @@ __global__ void __launch_bounds__(256) B_epilogue_kernel(Dev d, int diag_var) {
             T[i * ld + h] = q;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < 32 * H; e += 256) {
-            const int h = e >> 5, i = e & 31;
+        for (int e = threadIdx.x; e < TR * H; e += NT) {
+            const int h = e / TR, i = e - h * TR;
+            double bn = 0.0, dn = 0.0;
             if (i < nr) {
                 double s = 0.0;
                 for (int k = 0; k < H; ++k) s = fma(T[i * ld + k], S[k * ld + h], s);
@@ -552,33 +624,80 @@ __global__ void __launch_bounds__(256) B_epilogue_kernel(Dev d, int diag_var) {
                 const size_t idx = (size_t)h * d.ldB + l0 + i;
                 const double old = d.B[idx];
                 d.Bold[idx] = old;
-                d.D[idx] = s - old;
+                dn = s - old;
+                d.D[idx] = dn;
                 d.B[idx] = s;
                 tr = fma(s, Q[idx], tr);
+                bn = s;
             }
+            Bn[i * ld + h] = bn;
+            Dn[i * ld + h] = dn;
+        }
+        __syncthreads();
+        for (int i = 0; i < TR; ++i) {
+            double xa[R], xb[R], ya[R], yb[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int a = ta + TD * q, b = tb + TD * q;
+                xa[q] = (a < H) ? Bn[i * ld + a] : 0.0; xb[q] = (b < H) ? Bn[i * ld + b] : 0.0;
+                ya[q] = (a < H) ? Dn[i * ld + a] : 0.0; yb[q] = (b < H) ? Dn[i * ld + b] : 0.0;
+            }
+#pragma unroll
+            for (int p = 0; p < R; ++p)
+#pragma unroll
+                for (int q = 0; q < R; ++q) { gB[p][q] = fma(xa[p], xb[q], gB[p][q]); gD[p][q] = fma(ya[p], yb[q], gD[p][q]); }
         }
     }
+    double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
+#pragma unroll
+    for (int p = 0; p < R; ++p)
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int a = ta + TD * p, b = tb + TD * q;
+            if (a < H && b < H) { out[a * H + b] = gB[p][q]; out[H * H + a * H + b] = gD[p][q]; }
+        }
     tr = block_sum(tr, red);
-    if (threadIdx.x == 0) d.part[blockIdx.x] = tr;
+    if (threadIdx.x == 0) out[2 * H * H] = tr;
 }
-__global__ void trbq_kernel(Dev d, int nparts) {
+// fixed-order reduction of the per-CTA partials: BtB, DtD, sc->trBQ
+__global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
     ACTIVE_OR_RETURN(d);
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += d.part[p];
-    d.sc->trBQ = s;
+    const int H = d.H, n = 2 * H * H + 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * n + e];
+        if (e < H * H) d.BtB[e] = s;
+        else if (e < 2 * H * H) d.DtD[e - H * H] = s;
+        else d.sc->trBQ = s;
+    }
 }
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
-    static bool done = false;
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * 129 * 8))); done = true; }
-    const size_t smem = (size_t)((d.H + 32) * (d.H + 1)) * sizeof(double);
-    const int grid = std::max(1, std::min(cdiv(d.L, 32), MAX_PARTS));
-    B_epilogue_kernel<<<grid, 256, smem, st>>>(d, (flags & F_DIAG_VAR) ? 1 : 0);
+    const int H = d.H, dv = (flags & F_DIAG_VAR) ? 1 : 0;
+    const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), 148));
+#define BEPI(RR, TDD, TRR)                                                                                                   \
+    {                                                                                                                        \
+        static bool done = false;                                                                                            \
+        const size_t smem = (size_t)((H + 3 * TRR) * (H + 1)) * sizeof(double);                                              \
+        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_kernel<RR, TDD, TRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                     (int)((TDD * RR + 3 * TRR) * (TDD * RR + 1) * 8))); done = true; }      \
+        B_epilogue_kernel<RR, TDD, TRR><<<grid, TDD * TDD, smem, st>>>(d, dv);                                               \
+    }
+    if (H <= 16) BEPI(1, 16, 32) else if (H <= 32) BEPI(2, 16, 32) else if (H <= 64) BEPI(4, 16, 32) else BEPI(4, 32, 16)
+#undef BEPI
     VB_LAUNCH_OK();
-    trbq_kernel<<<1, 1, 0, st>>>(d, grid);
+    B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 256)), 256, 0, st>>>(d, grid);
     VB_LAUNCH_OK();
     return 0;
 }
 
+__global__ void trbq_kernel(Dev d, int nparts) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x) s += d.part[p];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) d.sc->trBQ = s;
+}
 // tr(BHat' * Q) only (step-level updateSigma / lowerBound when BHat was not just produced by the epilogue)
 __global__ void __launch_bounds__(256) trbq_partial_kernel(Dev d) {
     ACTIVE_OR_RETURN(d);
@@ -597,7 +716,7 @@ int k_trbq(cudaStream_t st, const Dev& d) {
     const int grid = std::max(1, std::min(cdiv((long)d.H * d.ldB, 1024), MAX_PARTS));
     trbq_partial_kernel<<<grid, 256, 0, st>>>(d);
     VB_LAUNCH_OK();
-    trbq_kernel<<<1, 1, 0, st>>>(d, grid);
+    trbq_kernel<<<1, 256, 0, st>>>(d, grid);
     VB_LAUNCH_OK();
     return 0;
 }
@@ -645,9 +764,11 @@ __global__ void __launch_bounds__(128) sigma_rows_kernel(Dev d) {
 }
 __global__ void mean_sigma_kernel(Dev d, int nparts) {
     ACTIVE_OR_RETURN(d);
+    __shared__ double red[32];
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += d.part[p];
-    d.sc->meanSigmaVec = s / (double)d.L;
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x) s += d.part[p];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) d.sc->meanSigmaVec = s / (double)d.L;
 }
 int k_sigma_rows(cudaStream_t st, const Dev& d) {
     static bool done = false;
@@ -655,7 +776,7 @@ int k_sigma_rows(cudaStream_t st, const Dev& d) {
     const int grid = std::max(1, std::min(cdiv(d.L, 128), MAX_PARTS));
     sigma_rows_kernel<<<grid, 128, (size_t)d.H * d.H * 8, st>>>(d);
     VB_LAUNCH_OK();
-    mean_sigma_kernel<<<1, 1, 0, st>>>(d, grid);
+    mean_sigma_kernel<<<1, 256, 0, st>>>(d, grid);
     VB_LAUNCH_OK();
     return 0;
 }
@@ -721,7 +842,6 @@ __global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
     if (!d.sc->active) return;
     extern __shared__ double sm[];
     __shared__ double red[32];
-    __shared__ double s_val[4];
     Scalars* sc = d.sc;
     const int H = d.H, ld = H + 2;       // even padded size for Jacobi needs ld >= H+1
     double* Mx = sm;                      // [(H+1)][ld]
@@ -813,44 +933,61 @@ __global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
     }
 
     if (what & (POST_DELTA | POST_NORM_INIT)) {
-        // delta(new, old) = norm(old - new)/norm(old), src/util.jl:27-29; Julia 0.5 norm(::Matrix) = sigma_max (Q1)
-        for (int pass = (what & POST_DELTA) ? 0 : 1; pass < 2; ++pass) {
-            const double* Gm = pass == 0 ? d.DtD : d.BtB;
-            double val;
-            if (sc->norm_mode == 1) {
-                double s = 0.0;
-                for (int h = t; h < H; h += blockDim.x) s += Gm[h * H + h];
-                s = block_sum(s, red);
-                if (t == 0) s_val[pass] = s;
-                __syncthreads();
-                val = s_val[pass];
-            } else {
-                __syncthreads();
-                for (int e = t; e < H * H; e += blockDim.x) {
-                    const int i = e / H, j = e - i * H;
-                    Mx[i * ld + j] = 0.5 * (Gm[i * H + j] + Gm[j * H + i]);
-                }
-                __syncthreads();
-                val = sym_lambda_max(Mx, ld, H, vec);
-            }
-            if (t == 0) s_val[pass] = sqrt(fmax(val, 0.0)) + (val != val ? val : 0.0);
-            __syncthreads();
-        }
+        // delta(new, old) = norm(old - new)/norm(old), src/util.jl:27-29; the two norms come from norms_kernel
         if (t == 0) {
             if (what & POST_DELTA) {
-                const double dd = s_val[0] / sc->normBold;
+                const double dd = sc->normD / sc->normBold;
                 sc->d = dd;
                 sc->iter += 1;
                 sc->active = (sc->iter < sc->niter) && (dd > sc->eps) ? 1 : 0;
             }
-            sc->normBold = s_val[1];
+            sc->normBold = sc->normBnew;
         }
+    }
+}
+// norm(BHat - Bold) (block 0) and norm(BHat) (block 1) from the Grams D'D, B'B: Julia 0.5 norm(::Matrix) = sigma_max (Q1)
+// = sqrt(lambda_max(Gram)); frobenius mode = sqrt(trace).
+__global__ void __launch_bounds__(512) norms_kernel(Dev d, int first) {
+    if (!d.sc->active) return;
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    Scalars* sc = d.sc;
+    const int H = d.H, ld = H + 1, t = threadIdx.x;
+    const int which = first + blockIdx.x;            // 0: D'D   1: B'B
+    const double* Gm = which == 0 ? d.DtD : d.BtB;
+    double* Mx = sm;
+    double* vec = sm + H * ld;
+    double val;
+    if (sc->norm_mode == 1) {
+        double s = 0.0;
+        for (int h = t; h < H; h += blockDim.x) s += Gm[h * H + h];
+        val = block_sum(s, red);
+    } else {
+        for (int e = t; e < H * H; e += blockDim.x) {
+            const int i = e / H, j = e - i * H;
+            Mx[i * ld + j] = 0.5 * (Gm[i * H + j] + Gm[j * H + i]);
+        }
+        __syncthreads();
+        val = sym_lambda_max(Mx, ld, H, vec);
+    }
+    if (t == 0) {
+        const double nv = sqrt(fmax(val, 0.0)) + (val != val ? val : 0.0);
+        if (which == 0) sc->normD = nv; else sc->normBnew = nv;
     }
 }
 static size_t post_smem(int H) { return (size_t)((H + 2) * (H + 2) + 4 * (H + 2) + 8) * sizeof(double); }
 static int post_launch(cudaStream_t st, const Dev& d, int what, int flags) {
     static bool done = false;
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128))); done = true; }
+    if (!done) {
+        VB_CUDA_OK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128)));
+        VB_CUDA_OK(cudaFuncSetAttribute(norms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128)));
+        done = true;
+    }
+    if (what & (POST_DELTA | POST_NORM_INIT)) {
+        const int first = (what & POST_DELTA) ? 0 : 1;
+        norms_kernel<<<2 - first, 512, post_smem(d.H), st>>>(d, first);
+        VB_LAUNCH_OK();
+    }
     post_kernel<<<1, 256, post_smem(d.H), st>>>(d, what, flags);
     VB_LAUNCH_OK();
     return 0;

@@ -22,14 +22,15 @@ struct WarpGroup {
 };
 
 // In-place inverse of the SPD matrix A (H x H, row stride ld, shared memory).  `vec` = 2*H doubles of scratch.
-// Returns false (for every thread of the group) when a pivot is not positive / not finite; A is then garbage.
+// Diagonal equilibration to unit diagonal, then H symmetric Gauss-Jordan sweeps without pivoting (every pivot of an SPD
+// matrix is positive; elimination on the equilibrated matrix is as accurate as Cholesky up to a modest constant), two
+// group barriers per sweep.  Returns false (for every thread of the group) when a pivot is not positive / not finite.
 template <class G>
 __device__ bool spd_inverse(const G& g, double* A, int ld, int H, double* vec) {
     const int t = g.tid(), n = g.size();
     double* scal = vec;
     double* col = vec + H;
     bool ok = true;
-    // 1. equilibrate to unit diagonal
     for (int i = t; i < H; i += n) scal[i] = 1.0 / sqrt(A[i * ld + i]);
     g.sync();
     for (int e = t; e < H * H; e += n) {
@@ -37,56 +38,119 @@ __device__ bool spd_inverse(const G& g, double* A, int ld, int H, double* vec) {
         A[i * ld + j] *= scal[i] * scal[j];
     }
     g.sync();
-    // 2. Cholesky, lower triangle, right-looking
     for (int k = 0; k < H; ++k) {
-        const double pkk = A[k * ld + k];
-        if (!(pkk > 0.0) || !(pkk < 1e300)) ok = false;
-        const double rk = sqrt(pkk), ik = 1.0 / rk;
+        // sweep on pivot k:  A <- [[ A11 - a a'/d , a/d ], [ a'/d , -1/d ]] (sign fixed at the end), a = column k
+        const double d = A[k * ld + k];
+        if (!(d > 0.0) || !(d < 1e300)) ok = false;
+        const double id = 1.0 / d;
+        for (int i = t; i < H; i += n) col[i] = A[i * ld + k];
         g.sync();
-        for (int i = k + t; i < H; i += n) A[i * ld + k] = (i == k) ? rk : A[i * ld + k] * ik;
-        g.sync();
-        const int cnt = H - k - 1;
-        for (int e = t; e < cnt * cnt; e += n) {
-            const int i = k + 1 + e / cnt, j = k + 1 + e % cnt;
-            if (i >= j) A[i * ld + j] -= A[i * ld + k] * A[j * ld + k];
+        for (int e = t; e < H * H; e += n) {
+            const int i = e / H, j = e - i * H;
+            double v;
+            if (i == k) v = (j == k) ? -id : col[j] * id;
+            else if (j == k) v = col[i] * id;
+            else v = A[i * ld + j] - col[i] * col[j] * id;
+            A[i * ld + j] = v;
         }
         g.sync();
     }
-    // 3. X = L^{-1} in place (lower), columns from last to first
-    for (int j = H - 1; j >= 0; --j) {
-        for (int k = j + t; k < H; k += n) col[k] = A[k * ld + j];
-        g.sync();
-        const double xjj = 1.0 / col[j];
-        for (int i = j + t; i < H; i += n) {
-            if (i == j) { A[j * ld + j] = xjj; continue; }
-            double s = 0.0;
-            for (int k = j + 1; k <= i; ++k) s = fma(A[i * ld + k], col[k], s);   // X[i][k] (already inverted) * L[k][j]
-            A[i * ld + j] = -s * xjj;
+    // after sweeping every pivot A holds -inv; undo the sign and the scaling
+    for (int e = t; e < H * H; e += n) {
+        const int i = e / H, j = e - i * H;
+        A[i * ld + j] = -A[i * ld + j] * scal[i] * scal[j];
+    }
+    g.sync();
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-resident variants of the same equilibrated Gauss-Jordan inverse (the matrix never lives in shared memory).
+//
+// Warp version, H <= HP <= 32 (HP compile time so every register index is static): lane l owns column l, a[q] = A[q][l].
+// In sweep k every lane already holds A[k][l] (= A[l][k]) in a[k]; the lanes publish that row through a 32-double shared
+// vector (one STS) and read the whole column back as broadcasts (LDS.128), so a sweep costs ~2 FP64 ops per element and one
+// __syncwarp.  Rows / lanes >= H must be padded with the identity by the caller.  col = 64 doubles per warp (double buffer).
+// `dg` = A[l][l] of this lane.  On return a[q] = inv(A)[q][l]; `ok` is uniform across the warp.
+template <int HP>
+__device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg, int lane, double* col) {
+    bool ok = true;
+    const double sl = 1.0 / sqrt(dg);
+    col[lane] = sl;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < HP; q += 2) {
+        const double2 sq = *reinterpret_cast<const double2*>(col + q);
+        a[q] *= sq.x * sl;
+        a[q + 1] *= sq.y * sl;
+    }
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+        double* c = col + ((k + 1) & 1) * 32;
+        const double myk = a[k];                               // A[k][l]
+        c[lane] = myk;
+        __syncwarp();
+        const double d = c[k];
+        if (!(d > 0.0) || !(d < 1e300)) ok = false;
+        const double id = 1.0 / d;
+        const double t = myk * id;
+        const bool piv = lane == k;
+        const double alpha = piv ? 0.0 : 1.0, beta = piv ? id : -t;
+#pragma unroll
+        for (int q = 0; q < HP; q += 2) {
+            const double2 ck = *reinterpret_cast<const double2*>(c + q);
+            a[q] = fma(ck.x, beta, a[q] * alpha);
+            a[q + 1] = fma(ck.y, beta, a[q + 1] * alpha);
         }
-        g.sync();
+        a[k] = piv ? -id : t;
     }
-    // 4. inv = X' X : strict upper part into the upper triangle, diagonal into col[]
-    for (int e = t; e < H * H; e += n) {
-        const int i = e / H, j = e - i * H;
-        if (i <= j) {
-            double s = 0.0;
-            for (int k = j; k < H; ++k) s = fma(A[k * ld + i], A[k * ld + j], s);
-            if (i == j) col[i] = s; else A[i * ld + j] = s;
+    __syncwarp();
+    col[lane] = sl;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < HP; q += 2) {
+        const double2 sq = *reinterpret_cast<const double2*>(col + q);
+        a[q] = -a[q] * sq.x * sl;
+        a[q + 1] = -a[q + 1] * sq.y * sl;
+    }
+    __syncwarp();
+    return ok;
+}
+
+// CTA version: thread t owns elements e = t + q*blockDim.x (q < Q) of the row-major H x H matrix; column k travels
+// through a double-buffered shared vector, one __syncthreads per sweep.  cbuf = 2*H doubles, sbuf = H doubles.
+// Result stays in a[]; `ok` is uniform across the CTA.
+template <int Q>
+__device__ __forceinline__ bool block_spd_inverse_reg(double (&a)[Q], const int (&eij)[Q], int H, double* cbuf, double* sbuf) {
+    // eij[q] = row | (col << 8) of the owned element, -1 when the slot is unused (H <= 128)
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) if (eij[q] >= 0 && (eij[q] & 255) == (eij[q] >> 8)) sbuf[eij[q] & 255] = 1.0 / sqrt(a[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < Q; ++q) if (eij[q] >= 0) a[q] *= sbuf[eij[q] & 255] * sbuf[eij[q] >> 8];
+    for (int k = 0; k < H; ++k) {
+        double* col = cbuf + (k & 1) * H;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) if ((eij[q] >> 8) == k) col[eij[q] & 255] = a[q];
+        __syncthreads();
+        const double d = col[k];
+        if (!(d > 0.0) || !(d < 1e300)) ok = false;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            if (eij[q] >= 0) {
+                const int i = eij[q] & 255, j = eij[q] >> 8;
+                double v;
+                if (i == k) v = (j == k) ? -id : col[j] * id;
+                else if (j == k) v = col[i] * id;
+                else v = a[q] - (col[i] * col[j]) * id;
+                a[q] = v;
+            }
         }
     }
-    g.sync();
-    // 5. mirror + undo the scaling
-    for (int e = t; e < H * H; e += n) {
-        const int i = e / H, j = e - i * H;
-        if (i == j) A[i * ld + i] = col[i] * scal[i] * scal[i];
-        else if (i > j) A[i * ld + j] = A[j * ld + i] * scal[i] * scal[j];
-    }
-    g.sync();
-    for (int e = t; e < H * H; e += n) {
-        const int i = e / H, j = e - i * H;
-        if (i < j) A[i * ld + j] = A[j * ld + i];
-    }
-    g.sync();
+#pragma unroll
+    for (int q = 0; q < Q; ++q) if (eij[q] >= 0) a[q] = -a[q] * sbuf[eij[q] & 255] * sbuf[eij[q] >> 8];
     return ok;
 }
 
