@@ -33,6 +33,8 @@ WORKLOADS = {
            "configs[2]: synthetic dense Y 20000x200000, rank-32 signal + 0.1 noise, vbmf H=64 with ARD (est_covs, est_var), Float64"),
     "c4": (10000, 100000, 32, "sparse", ("est_cb",), "configs[3] (diagonal covariance path): vbmf_sparse 10000x100000 H=32"),
     "c4full": (10000, 100000, 32, "sparse", ("est_cb", "full_cov"), "configs[3]: vbmf_sparse 10000x100000 H=32 full_cov (batched per-row Cholesky)"),
+    # configs[4] needs >= 4 GPUs at full size (Y = 400 GB); per SURVEY 8(d) fewer GPUs run M = 125000 columns per GPU
+    "c5": (50000, 125000, 128, "dual", ("est_cb", "est_priors"), "configs[4] scaled to 125000 columns per GPU: vbmf_dual 50000x(125000*n)x128, H0=64, diagonal covariance, est_priors"),
 }
 FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue-rate peak on this pool's B200 (profiles/r01_fp64_peak_microbench.jsonl)
 SEED = 20260101
@@ -123,9 +125,13 @@ def cpu_reference(L, M, H, kind, flags, steps, warmup, budget_s):
     if kind == "dense":
         p = vo.vbmf_init(Y, H, rng=np.random.default_rng(SEED + 1))
         step = lambda: vo.vbmf_run(Y, p, 1, eps=0.0, est_covs="est_covs" in flags, est_var="est_var" in flags)
-    else:
+    elif kind == "sparse":
         p = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(SEED + 1))
         step = lambda: vo.vbmf_sparse_run(Y, p, 1, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags)
+    else:
+        p = vo.vbmf_dual_init(Y, H, H // 2, rng=np.random.default_rng(SEED + 1))
+        step = lambda: vo.vbmf_dual_run(Y, p, 1, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags,
+                                        est_priors="est_priors" in flags)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -167,6 +173,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     L, M, H, kind, flags, desc = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        M = M * max(1, env_int("WORLD_SIZE", 1))        # weak-scaled columns (the full 1e6 at 8 GPUs)
 
     if args.impl == "reference":
         run_reference(args, L, M, H, kind, flags, desc)
@@ -210,9 +218,13 @@ def main():
     if kind == "dense":
         pg = vb.vbmf_init(Shape, H, rng=rng)
         fl = (vb._lib.EST_COVS if "est_covs" in flags else 0) | (vb._lib.EST_VAR if "est_var" in flags else 0)
-    else:
+    elif kind == "sparse":
         pg = vb.vbmf_sparse_init(Shape, H, rng=rng, trYTY=ctx.trYTY())
         fl = (vb._lib.EST_CB if "est_cb" in flags else 0) | (vb._lib.FULL_COV if "full_cov" in flags else 0)
+    else:
+        pg = vb.vbmf_dual_init(Shape, H, H // 2, rng=rng, trYTY=ctx.trYTY())
+        fl = (vb._lib.EST_CB if "est_cb" in flags else 0) | (vb._lib.FULL_COV if "full_cov" in flags else 0) | \
+             (vb._lib.EST_PRIORS if "est_priors" in flags else 0)
 
     def local_params():
         p = vb.copy(pg)
@@ -223,6 +235,10 @@ def main():
             sl = slice(off * H, (off + Mloc) * H)
             for f in ("ATVecHat", "diagSigmaATVec", "CA", "beta"):
                 setattr(p, f, getattr(pg, f)[sl].copy())
+        if kind == "dual":
+            p.A0Hat = np.asfortranarray(p.AHat[:, :p.H0]); p.A1Hat = np.asfortranarray(p.AHat[:, p.H0:])
+            for f, w in (("CA0", p.H0), ("beta0", p.H0), ("CA1", p.H1), ("beta1", p.H1)):
+                setattr(p, f, getattr(pg, f)[off * w:(off + Mloc) * w].copy())
         return p
 
     p = local_params()
@@ -303,8 +319,12 @@ def main():
         if kind == "dense":
             vb.vbmf_(None, p2, args.steps, eps=0.0, est_covs="est_covs" in flags, est_var="est_var" in flags, ctx=ctx, yhat=False)
             done = p2.iterations
-        else:
+        elif kind == "sparse":
             vb.vbmf_sparse_(None, p2, args.steps, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags, ctx=ctx, yhat=False)
+            done = p2.iterations
+        else:
+            vb.vbmf_dual_(None, p2, args.steps, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags,
+                          est_priors="est_priors" in flags, ctx=ctx, yhat=False)
             done = p2.iterations
         barrier()
         w = time.perf_counter() - w0
@@ -330,7 +350,7 @@ def main():
     line = {
         "metric": "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, "dense vbmf" if kind == "dense" else "vbmf_" + kind),
         "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "c5" else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "global_shape": [L, M, H], "columns_per_gpu": Mloc, "parallelism": "column-sharded Y, dp%d, one packed "
                    "NCCL all-reduce per iteration" % world if world > 1 else "single GPU", "l2": "inputs larger than L2 (Y shard %.1f GB), no flush"
