@@ -291,6 +291,7 @@ struct vbmf_b200_solver {
     bool k2_simt = false;
     // host-side validity of derived quantities (every enqueued kernel either runs or is skipped as a whole iteration)
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
+    bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
     int* h_flag = nullptr;   // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
     Scalars h_sc;
@@ -343,7 +344,7 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
         items.push_back({&d.CBv, (size_t)H}); items.push_back({&d.deltav, (size_t)H});
         if (keep_blocks) items.push_back({&d.blocks, MH * H});
     }
-    size_t total = 256 + align_up(sizeof(Scalars), 256) + align_up((size_t)std::max(d.nlabels, 1) * 4, 256);
+    size_t total = 256 + align_up(sizeof(Scalars), 256) + align_up((size_t)std::max(d.nlabels, 1) * 4, 256) + align_up((size_t)std::max(d.Mloc, 1), 256);
     for (auto& it : items) total += align_up(it.n * 8, 256);
     if (cudaMalloc(&s->arena, total) != cudaSuccess) {
         cudaGetLastError();
@@ -356,6 +357,7 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
     char* p = s->arena;
     d.sc = (Scalars*)p; p += align_up(sizeof(Scalars), 256);
     s->d_labels = (int*)p; p += align_up((size_t)std::max(d.nlabels, 1) * 4, 256);
+    unsigned char* d_rowmask = (unsigned char*)p; p += align_up((size_t)std::max(d.Mloc, 1), 256);
     for (auto& it : items) { *it.p = (double*)p; p += align_up(it.n * 8, 256); }
     d.labels = s->d_labels;
     if (d.nlabels > 0) {
@@ -365,8 +367,12 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
             if (v < 1 || v > d.Mloc) { set_error("label %lld out of range 1..%d", (long long)v, d.Mloc); cudaFree(s->arena); delete s; return -1; }
             lab[i] = (int)(v - 1);
         }
+        std::vector<unsigned char> rm((size_t)std::max(d.Mloc, 1), 0);
+        for (int v : lab) rm[v] = 1;
         if (cudaMemcpyAsync(s->d_labels, lab.data(), (size_t)d.nlabels * 4, cudaMemcpyHostToDevice, c->st) != cudaSuccess ||
+            cudaMemcpyAsync(d_rowmask, rm.data(), rm.size(), cudaMemcpyHostToDevice, c->st) != cudaSuccess ||
             cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("label upload failed"); cudaFree(s->arena); delete s; return -1; }
+        d.rowmask = (d.H1 > 0) ? d_rowmask : nullptr;
     }
     const GemmGeometry g = gemm_geometry(d.H);
     int rc = 0;
@@ -441,7 +447,7 @@ static int push_scalars(vbmf_b200_solver* s) {
     s->h_sc.chol_fail = 0;
     VB_CUDA_OK(cudaMemcpyAsync(s->d.sc, &s->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, s->c->st));
     VB_CUDA_OK(cudaStreamSynchronize(s->c->st));
-    s->btb_valid = s->ata_valid = s->q_valid = s->extras_valid = s->mean_valid = false;
+    s->btb_valid = s->ata_valid = s->q_valid = s->extras_valid = s->mean_valid = s->ata_local = false;
     return 0;
 }
 static int pull_scalars(vbmf_b200_solver* s) {
@@ -581,7 +587,7 @@ extern "C" int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state
 }
 
 // ---- enqueue helpers ---------------------------------------------------------------------------------------------------
-static int enq_k1(vbmf_b200_solver* s, bool scaledB) {
+static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
     vbmf_b200_ctx* c = s->c;
     const Dev& d = s->d;
     prof_mark(c, c->ev_k1);
@@ -591,7 +597,7 @@ static int enq_k1(vbmf_b200_solver* s, bool scaledB) {
         const size_t MH = (size_t)d.Mloc * d.H;
         rc = launch_gemm_ytb(c->st, &c->tmY1, scaledB ? &s->tmBs : &s->tmB, s->S1 > 1 ? s->Ppart : d.P, d.Mloc, d.L, d.H, d.H,
                              s->S1, s->kbs1, MH, d.sc, c->num_sms);
-        if (!rc && s->S1 > 1) rc = k_sum_slabs(c->st, s->Ppart, s->S1, MH, d.P, d.sc);
+        if (!rc && s->S1 > 1 && reduce_slabs) rc = k_sum_slabs(c->st, s->Ppart, s->S1, MH, d.P, d.sc);
     }
     prof_mark(c, c->ev_k1);
     return rc;
@@ -632,7 +638,11 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
     cudaStream_t st = s->c->st;
     if (!s->btb_valid && enq_gram_B(s, flags)) return -1;
     if (d.kind == KIND_DENSE) {
-        if (k_dense_sigmaA(st, d) || enq_k1(s, false) || k_dense_A_epilogue(st, d) || k_mask(st, d)) return -1;
+        // the epilogue sums the K1 slabs itself, multiplies by SigmaA/sigma2, masks, and leaves the local AHat'AHat in packed
+        if (k_dense_sigmaA(st, d) || enq_k1(s, false, false)) return -1;
+        const bool slabs = !s->c->simt && s->S1 > 1;
+        if (k_dense_A_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H)) return -1;
+        s->ata_local = true;
     } else {
         const bool dv = (flags & F_DIAG_VAR) != 0;
         if (enq_k1(s, dv)) return -1;
@@ -642,6 +652,7 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
         if (!fused && copy_sa(s)) return -1;
     }
     s->ata_valid = false; s->q_valid = false;
+    if (d.kind != KIND_DENSE) s->ata_local = false;
     return 0;
 }
 static int enq_gram_A(vbmf_b200_solver* s) {
@@ -651,7 +662,9 @@ static int enq_gram_A(vbmf_b200_solver* s) {
 // Q = Y*AHat and AHat'AHat, all-reduced across shards.  fused: the payload also carries SigmaA blocks and dual sums.
 static int enq_q_ata(vbmf_b200_solver* s, bool fused) {
     const Dev& d = s->d;
-    if (enq_gram_A(s) || enq_k2(s)) return -1;
+    if (!s->ata_local && enq_gram_A(s)) return -1;
+    s->ata_local = false;
+    if (enq_k2(s)) return -1;
     const size_t n = fused ? packed_len(d) : packed_sa(d);
     if (ctx_allreduce(s->c, d.packed, n)) return -1;
     s->ata_valid = true; s->q_valid = true;
@@ -674,7 +687,12 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
 static int enq_updateCA(vbmf_b200_solver* s, int flags, bool fused) {
     const Dev& d = s->d;
     if (d.kind == KIND_DENSE) {
-        if (!s->ata_valid) { if (enq_gram_A(s) || ctx_allreduce(s->c, d.packed + packed_ata(d), (size_t)d.H * d.H)) return -1; s->ata_valid = true; }
+        if (!s->ata_valid) {
+            if (!s->ata_local && enq_gram_A(s)) return -1;
+            s->ata_local = false;
+            if (ctx_allreduce(s->c, d.packed + packed_ata(d), (size_t)d.H * d.H)) return -1;
+            s->ata_valid = true;
+        }
         return k_dense_cov_only(s->c->st, d, 0);
     }
     if (k_update_CA(s->c->st, d)) return -1;

@@ -248,38 +248,121 @@ int k_sigmaB(cudaStream_t st, const Dev& d, int flags) {
 }
 
 // ------------------------------------------------------------------------------------------- dense A epilogue
-// AHat = ((Y'*BHat)*SigmaA)/sigma2   src/vbmf.jl:98  (P = Y'*BHat from K1; left-to-right association, Q12)
-__global__ void __launch_bounds__(256) dense_A_epilogue_kernel(Dev d) {
+// AHat = ((Y'*BHat)*SigmaA)/sigma2   src/vbmf.jl:98  (left-to-right association, Q12), label mask (:101), and the Gram
+// AHat'AHat that updateB!/updateCA!/updateSigma2! need (src/vbmf.jl:110,131,155) -- one pass over the K1 slabs:
+//   T  = sum_s Pslab_s[tile]            (fixed-order split-K reduction, 32 rows x H)
+//   An = (T * SigmaA) / sigma2          DMMA, operands in shared memory with row pitch = 4 (mod 16) doubles so that the
+//                                       fragment loads (lane (r, j) -> [r][k0+j] resp. [k0+j][r]) hit 16 distinct banks
+//   G += An' * An                       DMMA, accumulators live in registers across the CTA's tiles
+__device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int pitch4(int hp8) { return ((hp8 + 11) / 16) * 16 + 4; }
+
+template <int TPW>   // Gram tiles per warp: ceil((HP8/8)^2 / 8)
+__global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(Dev d, const double* __restrict__ slabs, int S, size_t slab_stride) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
-    const int H = d.H, ld = H + 1;
-    double* S = sm;                 // [H][ld]
-    double* T = sm + H * ld;        // [32][ld]
-    for (int e = threadIdx.x; e < H * H; e += 256) S[(e / H) * ld + (e % H)] = d.SigmaA[e];
+    const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
+    double* Ss = sm;                 // [HP8][ld]  SigmaA, zero padded
+    double* T = Ss + HP8 * ld;       // [32][ld]   P tile
+    double* An = T + 32 * ld;        // [32][ld]   new AHat tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+    for (int e = threadIdx.x; e < HP8 * ld; e += 256) {
+        const int i = e / ld, c = e - i * ld;
+        Ss[e] = (i < H && c < H) ? d.SigmaA[i * H + c] : 0.0;
+    }
     const double s2 = d.sc->sigma2;
+    const int hmask = H - d.H1;      // columns >= hmask are zeroed on labelled rows
+    double g[TPW][2];
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) { g[q][0] = 0.0; g[q][1] = 0.0; }
     const int ntiles = (d.Mloc + 31) / 32;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
         __syncthreads();
-        for (int e = threadIdx.x; e < nr * H; e += 256) T[(e / H) * ld + (e % H)] = d.P[(size_t)m0 * H + e];
+#pragma unroll 4
+        for (int e = threadIdx.x; e < 32 * HP8; e += 256) {      // independent loads of several elements in flight
+            const int i = e / HP8, c = e - i * HP8;
+            double v = 0.0;
+            if (i < nr && c < H) {
+                const size_t idx = (size_t)(m0 + i) * H + c;
+                v = slabs[idx];
+                if (S > 1) v += slabs[slab_stride + idx];
+                if (S > 2) v += slabs[2 * slab_stride + idx];
+                for (int s = 3; s < S; ++s) v += slabs[(size_t)s * slab_stride + idx];
+            }
+            T[i * ld + c] = v;
+        }
         __syncthreads();
-        for (int e = threadIdx.x; e < nr * H; e += 256) {
-            const int r = e / H, h = e - r * H;
-            double s = 0.0;
-            for (int k = 0; k < H; ++k) s = fma(T[r * ld + k], S[k * ld + h], s);
-            d.A[(size_t)m0 * H + e] = s / s2;
+        // An = T * SigmaA / sigma2 : warp -> row tile (warp & 3), column tiles (warp >> 2), +2, ...
+        {
+            const int mt = warp & 3;
+            for (int nt = warp >> 2; nt < nt8; nt += 2) {
+                double c2[2] = {0.0, 0.0};
+#pragma unroll 8
+                for (int k0 = 0; k0 < HP8; k0 += 4)
+                    dmma_acc(c2, T[(8 * mt + r) * ld + k0 + j], Ss[(k0 + j) * ld + 8 * nt + r]);
+                const int row = 8 * mt + r, col = 8 * nt + 2 * j;
+                double v0 = c2[0] / s2, v1 = c2[1] / s2;
+                const bool lab = d.rowmask != nullptr && row < nr && d.rowmask[m0 + row];
+                if (lab && col >= hmask) v0 = 0.0;
+                if (lab && col + 1 >= hmask) v1 = 0.0;
+                An[row * ld + col] = v0;
+                An[row * ld + col + 1] = v1;
+                if (row < nr) {
+                    double* out = d.A + (size_t)(m0 + row) * H + col;
+                    if (col < H) out[0] = v0;
+                    if (col + 1 < H) out[1] = v1;
+                }
+            }
+        }
+        __syncthreads();
+        // G += An' * An over the 32 rows of the tile
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            const int idx = warp + 8 * q;
+            if (idx < nt8 * nt8) {
+                const int at = idx / nt8, bt = idx - at * nt8;
+#pragma unroll
+                for (int i0 = 0; i0 < 32; i0 += 4)
+                    dmma_acc(g[q], An[(i0 + j) * ld + 8 * at + r], An[(i0 + j) * ld + 8 * bt + r]);
+            }
+        }
+    }
+    double* out = d.part + (size_t)blockIdx.x * H * H;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+        const int idx = warp + 8 * q;
+        if (idx < nt8 * nt8) {
+            const int at = idx / nt8, bt = idx - at * nt8;
+            const int a = 8 * at + r, b = 8 * bt + 2 * j;
+            if (a < H && b < H) out[a * H + b] = g[q][0];
+            if (a < H && b + 1 < H) out[a * H + b + 1] = g[q][1];
         }
     }
 }
-int k_dense_A_epilogue(cudaStream_t st, const Dev& d) {
-    static bool done = false;
-    const size_t smem = (size_t)((d.H + 32) * (d.H + 1)) * sizeof(double);
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(dense_A_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * 129 * 8))); done = true; }
+// slabs: S split-K slabs of K1 (slab_stride apart) or the single P buffer (S = 1); writes AHat and packed.AtA (local part)
+int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride) {
     if (d.Mloc <= 0) return 0;
-    const int grid = std::max(1, std::min(cdiv(d.Mloc, 32), 148 * 4));
-    dense_A_epilogue_kernel<<<grid, 256, smem, st>>>(d);
+    const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8);
+    const size_t smem = (size_t)((HP8 + 64) * ld) * sizeof(double);
+    const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));     // latency hiding across CTAs
+    const int grid = std::max(1, std::min(cdiv(d.Mloc, 32), 148 * per_sm));
+    static bool done = false;
+    if (!done) {
+        const int mx = (int)((128 + 64) * pitch4(128) * 8);
+        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        done = true;
+    }
+    if (HP8 <= 32) dense_A_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
+    else if (HP8 <= 64) dense_A_fused_kernel<8><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
+    else dense_A_fused_kernel<32><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
     VB_LAUNCH_OK();
-    return 0;
+    return sum_partials(st, d.part, grid, (size_t)H * H, (size_t)H * H, d.packed + packed_ata(d), d.sc);
 }
 
 // AHat[labels, end-H1+1:end] = 0.0     src/vbmf.jl:101, src/vbmf_sparse.jl:245

@@ -33,6 +33,7 @@ struct Dev {
     double* Gm;          // [H][H] likelihood part of the per-column precision (full_cov)
     double* part;        // partial-sum workspace
     const int* labels;   // local 0-based rows of A to mask
+    const unsigned char* rowmask;   // [Mloc] 1 where the row is labelled (nullptr without labels)
     double* lbacc;       // [32] lower-bound accumulators
 };
 
@@ -60,7 +61,7 @@ int k_mean_sigma(cudaStream_t st, const Dev& d);                 // sc->meanSigm
 int k_total(cudaStream_t st, const double* x, int n, double* out);   // out[0] = sum(x), single CTA, fixed order
 int k_norms_init(cudaStream_t st, const Dev& d);                 // normBold = norm(BHat) from d.BtB
 int k_dense_sigmaA(cudaStream_t st, const Dev& d);               // SigmaA = sigma2*inv(B'B + L*SigmaB + sigma2*invCA)
-int k_dense_A_epilogue(cudaStream_t st, const Dev& d);           // A = (P*SigmaA)/sigma2, mask
+int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride);   // A = (sum_s P_s * SigmaA)/sigma2, mask, A'A
 int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags);   // diagonal path incl. Q2 map; partial column sums of s
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags);   // batched H x H SPD inverse per column
 int k_mask(cudaStream_t st, const Dev& d);
