@@ -160,6 +160,93 @@ def run_reference(args, L, M, H, kind, flags, desc):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ config 2: batched MIL-like problems
+def make_mil_problems(vbmod, nbags=548, L=38, H=20, seed=SEED):
+    """Synthetic stand-in for the MIL bags (the real .jld datasets are not in the reference repo, examples/mil_data.jl:97):
+    548 bags, 38 features, 5-40 instances per bag, two class models (BHat, SigmaB), H = 20, H1 = 1, scale = 10."""
+    rng = np.random.default_rng(seed)
+    B = [np.asfortranarray(rng.standard_normal((L, H))) for _ in range(2)]
+    SB = [np.asfortranarray(np.diag(rng.uniform(1e-3, 1e-2, H))) for _ in range(2)]
+    Ys, ps = [], []
+    for _ in range(nbags):
+        M = int(rng.integers(5, 41))
+        Y = np.asfortranarray(10.0 * (rng.standard_normal((L, 3)) @ rng.standard_normal((3, M)) + 0.1 * rng.standard_normal((L, M))))
+        for c in range(2):
+            p = vbmod.vbmf_dual_init(Y, H, H - 1, rng=rng)
+            p.BHat, p.SigmaB, p.sigmaHat = B[c].copy(), SB[c].copy(), 0.7
+            Ys.append(Y)
+            ps.append(p)
+    return Ys, ps
+
+
+def run_c2(args):
+    """`--workload c2`: classify(...; class_alg="dual") pattern = vbls!(Y, params, 20, full_cov=true) on every bag x class
+    model (examples/mil_util.jl:504-511), all 1096 problems in one launch of the one-CTA-per-problem kernel."""
+    import torch
+    import vbmf_b200_loader
+    vb = vbmf_b200_loader.load()
+    lib = vb._lib.load()
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    ctx = vb.Context(device=0, stream=stream.cuda_stream)
+    niter = 20
+    Ys, ps = make_mil_problems(vb)
+    n = len(ps)
+    for _ in range(max(args.warmup, 3)):
+        vb.vbls_batched_(Ys, [vb.copy(p) for p in ps], niter, full_cov=True, ctx=ctx, yhat=True)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.1)
+    dev_ms, wall = [], []
+    ctx.profile(True)
+    n0 = lib.vbmf_b200_launch_count()
+    t_start = time.time()
+    for _ in range(args.steps):
+        qs = [vb.copy(p) for p in ps]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        vb.vbls_batched_(Ys, qs, niter, full_cov=True, ctx=ctx, yhat=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - w0)
+        dev_ms.append(e0.elapsed_time(e1))
+    t_end = time.time()
+    launches = lib.vbmf_b200_launch_count() - n0
+    prof = ctx.profile_read()
+    kernel_ms = prof["k1_ms"] / max(prof["k1_launches"], 1)
+    clocks = sampler.stop(t_start, t_end)
+    ms = float(np.mean(dev_ms))
+    cpu = None
+    if not args.no_cpu:
+        from oracle import vbmf_oracle as vo
+        from tests.gpu_helpers import to_gpu_params  # noqa: F401  (only to keep the import graph obvious)
+        rngc = np.random.default_rng(SEED)
+        k = 24
+        t0 = time.perf_counter()
+        for Y, p in zip(Ys[:k], ps[:k]):
+            po = vo.vbmf_dual_init(np.ascontiguousarray(Y), p.H, p.H0, rng=rngc)
+            po.BHat, po.SigmaB, po.sigmaHat = np.array(p.BHat), np.array(p.SigmaB), p.sigmaHat
+            vo.vbls(np.ascontiguousarray(Y), po, niter, full_cov=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": k / dt, "unit": "problems/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "oracle vbls (20 iterations, full_cov) on the first %d of the %d problems" % (k, n)}
+    Mtot = sum(Y.shape[1] for Y in Ys)
+    line = {"metric": "vbls! problems/s (MIL pattern: 548 bags x 2 class models, L=38, M=5..40, H=20, 20 iterations, full_cov)",
+            "value": n / (ms * 1e-3), "unit": "problems/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1] stand-in: synthetic MIL bags (real datasets are not in the reference repo), vbmf_dual "
+                                   "parameters, one CTA per problem", "problems": n, "l2": "working set (%.1f MB) fits L2; each step re-uploads "
+                                   "every input from the host" % (Mtot * 38 * 8 / 1e6)},
+            "roofline": {"bound": "latency", "kernel": "batched_vbls_kernel", "kernel_ms": kernel_ms, "kernel_problems_per_s": n / (kernel_ms * 1e-3),
+                         "note": "one CTA per problem, state in shared memory/registers for all 20 iterations; `value` brackets the whole ABI "
+                                 "call with CUDA events (host packing + upload + kernel + download), kernel_ms is the kernel alone"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": n / float(np.mean(wall)), "unit": "problems/s", "h2d_bytes_per_step": int(Mtot * 38 * 8 + n * (38 * 20 + 400) * 8 + Mtot * 20 * 8),
+                    "d2h_bytes_per_step": int(Mtot * 20 * 8 * 4 + Mtot * 38 * 8), "note": "wall clock incl. Python/ctypes marshalling of 1096 structs"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -167,11 +254,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c2"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.workload == "c2":
+        if args.impl == "ours":
+            run_c2(args)
+        return
     L, M, H, kind, flags, desc = WORKLOADS[args.workload]
     if args.workload == "c5":
         M = M * max(1, env_int("WORLD_SIZE", 1))        # weak-scaled columns (the full 1e6 at 8 GPUs)

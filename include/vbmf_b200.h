@@ -180,6 +180,15 @@ int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, int trimmed, 
 /* updateYHat!: YHat (L x M_local, leading dimension ld) = BHat*AHat', src/vbmf.jl:120 */
 int vbmf_b200_solver_yhat(vbmf_b200_solver* s, double* YHat, int64_t ld);
 
+/* ---- batched small problems (the MIL classification pattern) ---- */
+/* vbls! (examples/mil_util.jl:179-203) for nprob independent problems in ONE kernel launch, one CTA per problem:
+ * niter x { updateA!, updateCA!, updateSigma! } with BHat fixed, then updateYHat! -- what classify(...; class_alg="dual")
+ * runs for every test bag and class model (examples/mil_util.jl:504-511).  kind = VBMF_B200_SPARSE or VBMF_B200_DUAL;
+ * states[p] points to the matching state struct of problem p, Y[p] to its L x states[p]->M matrix.  All problems share
+ * L, H (and H0); M may differ.  flags: VBMF_B200_FULL_COV.  Needs no attached Y.  Limits: H <= 32, no labels, no diag_var. */
+int vbmf_b200_batched_vbls(vbmf_b200_ctx* ctx, int kind, int64_t nprob, const double* const* Y, void* const* states,
+                           int64_t niter, int flags);
+
 /* ---- one-call drop-ins: upload + loop + updateYHat! + download ---- */
 /* vbmf!(Y, params, niter; eps, est_covs, est_var)   src/vbmf.jl:175 */
 int vbmf_b200_dense_run(vbmf_b200_ctx* ctx, vbmf_b200_dense_state* st, int64_t niter, double eps, int est_covs, int est_var,

@@ -275,3 +275,31 @@ def test_no_y_attached_errors(G):
     with pytest.raises(G.vb.VBMFError):
         G.vb.Solver(c, p)
     c.close()
+
+
+# ------------------------------------------------------------------------------------------------ batched small problems (MIL pattern)
+@pytest.mark.parametrize("kind,full_cov,H", [("dual", True, 20), ("dual", False, 20), ("sparse", True, 20), ("sparse", False, 7),
+                                             ("sparse", True, 32), ("dual", True, 4)])
+def test_vbls_batched(G, ctx, kind, full_cov, H):
+    """examples/mil_util.jl:504-511: vbls! on every bag x class model; one CTA per problem must equal the oracle's vbls."""
+    rng = np.random.default_rng(17)
+    L, nprob, niter = 38, 40, 20
+    Ys, ps, qs = [], [], []
+    for b in range(nprob):
+        M = int(rng.integers(2, 41)) if b else 1          # includes the M = 1 edge (Q2 degenerates)
+        Y = 10.0 * synth(L, M, 3, seed=100 + b)           # scale = 10 as in examples/mil_data.jl:19
+        if kind == "sparse":
+            p = vo.vbmf_sparse_init(Y, H, rng=rng)
+        else:
+            p = vo.vbmf_dual_init(Y, H, H - 1, rng=rng)   # H1 = 1 as in examples/mil_data.jl:23
+        p.SigmaB = np.diag(rng.uniform(1e-3, 1e-2, H))    # a trained model carries a non-trivial SigmaB
+        p.sigmaHat = 0.7
+        Ys.append(np.asfortranarray(Y)); ps.append(p); qs.append(G.to_gpu_params(p))
+    G.vb.vbls_batched_(Ys, qs, niter, full_cov=full_cov, ctx=ctx)
+    fields = ["AHat", "ATVecHat", "diagSigmaATVec", "SigmaA", "CA", "beta", "sigmaHat", "zeta"]
+    if kind == "dual":
+        fields += ["A0Hat", "A1Hat", "CA0", "CA1", "beta0", "beta1", "alpha0", "alpha1"]
+    for Y, p, q in zip(Ys, ps, qs):
+        vo.vbls(Y, p, niter, full_cov=full_cov)
+        G.compare(q, p, TOL, fields)
+        assert G.rel(q.YHat, p.YHat) < TOL

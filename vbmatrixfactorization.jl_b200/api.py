@@ -27,7 +27,7 @@ __all__ = [
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
-    "vbls_", "VBMFError",
+    "vbls_", "vbls_batched_", "VBMFError",
 ]
 
 VBMFError = L_.VBMFError
@@ -626,3 +626,24 @@ def vbls_(Y, params, niter, diag_var=False, full_cov=False, ctx=None):
     finally:
         s.close()
     return params.AHat
+
+
+def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, keep_blocks=False):
+    """`vbls!` (examples/mil_util.jl:179-203) for many small problems in ONE kernel launch (one CTA per problem): the MIL
+    classification pattern, classify(...; class_alg = "dual") runs it for every test bag and class model.  All params must
+    be vbmf_sparse_parameters or all vbmf_dual_parameters with the same L, H (and H0); M may differ per problem."""
+    ctx = ctx or default_context()
+    n = len(params_list)
+    if n == 0:
+        return []
+    kind = params_list[0].kind
+    if kind == L_.DENSE or any(p.kind != kind for p in params_list):
+        raise VBMFError("vbls_batched_ needs a homogeneous list of vbmf_sparse or vbmf_dual parameters")
+    Ys = [_f(Y) for Y in Ys]
+    structs = [_struct(p, yhat, keep_blocks) for p in params_list]
+    yp = (L_.p_f64 * n)(*[_ptr(Y) for Y in Ys])
+    sp = (C.c_void_p * n)(*[C.cast(C.pointer(st), C.c_void_p) for st in structs])
+    L_.check(ctx.lib.vbmf_b200_batched_vbls(ctx.h, kind, n, yp, sp, int(niter), L_.FULL_COV if full_cov else 0), allow=(-2,))
+    for p, st in zip(params_list, structs):
+        _readback(p, st)
+    return [p.AHat for p in params_list]

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <type_traits>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -931,4 +932,139 @@ extern "C" int vbmf_b200_dual_run(vbmf_b200_ctx* c, vbmf_b200_dual_state* st, in
     if (rc == 0 || rc == -2) { int r2 = vbmf_b200_dual_download(s, st); if (r2) rc = r2; }
     vbmf_b200_solver_destroy(s);
     return rc;
+}
+
+// ---- K11: batched vbls! ----------------------------------------------------------------------------------------------------
+namespace vb {
+struct BatchDesc {
+    int nprob, L, H, H0, kind, niter, full_cov, Mmax;
+    const int* moff; const double* Y; const double* B; const double* SigmaB;
+    double* A; double* CA; double* beta; double* sdiag; double* SigmaA; double* blocks; double* YHat; double* scal;
+};
+}
+
+template <class ST> struct BatchView {
+    static const ST* get(void* const* states, int64_t p) { return (const ST*)states[p]; }
+};
+
+template <class ST>
+static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const double* const* Y, void* const* states,
+                             int64_t niter, int flags) {
+    if (nprob <= 0) return 0;
+    if (flags & F_DIAG_VAR) { set_error("batched vbls: diag_var is not supported"); return -1; }
+    const ST* s0 = (const ST*)states[0];
+    const int64_t L = s0->L, H = s0->H;
+    int64_t H0 = H;
+    if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) H0 = s0->H0;
+    if (L < 1 || H < 1 || H > 32) { set_error("batched vbls supports 1 <= H <= 32 (got H = %lld)", (long long)H); return -1; }
+    std::vector<int> moff(nprob + 1, 0);
+    int Mmax = 0;
+    bool want_yhat = false, want_blocks = false;
+    for (int64_t p = 0; p < nprob; ++p) {
+        const ST* s = (const ST*)states[p];
+        if (s == nullptr || Y[p] == nullptr) { set_error("batched vbls: NULL problem %lld", (long long)p); return -1; }
+        if (s->L != L || s->H != H || s->M < 1) { set_error("batched vbls: problem %lld has different L/H or M < 1", (long long)p); return -1; }
+        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) { if (s->H0 != H0) { set_error("batched vbls: H0 differs"); return -1; } }
+        else { if (s->n_labels > 0 && s->H1 > 0) { set_error("batched vbls: labels are not supported"); return -1; } }
+        moff[p + 1] = moff[p] + (int)s->M;
+        Mmax = std::max<int>(Mmax, (int)s->M);
+        want_yhat = want_yhat || s->YHat != nullptr;
+        want_blocks = want_blocks || s->SigmaATVec_blocks != nullptr;
+    }
+    const size_t Mtot = (size_t)moff[nprob], MH = Mtot * H, HH = (size_t)H * H, LH = (size_t)L * H;
+    // ---- pack
+    std::vector<double> hY(L * Mtot), hB(nprob * LH), hSB(nprob * HH), hCA(MH), hsc((size_t)nprob * 16, 0.0);
+    for (int64_t p = 0; p < nprob; ++p) {
+        const ST* s = (const ST*)states[p];
+        memcpy(&hY[(size_t)moff[p] * L], Y[p], (size_t)s->M * L * 8);
+        memcpy(&hB[p * LH], s->BHat, LH * 8);
+        memcpy(&hSB[p * HH], s->SigmaB, HH * 8);
+        memcpy(&hCA[(size_t)moff[p] * H], s->CA, (size_t)s->M * H * 8);
+        double* sc = &hsc[(size_t)p * 16];
+        sc[0] = s->sigmaHat; sc[1] = s->eta; sc[2] = s->zeta; sc[3] = s->zeta0; sc[4] = s->trYTY;
+        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) { sc[7] = s->alpha00; sc[8] = s->beta00; sc[9] = s->alpha01; sc[10] = s->beta01; }
+        else { sc[5] = s->alpha; sc[6] = s->beta0; }
+    }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    // ---- device arena
+    struct Item { void** p; size_t bytes; };
+    int* d_moff = nullptr;
+    double *dY = nullptr, *dB = nullptr, *dSB = nullptr, *dA = nullptr, *dCA = nullptr, *dbeta = nullptr, *ds = nullptr, *dSA = nullptr,
+           *dblk = nullptr, *dYH = nullptr, *dsc = nullptr;
+    std::vector<Item> items = {{(void**)&d_moff, (size_t)(nprob + 1) * 4}, {(void**)&dY, L * Mtot * 8}, {(void**)&dB, nprob * LH * 8},
+                               {(void**)&dSB, nprob * HH * 8}, {(void**)&dA, MH * 8}, {(void**)&dCA, MH * 8}, {(void**)&dbeta, MH * 8},
+                               {(void**)&ds, MH * 8}, {(void**)&dSA, nprob * HH * 8}, {(void**)&dsc, (size_t)nprob * 16 * 8}};
+    if (want_blocks) items.push_back({(void**)&dblk, MH * H * 8});
+    if (want_yhat) items.push_back({(void**)&dYH, L * Mtot * 8});
+    size_t total = 0;
+    for (auto& it : items) total += align_up(it.bytes, 256);
+    char* arena = nullptr;
+    if (cudaMalloc(&arena, total) != cudaSuccess) { cudaGetLastError(); set_error("batched vbls: cudaMalloc of %zu bytes failed", total); return -1; }
+    char* q = arena;
+    for (auto& it : items) { *it.p = q; q += align_up(it.bytes, 256); }
+    int rc = 0;
+    cudaStream_t st = c->st;
+    auto H2D = [&](void* d, const void* h, size_t n) { if (!rc && cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("batched vbls: upload failed"); rc = -1; } };
+    H2D(d_moff, moff.data(), (size_t)(nprob + 1) * 4); H2D(dY, hY.data(), hY.size() * 8); H2D(dB, hB.data(), hB.size() * 8);
+    H2D(dSB, hSB.data(), hSB.size() * 8); H2D(dCA, hCA.data(), hCA.size() * 8); H2D(dsc, hsc.data(), hsc.size() * 8);
+    BatchDesc bd;
+    bd.nprob = (int)nprob; bd.L = (int)L; bd.H = (int)H; bd.H0 = (int)H0; bd.kind = kind; bd.niter = (int)std::max<int64_t>(niter, 0);
+    bd.full_cov = (flags & F_FULL_COV) ? 1 : 0; bd.Mmax = Mmax;
+    bd.moff = d_moff; bd.Y = dY; bd.B = dB; bd.SigmaB = dSB; bd.A = dA; bd.CA = dCA; bd.beta = dbeta; bd.sdiag = ds; bd.SigmaA = dSA;
+    bd.blocks = dblk; bd.YHat = dYH; bd.scal = dsc;
+    prof_mark(c, c->ev_k1);       // profiling: the kernel alone (read back through vbmf_b200_ctx_profile_read, K1 slot)
+    if (!rc && bd.niter > 0) rc = k_batched_vbls(st, bd);
+    prof_mark(c, c->ev_k1);
+    // ---- download + unpack
+    std::vector<double> hA(MH), hbeta(MH), hs(MH), hSA(nprob * HH), hYH, hblk;
+    auto D2H = [&](void* h, const void* d, size_t n) { if (!rc && cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("batched vbls: download failed"); rc = -1; } };
+    if (bd.niter > 0) {
+        D2H(hA.data(), dA, MH * 8); D2H(hCA.data(), dCA, MH * 8); D2H(hbeta.data(), dbeta, MH * 8); D2H(hs.data(), ds, MH * 8);
+        D2H(hSA.data(), dSA, nprob * HH * 8); D2H(hsc.data(), dsc, hsc.size() * 8);
+        if (want_yhat) { hYH.resize(L * Mtot); D2H(hYH.data(), dYH, hYH.size() * 8); }
+        if (want_blocks) { hblk.resize(MH * H); D2H(hblk.data(), dblk, hblk.size() * 8); }
+    }
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_error("batched vbls: %s", cudaGetErrorString(e)); rc = -1; } }
+    cudaFree(arena);
+    if (rc || bd.niter == 0) return rc;
+    bool failed = false;
+    for (int64_t p = 0; p < nprob; ++p) {
+        ST* s = (ST*)states[p];
+        const size_t M = (size_t)s->M, o = (size_t)moff[p] * H;
+        const double* sc = &hsc[(size_t)p * 16];
+        failed = failed || sc[13] != 0.0;
+        if (s->ATVecHat) memcpy(s->ATVecHat, &hA[o], M * H * 8);
+        if (s->AHat) for (size_t m = 0; m < M; ++m) for (size_t h = 0; h < (size_t)H; ++h) s->AHat[h * M + m] = hA[o + m * H + h];
+        if (s->diagSigmaATVec) memcpy(s->diagSigmaATVec, &hs[o], M * H * 8);
+        if (s->CA) memcpy(s->CA, &hCA[o], M * H * 8);
+        if (s->beta) memcpy(s->beta, &hbeta[o], M * H * 8);
+        if (s->SigmaA) memcpy(s->SigmaA, &hSA[p * HH], HH * 8);
+        if (s->YHat) memcpy(s->YHat, &hYH[(size_t)moff[p] * L], M * L * 8);
+        if (s->SigmaATVec_blocks) memcpy(s->SigmaATVec_blocks, &hblk[o * H], M * HH * 8);
+        s->sigmaHat = sc[0]; s->zeta = sc[2];
+        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) {
+            s->alpha0 = sc[11]; s->alpha1 = sc[12];
+            if (s->alpha) { s->alpha[0] = sc[11]; s->alpha[1] = sc[12]; }
+            const size_t h0 = (size_t)H0, h1 = (size_t)(H - H0);
+            for (size_t m = 0; m < M; ++m) for (size_t h = 0; h < (size_t)H; ++h) {
+                const bool g1 = h >= h0;
+                const size_t k = g1 ? m * h1 + (h - h0) : m * h0 + h;
+                if (g1) { if (s->CA1) s->CA1[k] = hCA[o + m * H + h]; if (s->beta1) s->beta1[k] = hbeta[o + m * H + h]; }
+                else { if (s->CA0) s->CA0[k] = hCA[o + m * H + h]; if (s->beta0) s->beta0[k] = hbeta[o + m * H + h]; }
+                if (g1) { if (s->A1Hat) s->A1Hat[(h - h0) * M + m] = hA[o + m * H + h]; }
+                else { if (s->A0Hat) s->A0Hat[h * M + m] = hA[o + m * H + h]; }
+            }
+        }
+    }
+    if (failed) { set_error("batched vbls: a per-column precision matrix was not positive definite (NaN written)"); return -2; }
+    return 0;
+}
+
+extern "C" int vbmf_b200_batched_vbls(vbmf_b200_ctx* c, int kind, int64_t nprob, const double* const* Y, void* const* states,
+                                      int64_t niter, int flags) {
+    if (!c || (nprob > 0 && (!Y || !states))) { set_error("batched vbls: NULL argument"); return -1; }
+    if (kind == VBMF_B200_SPARSE) return batched_vbls_impl<vbmf_b200_sparse_state>(c, kind, nprob, Y, states, niter, flags);
+    if (kind == VBMF_B200_DUAL) return batched_vbls_impl<vbmf_b200_dual_state>(c, kind, nprob, Y, states, niter, flags);
+    set_error("batched vbls exists for vbmf_sparse / vbmf_dual parameters only");
+    return -1;
 }

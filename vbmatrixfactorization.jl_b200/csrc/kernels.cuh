@@ -82,4 +82,8 @@ int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int p
 int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int rank, double noise, uint64_t seed);
 int k_randn(cudaStream_t st, double* x, size_t n, uint64_t seed, uint64_t stream);
 
+// K11: batched one-CTA-per-problem vbls! (csrc/batched.cu)
+struct BatchDesc;
+int k_batched_vbls(cudaStream_t st, const BatchDesc& bd);
+
 }  // namespace vb
