@@ -145,6 +145,11 @@ int vbmf_b200_attach_Y(vbmf_b200_ctx* ctx, const double* Y, int64_t L, int64_t M
 /* Low-rank-plus-noise Y generated on the device (Philox4x32-10, keyed by the global column so any sharding agrees). */
 int vbmf_b200_synth_Y(vbmf_b200_ctx* ctx, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset, int rank,
                       double noise, uint64_t seed);
+/* preprocess(Y, lambda) (src/util.jl:73-87 incl. scaleY :36-53) applied to the attached Y on the device: row-standardise over
+ * ALL columns (all shards), |var| <= 1e-15 -> 1, |Y - mean| <= 1e-8 -> 0, drop rows with sum(abs) < 1e-5, multiply by lambda.
+ * The resident Y is replaced (L may shrink); L_out = new row count, used_rows (capacity L, 1-based, may be NULL) = kept rows.
+ * Solvers created before this call are invalid. */
+int vbmf_b200_preprocess_Y(vbmf_b200_ctx* ctx, double lambda, int64_t* L_out, int64_t* used_rows);
 int vbmf_b200_download_Y(vbmf_b200_ctx* ctx, double* Y_out, int64_t ldY);
 int vbmf_b200_trYTY(vbmf_b200_ctx* ctx, double* out);          /* traceXTY(Y, Y), src/vbmf_sparse.jl:150 */
 int vbmf_b200_ctx_sync(vbmf_b200_ctx* ctx);

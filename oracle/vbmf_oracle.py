@@ -89,6 +89,28 @@ def delta(new, old, mode="spectral"):
         return float(np.float64(matnorm(old - new, mode)) / np.float64(matnorm(old, mode)))
 
 
+def scaleY(Y):
+    """src/util.jl:36-53: row-standardise (corrected variance), numerical-zero guards 1e-15 / 1e-8."""
+    Y = np.asarray(Y, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu = Y.mean(axis=1, keepdims=True)
+        den = Y.var(axis=1, ddof=1, keepdims=True)
+        den[np.abs(den) <= 1e-15] = 1.0
+        den[den == 0.0] = 1.0
+        den = np.sqrt(den)
+        nom = Y - mu
+        nom[np.abs(nom) <= 1e-8] = 0.0
+        return nom / den
+
+
+def preprocess(Y, lam):
+    """src/util.jl:73-87: scaleY, drop rows with sum(abs) < 1e-5, multiply by lambda.  Returns (Y_out, used_rows 1-based)."""
+    sY = scaleY(Y)
+    rowsums = np.sum(np.abs(sY), axis=1)
+    used = np.nonzero(rowsums >= 1e-5)[0]
+    return lam * sY[used, :], used + 1
+
+
 def traceXTY(X, Y):
     """src/util.jl:104-106."""
     return float(np.sum(X * Y))

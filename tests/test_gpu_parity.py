@@ -303,3 +303,28 @@ def test_vbls_batched(G, ctx, kind, full_cov, H):
         vo.vbls(Y, p, niter, full_cov=full_cov)
         G.compare(q, p, TOL, fields)
         assert G.rel(q.YHat, p.YHat) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ preprocess / scaleY (N3)
+def test_preprocess(G, ctx):
+    """src/util.jl:36-87: row standardisation with the 1e-15 / 1e-8 guards, removal of near-constant rows, times lambda."""
+    rng = np.random.default_rng(8)
+    L, M = 57, 333
+    Y = rng.standard_normal((L, M)) * rng.uniform(0.1, 50.0, (L, 1)) + rng.uniform(-5, 5, (L, 1))
+    Y[7, :] = 3.25            # constant row -> variance 0 -> scaled row is all zeros -> dropped
+    Y[20, :] = 0.0
+    Y[33, :] = 1.0 + 1e-12 * rng.standard_normal(M)   # |Y - mu| <= 1e-8 -> zeroed -> dropped
+    ref, used = vo.preprocess(Y, 10.0)
+    out = G.vb.preprocess(np.asfortranarray(Y), 10.0, ctx=ctx)
+    assert out.shape == ref.shape == (L - 3, M)
+    assert G.rel(out, ref) < 1e-12
+    # and the resident matrix is the processed one
+    assert abs(ctx.trYTY() - float(np.sum(ref * ref))) <= 1e-11 * float(np.sum(ref * ref))
+    rows = None
+    ctx.attach(np.asfortranarray(Y), force=True)
+    rows = ctx.preprocess(10.0)
+    assert np.array_equal(rows, used)
+    # no row dropped: in-place path
+    Y2 = rng.standard_normal((16, 40))
+    ref2, used2 = vo.preprocess(Y2, 2.0)
+    assert G.rel(G.vb.preprocess(np.asfortranarray(Y2), 2.0, ctx=ctx), ref2) < 1e-12 and used2.size == 16

@@ -103,3 +103,14 @@ def test_q2_repeat_inner():
     j = np.arange(1, M * H + 1)
     src = np.where(j <= H, j, np.ceil((j - H) / (M - 1))).astype(int) - 1
     assert np.array_equal(expect, d[src])
+
+
+def test_preprocess_guards():
+    """src/util.jl:36-87: constant rows survive scaleY as zeros and are dropped by preprocess; lambda multiplies the rest."""
+    rng = np.random.default_rng(0)
+    Y = rng.standard_normal((6, 50))
+    Y[2, :] = 4.0
+    out, used = vo.preprocess(Y, 10.0)
+    assert list(used) == [1, 2, 4, 5, 6] and out.shape == (5, 50)
+    s = out / 10.0
+    assert np.allclose(s.mean(axis=1), 0.0, atol=1e-12) and np.allclose(s.var(axis=1, ddof=1), 1.0)

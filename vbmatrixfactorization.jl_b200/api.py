@@ -27,7 +27,7 @@ __all__ = [
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
-    "vbls_", "vbls_batched_", "VBMFError",
+    "vbls_", "vbls_batched_", "preprocess", "VBMFError",
 ]
 
 VBMFError = L_.VBMFError
@@ -110,6 +110,15 @@ class Context:
         L_.check(self.lib.vbmf_b200_synth_Y(self.h, Lr, M_local, Mg, col_offset, rank, noise, seed))
         self._key = ("synth", Lr, M_local, Mg, col_offset, rank, noise, seed)
         self.L, self.M, self.M_global, self.col_offset = Lr, M_local, Mg, col_offset
+
+    def preprocess(self, lam):
+        """`preprocess(Y, lambda)` (src/util.jl:73-87) on the resident Y; returns the kept rows (1-based)."""
+        rows = np.zeros(max(self.L, 1), dtype=np.int64)
+        Ln = C.c_int64()
+        L_.check(self.lib.vbmf_b200_preprocess_Y(self.h, float(lam), C.byref(Ln), rows.ctypes.data_as(L_.p_i64)))
+        self.L = Ln.value
+        self._key = None
+        return rows[:Ln.value].copy()
 
     def download_Y(self):
         Y = np.empty((self.L, self.M), order="F")
@@ -647,3 +656,18 @@ def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, k
     for p, st in zip(params_list, structs):
         _readback(p, st)
     return [p.AHat for p in params_list]
+
+
+def preprocess(Y, lam, verb=False, ctx=None):
+    """`preprocess(Y, lambda; verb)` src/util.jl:73-87: returns the scaled matrix with near-constant rows removed, times lambda.
+    The result also stays resident on the device (ctx), ready for the solvers."""
+    ctx = ctx or default_context()
+    Y = _f(Y)
+    ctx.attach(Y, force=True)
+    L0 = ctx.L
+    rows = ctx.preprocess(lam)
+    if verb:
+        print("Original problem size: %d rows, %d rows not relevant and are not used." % (L0, L0 - rows.size))
+    out = ctx.download_Y()
+    ctx._key = Context._fingerprint(out) + (None, 0)     # the resident matrix IS `out`: the next solver call need not upload it
+    return out

@@ -240,6 +240,59 @@ extern "C" int vbmf_b200_synth_Y(vbmf_b200_ctx* c, int64_t L, int64_t M_local, i
     return ctx_finish_Y(c);
 }
 
+extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* L_out, int64_t* used_rows) {
+    if (!c || !c->have_Y) { set_error("preprocess_Y: no Y attached"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    const int L = c->L, M = c->Mloc;
+    cudaStream_t st = c->st;
+    double *mu = nullptr, *den = nullptr, *rs = nullptr;
+    VB_CUDA_OK(cudaMalloc(&mu, (size_t)L * 8));
+    VB_CUDA_OK(cudaMalloc(&den, (size_t)L * 8));
+    VB_CUDA_OK(cudaMalloc(&rs, (size_t)L * 8));
+    int rc = 0;
+    // mean(Y, 2) and var(Y, 2) over ALL columns (all-reduced across shards), src/util.jl:38-39
+    rc = k_row_pass(st, c->Y, c->ldY, L, M, 0, nullptr, nullptr, c->stats_part, mu);
+    if (!rc) rc = ctx_allreduce(c, mu, (size_t)L);
+    if (!rc) rc = k_finish_stats(st, mu, L, (double)c->Mglob, 0);
+    if (!rc) rc = k_row_pass(st, c->Y, c->ldY, L, M, 1, mu, nullptr, c->stats_part, den);
+    if (!rc) rc = ctx_allreduce(c, den, (size_t)L);
+    if (!rc) rc = k_finish_stats(st, den, L, (double)c->Mglob, 1);
+    // scale in place, rowsums = sum(abs(sY), 2), src/util.jl:75-76
+    if (!rc) rc = k_row_pass(st, c->Y, c->ldY, L, M, 2, mu, den, c->stats_part, rs);
+    if (!rc) rc = ctx_allreduce(c, rs, (size_t)L);
+    std::vector<double> hrs((size_t)L);
+    if (!rc && cudaMemcpyAsync(hrs.data(), rs, (size_t)L * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("preprocess_Y: copy failed"); rc = -1; }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("preprocess_Y: sync failed"); rc = -1; }
+    cudaFree(mu); cudaFree(den); cudaFree(rs);
+    if (rc) return rc;
+    std::vector<int> rows;
+    for (int l = 0; l < L; ++l) if (hrs[l] >= 1e-5) rows.push_back(l);      // used_rows[rowsums .>= 1e-5], :79
+    const int Lnew = (int)rows.size();
+    if (Lnew == 0) { set_error("preprocess_Y: every row is constant, nothing left"); return -1; }
+    if (Lnew == L) {
+        if (k_scale_all(st, c->Y, (size_t)c->ldY * (size_t)std::max(M, 1), lambda)) return -1;
+    } else {
+        const int ldn = (Lnew + 1) & ~1;
+        double* Yn = nullptr;
+        int* drows = nullptr;
+        const size_t bytes = std::max<size_t>((size_t)ldn * (size_t)std::max(M, 1) * 8, 16);
+        VB_CUDA_OK(cudaMalloc(&Yn, bytes));
+        VB_CUDA_OK(cudaMalloc(&drows, (size_t)Lnew * 4));
+        VB_CUDA_OK(cudaMemsetAsync(Yn, 0, bytes, st));
+        VB_CUDA_OK(cudaMemcpyAsync(drows, rows.data(), (size_t)Lnew * 4, cudaMemcpyHostToDevice, st));
+        if (k_compact_rows(st, c->Y, c->ldY, Yn, ldn, drows, Lnew, M, lambda)) return -1;
+        VB_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(drows);
+        cudaFree(c->Y); cudaFree(c->rowY2); cudaFree(c->stats_part);
+        c->Y = Yn; c->L = Lnew; c->ldY = ldn;
+        VB_CUDA_OK(cudaMalloc(&c->rowY2, (size_t)Lnew * 8));
+        VB_CUDA_OK(cudaMalloc(&c->stats_part, (size_t)(MAX_PARTS / 2) * Lnew * 8));
+    }
+    if (L_out) *L_out = Lnew;
+    if (used_rows) for (int k = 0; k < Lnew; ++k) used_rows[k] = rows[k] + 1;
+    return ctx_finish_Y(c);
+}
+
 extern "C" int vbmf_b200_download_Y(vbmf_b200_ctx* c, double* out, int64_t ldY) {
     if (!c || !c->have_Y) { set_error("download_Y: no Y attached"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));

@@ -105,6 +105,82 @@ int k_y_stats(cudaStream_t st, const Dev& d, double* out_tr) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- N3: preprocess / scaleY
+// src/util.jl:36-53 (scaleY) and :73-87 (preprocess) on the resident shard: row mean and corrected variance over ALL columns
+// (the caller all-reduces the per-row sums across shards), |var| <= 1e-15 -> 1, |Y - mu| <= 1e-8 -> 0, divide, then drop rows
+// whose sum(abs) < 1e-5 and multiply by lambda.  mode 0: out[l] = sum_m Y   1: out[l] = sum_m (Y - mu_l)^2
+// mode 2: Y <- scaled in place, out[l] = sum_m |Y_scaled|.  Fixed-order partials over column blocks.
+__global__ void __launch_bounds__(128) row_pass_kernel(double* __restrict__ Y, int ldY, int L, int M, int cols_per_blk, int mode,
+                                                       const double* __restrict__ mu, const double* __restrict__ den,
+                                                       double* __restrict__ part) {
+    const int m0 = blockIdx.y * cols_per_blk, m1 = min(M, m0 + cols_per_blk);
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double s = 0.0;
+    const double mul = mode ? mu[l] : 0.0, dl = (mode == 2) ? den[l] : 1.0;
+    for (int m = m0; m < m1; ++m) {
+        double* p = Y + (size_t)m * ldY + l;
+        const double v = *p;
+        if (mode == 0) s += v;
+        else if (mode == 1) { const double c = v - mul; s = fma(c, c, s); }
+        else {
+            double c = v - mul;
+            if (fabs(c) <= 1e-8) c = 0.0;
+            c = c / dl;
+            *p = c;
+            s += fabs(c);
+        }
+    }
+    part[(size_t)blockIdx.y * L + l] = s;
+}
+__global__ void finish_stats_kernel(double* mu_or_den, int L, double n, int mode) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    if (mode == 0) mu_or_den[l] = mu_or_den[l] / n;                 // mean(Y, 2)
+    else {                                                          // var(Y, 2) -> guarded sqrt
+        double d = mu_or_den[l] / (n - 1.0);
+        if (fabs(d) <= 1e-15) d = 1.0;
+        if (d == 0.0) d = 1.0;
+        mu_or_den[l] = sqrt(d);
+    }
+}
+// out[k, m] = lambda * Y[rows[k], m]   (row compaction into a fresh buffer)
+__global__ void compact_rows_kernel(const double* __restrict__ Y, int ldY, double* __restrict__ out, int ldo, const int* __restrict__ rows,
+                                    int Lnew, int M, double lambda) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (k < Lnew && m < M) out[(size_t)m * ldo + k] = lambda * Y[(size_t)m * ldY + rows[k]];
+}
+__global__ void scale_all_kernel(double* Y, size_t n, double lambda) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) Y[i] *= lambda;
+}
+int k_row_pass(cudaStream_t st, double* Y, int ldY, int L, int M, int mode, const double* mu, const double* den, double* part, double* out) {
+    const int nby = std::max(1, std::min(MAX_PARTS / 2, cdiv(std::max(M, 1), 64)));
+    const int cpb = cdiv(std::max(M, 1), nby);
+    dim3 grid(cdiv(L, 128), nby);
+    row_pass_kernel<<<grid, 128, 0, st>>>(Y, ldY, L, M, cpb, mode, mu, den, part);
+    VB_LAUNCH_OK();
+    return sum_partials(st, part, nby, (size_t)L, (size_t)L, out, nullptr);
+}
+int k_finish_stats(cudaStream_t st, double* v, int L, double n, int mode) {
+    finish_stats_kernel<<<cdiv(L, 256), 256, 0, st>>>(v, L, n, mode);
+    VB_LAUNCH_OK();
+    return 0;
+}
+int k_compact_rows(cudaStream_t st, const double* Y, int ldY, double* out, int ldo, const int* rows, int Lnew, int M, double lambda) {
+    if (Lnew <= 0 || M <= 0) return 0;
+    dim3 grid(cdiv(Lnew, 128), M);
+    compact_rows_kernel<<<grid, 128, 0, st>>>(Y, ldY, out, ldo, rows, Lnew, M, lambda);
+    VB_LAUNCH_OK();
+    return 0;
+}
+int k_scale_all(cudaStream_t st, double* Y, size_t n, double lambda) {
+    if (n == 0) return 0;
+    scale_all_kernel<<<2368, 256, 0, st>>>(Y, n, lambda);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- Gram matrices
 // G[a][b] = sum_i w_i^wpow X(i,a) X(i,b).  AMAT: X is [n][H] row-major (AHat rows); else X is [H][ld] (BHat-like).
 // Used for BHat'BHat, AHat'AHat (src/vbmf.jl:96,110), B'diag(sv)B (src/vbmf_sparse.jl:182), norm2(B[:,h].*sv) (:211),

@@ -82,6 +82,12 @@ int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int p
 int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int rank, double noise, uint64_t seed);
 int k_randn(cudaStream_t st, double* x, size_t n, uint64_t seed, uint64_t stream);
 
+// N3: preprocess / scaleY on the resident shard (src/util.jl:36-87)
+int k_row_pass(cudaStream_t st, double* Y, int ldY, int L, int M, int mode, const double* mu, const double* den, double* part, double* out);
+int k_finish_stats(cudaStream_t st, double* v, int L, double n, int mode);
+int k_compact_rows(cudaStream_t st, const double* Y, int ldY, double* out, int ldo, const int* rows, int Lnew, int M, double lambda);
+int k_scale_all(cudaStream_t st, double* Y, size_t n, double lambda);
+
 // K11: batched one-CTA-per-problem vbls! (csrc/batched.cu)
 struct BatchDesc;
 int k_batched_vbls(cudaStream_t st, const BatchDesc& bd);
