@@ -142,6 +142,9 @@ int vbmf_b200_ctx_destroy(vbmf_b200_ctx* ctx);
 /* Y: L x M_local column-major host matrix with leading dimension ldY (the argument `Y` of every reference function). */
 int vbmf_b200_attach_Y(vbmf_b200_ctx* ctx, const double* Y, int64_t L, int64_t M_local, int64_t ldY, int64_t M_global,
                        int64_t col_offset);
+/* Declare the problem geometry without data, for the step functions that take no Y in the reference (updateCA!(params),
+ * updateCB!(params), updateAlpha0x!, updateYHat!): solvers can be created, steps that contract with Y return an error. */
+int vbmf_b200_set_shape(vbmf_b200_ctx* ctx, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset);
 /* Low-rank-plus-noise Y generated on the device (Philox4x32-10, keyed by the global column so any sharding agrees). */
 int vbmf_b200_synth_Y(vbmf_b200_ctx* ctx, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset, int rank,
                       double noise, uint64_t seed);

@@ -328,3 +328,64 @@ def test_preprocess(G, ctx):
     Y2 = rng.standard_normal((16, 40))
     ref2, used2 = vo.preprocess(Y2, 2.0)
     assert G.rel(G.vb.preprocess(np.asfortranarray(Y2), 2.0, ctx=ctx), ref2) < 1e-12 and used2.size == 16
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("L,M,H", [(1, 5, 1), (7, 1, 2), (3, 2, 3), (5, 9, 1), (2, 2, 2)])
+def test_degenerate_shapes(G, ctx, L, M, H):
+    """Smallest shapes the reference accepts: single row / single column (Q2's repeat(inner = 0)) / rank one."""
+    Y = synth(L, M, 1, seed=L * 10 + M)
+    Yf = np.asfortranarray(Y)
+    p = vo.vbmf_init(Y, H, rng=np.random.default_rng(1))
+    q = G.to_gpu_params(p)
+    vo.vbmf_run(Y, p, 4, eps=0.0, est_covs=True, est_var=True)
+    G.vb.vbmf_(Yf, q, 4, eps=0.0, est_covs=True, est_var=True, ctx=ctx)
+    G.compare(q, p, 1e-9)
+    for full_cov in (False, True):
+        ps = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(2))
+        qs = G.to_gpu_params(ps)
+        vo.vbmf_sparse_run(Y, ps, 3, eps=0.0, full_cov=full_cov)
+        G.vb.vbmf_sparse_(Yf, qs, 3, eps=0.0, full_cov=full_cov, ctx=ctx)
+        G.compare(qs, ps, 1e-9)
+
+
+def test_zero_iterations_and_eps_edge(G, ctx):
+    """niter = 0 leaves the state untouched (d = eps + 1); eps = Inf never enters the loop (eps + 1 > eps is false)."""
+    Y = synth(12, 30, 2, seed=3)
+    p = vo.vbmf_init(Y, 3, rng=np.random.default_rng(1))
+    for niter, eps in ((0, 1e-6), (10, float("inf"))):
+        q = G.to_gpu_params(p)
+        G.vb.vbmf_(np.asfortranarray(Y), q, niter, eps=eps, est_covs=True, est_var=True, ctx=ctx)
+        assert q.iterations == 0
+        assert np.array_equal(q.AHat, p.AHat) and np.array_equal(q.BHat, p.BHat) and q.sigma2 == p.sigma2
+        assert G.rel(q.YHat, p.BHat @ p.AHat.T) < 1e-14      # updateYHat! still runs after the loop
+
+
+def test_dual_prior_steps(G, ctx):
+    """updateAlpha00!/01!, updateBeta00!/01! called one by one (src/vbmf_dual.jl:393-434) after a few iterations."""
+    Y = synth(20, 64, 2, seed=5)
+    p = vo.vbmf_dual_init(Y, 4, 2, rng=np.random.default_rng(3))
+    vo.vbmf_dual_run(Y, p, 3, eps=0.0, est_priors=False)
+    q = G.to_gpu_params(p)
+    for fo, fg in ((vo.dual_updateAlpha00, G.vb.updateAlpha00_), (vo.dual_updateAlpha01, G.vb.updateAlpha01_),
+                   (vo.dual_updateBeta00, G.vb.updateBeta00_), (vo.dual_updateBeta01, G.vb.updateBeta01_)):
+        fo(p)
+        fg(q, ctx=ctx)
+        G.compare(q, p, TOL, ["alpha00", "alpha01", "beta00", "beta01", "CA", "beta"])
+
+
+def test_error_paths(G, ctx):
+    Y = np.asfortranarray(synth(8, 10, 2, seed=1))
+    with pytest.raises(G.vb.VBMFError, match="outside the supported range"):
+        G.vb.vbmf_(Y, G.vb.vbmf_init(Y, 129), 1, ctx=ctx)
+    p = G.vb.vbmf_init(Y, 2)
+    p.M = 11
+    with pytest.raises((G.vb.VBMFError, ValueError)):
+        G.vb.vbmf_(Y, p, 1, ctx=ctx)
+    with pytest.raises(G.vb.VBMFError, match="no lowerBound"):
+        G.vb.lowerBound(Y, G.vb.vbmf_init(Y, 2), ctx=ctx)
+    # a non positive definite precision (negative prior covariance) must surface as NaN + ended loop, not as garbage
+    q = G.vb.vbmf_init(Y, 2, rng=np.random.default_rng(0))
+    q.invCA = np.asfortranarray(-1e6 * np.eye(2))
+    G.vb.vbmf_(Y, q, 5, eps=0.0, ctx=ctx)
+    assert q.iterations == 1 and np.isnan(q.d) and np.isnan(q.AHat).all()

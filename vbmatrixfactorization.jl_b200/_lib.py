@@ -54,6 +54,7 @@ SYMBOLS = {
     "vbmf_b200_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "vbmf_b200_ctx_destroy": (C.c_int, [C.c_void_p]),
     "vbmf_b200_attach_Y": (C.c_int, [C.c_void_p, p_f64, c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "vbmf_b200_set_shape": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, c_i64]),
     "vbmf_b200_synth_Y": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_int, c_f64, C.c_uint64]),
     "vbmf_b200_preprocess_Y": (C.c_int, [C.c_void_p, c_f64, p_i64, p_i64]),
     "vbmf_b200_download_Y": (C.c_int, [C.c_void_p, p_f64, c_i64]),

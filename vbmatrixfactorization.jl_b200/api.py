@@ -105,6 +105,13 @@ class Context:
         self._key = key
         self.L, self.M, self.M_global, self.col_offset = Lr, M, Mg, col_offset
 
+    def set_shape(self, Lr, M_local, M_global=None, col_offset=0):
+        """Geometry only (no data): enough for the step functions that take no Y in the reference."""
+        Mg = M_local if M_global is None else M_global
+        L_.check(self.lib.vbmf_b200_set_shape(self.h, Lr, M_local, Mg, col_offset))
+        self._key = None
+        self.L, self.M, self.M_global, self.col_offset = Lr, M_local, Mg, col_offset
+
     def synth(self, Lr, M_local, M_global=None, col_offset=0, rank=8, noise=0.1, seed=20260101):
         Mg = M_local if M_global is None else M_global
         L_.check(self.lib.vbmf_b200_synth_Y(self.h, Lr, M_local, Mg, col_offset, rank, noise, seed))
@@ -522,8 +529,16 @@ def vbmf_dual(Y, params_in, niter, **kw):
 
 
 # ----------------------------------------------------------------------------------------------------------- step functions
+def _shape_for(params, ctx):
+    """Y-less steps (updateCA!(params), ...): make sure the context's geometry matches the params."""
+    ctx = ctx or default_context()
+    if (ctx.L, ctx.M) != (params.L, params.M):
+        ctx.set_shape(params.L, params.M)
+    return ctx
+
+
 def _one_step(Y, params, step, flags=0, ctx=None, want_yhat=False):
-    ctx = _ctx_for(Y, ctx)
+    ctx = _ctx_for(Y, ctx) if Y is not None else _shape_for(params, ctx)
     s = Solver(ctx, params, keep_blocks=bool(flags & L_.FULL_COV) and getattr(params, "SigmaATVec_blocks", None) is not None)
     try:
         s.upload(params)
@@ -570,13 +585,11 @@ def updateYHat_(params, ctx=None):
 
 
 def _prior_step(params, step, ctx):
-    ctx = ctx or default_context()
+    ctx = _shape_for(params, ctx)
     s = Solver(ctx, params)
     try:
         s.upload(params)
-        # the sums the root needs come from the current CA/beta vectors; recompute them without touching the state
-        s.step(L_.STEP_UPDATE_CA, 0)
-        s.step(step, 0)
+        s.step(step, 0)          # the library sums the current CA / beta vectors itself, the state stays untouched
         s.download(params)
     finally:
         s.close()

@@ -232,6 +232,21 @@ extern "C" int vbmf_b200_attach_Y(vbmf_b200_ctx* c, const double* Y, int64_t L, 
     return ctx_finish_Y(c);
 }
 
+extern "C" int vbmf_b200_set_shape(vbmf_b200_ctx* c, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset) {
+    if (!c) { set_error("set_shape: NULL ctx"); return -1; }
+    if (L <= 0 || M_local < 0 || M_global < M_local || col_offset < 0 || col_offset + M_local > M_global || L > 0x7fffff00LL || M_global > 0x7fffff00LL) {
+        set_error("set_shape: bad geometry"); return -1;
+    }
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    ctx_free_Y(c);
+    c->L = (int)L; c->Mloc = (int)M_local; c->Mglob = (int)M_global; c->moff = (int)col_offset;
+    c->ldY = (int)((L + 1) & ~1LL);
+    c->trYTY = nan("");
+    c->have_Y = true;          // geometry only: Y stays NULL, steps that contract with Y refuse to run
+    return 0;
+}
+
 extern "C" int vbmf_b200_synth_Y(vbmf_b200_ctx* c, int64_t L, int64_t M_local, int64_t M_global, int64_t col_offset,
                                  int rank, double noise, uint64_t seed) {
     if (!c) { set_error("synth_Y: NULL ctx"); return -1; }
@@ -241,7 +256,7 @@ extern "C" int vbmf_b200_synth_Y(vbmf_b200_ctx* c, int64_t L, int64_t M_local, i
 }
 
 extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* L_out, int64_t* used_rows) {
-    if (!c || !c->have_Y) { set_error("preprocess_Y: no Y attached"); return -1; }
+    if (!c || !c->have_Y || !c->Y) { set_error("preprocess_Y: no Y attached"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     const int L = c->L, M = c->Mloc;
     cudaStream_t st = c->st;
@@ -294,7 +309,7 @@ extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* 
 }
 
 extern "C" int vbmf_b200_download_Y(vbmf_b200_ctx* c, double* out, int64_t ldY) {
-    if (!c || !c->have_Y) { set_error("download_Y: no Y attached"); return -1; }
+    if (!c || !c->have_Y || !c->Y) { set_error("download_Y: no Y attached"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     if (c->Mloc > 0)
         VB_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ldY * 8, c->Y, (size_t)c->ldY * 8, (size_t)c->L * 8, (size_t)c->Mloc,
@@ -644,6 +659,7 @@ extern "C" int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state
 static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
     vbmf_b200_ctx* c = s->c;
     const Dev& d = s->d;
+    if (c->Y == nullptr) { set_error("this step contracts with Y: attach Y first (the context only holds its shape)"); return -1; }
     prof_mark(c, c->ev_k1);
     int rc;
     if (c->simt) rc = launch_gemm_ytb_simt(c->st, d.Y, d.ldY, scaledB ? d.Bs : d.B, d.ldB, d.P, d.Mloc, d.L, d.H, d.H, d.sc);
@@ -659,6 +675,7 @@ static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
 static int enq_k2(vbmf_b200_solver* s) {
     vbmf_b200_ctx* c = s->c;
     const Dev& d = s->d;
+    if (c->Y == nullptr) { set_error("this step contracts with Y: attach Y first (the context only holds its shape)"); return -1; }
     prof_mark(c, c->ev_k2);
     int rc;
     if (s->k2_simt) rc = launch_gemm_ya_simt(c->st, d.Y, d.ldY, d.A, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc);
@@ -781,8 +798,12 @@ extern "C" int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags) {
         case VBMF_B200_STEP_UPDATE_ALPHA00: case VBMF_B200_STEP_UPDATE_ALPHA01:
         case VBMF_B200_STEP_UPDATE_BETA00: case VBMF_B200_STEP_UPDATE_BETA01:
             if (d.kind != KIND_DUAL) { set_error("hyper-prior steps exist for vbmf_dual only"); return -1; }
-            if (!s->extras_valid) { set_error("call updateCA! before the hyper-prior updates (they need sum(CA_g), sum(log(beta_g)))"); return -1; }
-            rc = k_prior_only(st, d, step - VBMF_B200_STEP_UPDATE_ALPHA00);
+            if (!s->extras_valid) {     // sum(CA_g), sum(log(beta_g)) of the CURRENT vectors; CA / beta stay as uploaded
+                rc = k_update_CA(st, d, 1);
+                if (!rc) rc = ctx_allreduce(s->c, d.packed + packed_ex(d), 8);
+                s->extras_valid = true;
+            }
+            if (!rc) rc = k_prior_only(st, d, step - VBMF_B200_STEP_UPDATE_ALPHA00);
             break;
         default: set_error("unknown step %d", step); return -1;
     }
@@ -878,7 +899,7 @@ extern "C" int vbmf_b200_solver_yhat(vbmf_b200_solver* s, double* YHat, int64_t 
 
 // ---- K1 / K2 on their own ------------------------------------------------------------------------------------------------
 extern "C" int vbmf_b200_gemm_YtB(vbmf_b200_ctx* c, const double* B, int64_t H, double* P) {
-    if (!c || !c->have_Y || !B || !P) { set_error("gemm_YtB: bad argument"); return -1; }
+    if (!c || !c->have_Y || !c->Y || !B || !P) { set_error("gemm_YtB: bad argument"); return -1; }
     if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     const int ldB = (c->L + 1) & ~1;
@@ -911,7 +932,7 @@ extern "C" int vbmf_b200_gemm_YtB(vbmf_b200_ctx* c, const double* B, int64_t H, 
 }
 
 extern "C" int vbmf_b200_gemm_YA(vbmf_b200_ctx* c, const double* A, int64_t H, double* Q) {
-    if (!c || !c->have_Y || !A || !Q) { set_error("gemm_YA: bad argument"); return -1; }
+    if (!c || !c->have_Y || !c->Y || !A || !Q) { set_error("gemm_YA: bad argument"); return -1; }
     if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     const int ldQ = (c->L + 1) & ~1;

@@ -18,7 +18,8 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int nparts,
     if (sc != nullptr && !sc->active) return;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + e];
+#pragma unroll 8
+        for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + e];   // loads batched, sum order unchanged
         out[e] = s;
     }
 }
@@ -678,7 +679,7 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
 // sparse: beta = beta0 + 1/2*(a.^2 + s);  CA = alpha ./ beta                        src/vbmf_sparse.jl:284-288
 // dual  : alpha_g = alpha0g + 1/2; beta_g = beta0g + 1/2*(a_g.^2 + s_g); CA_g = alpha_g ./ beta_g, group g = (h > H0)
 //         plus the sums the hyper-prior updates need: sum(CA_g), sum(log(beta_g))   src/vbmf_dual.jl:322-351,393-434
-__global__ void __launch_bounds__(256) update_CA_kernel(Dev d) {
+__global__ void __launch_bounds__(256) update_CA_kernel(Dev d, int sums_only) {
     ACTIVE_OR_RETURN(d);
     __shared__ double red[32];
     Scalars* sc = d.sc;
@@ -693,11 +694,15 @@ __global__ void __launch_bounds__(256) update_CA_kernel(Dev d) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int h = (int)(e % H);
         const bool g1 = dual && h >= d.H0;
-        const double a = d.A[e];
-        const double beta = (g1 ? b1 : b0) + 0.5 * (a * a + d.sdiag[e]);
-        const double ca = (g1 ? a1 : a0) / beta;
-        d.beta[e] = beta;
-        d.CAv[e] = ca;
+        double beta, ca;
+        if (sums_only) { beta = d.beta[e]; ca = d.CAv[e]; }      // hyper-prior steps right after an upload: state untouched
+        else {
+            const double a = d.A[e];
+            beta = (g1 ? b1 : b0) + 0.5 * (a * a + d.sdiag[e]);
+            ca = (g1 ? a1 : a0) / beta;
+            d.beta[e] = beta;
+            d.CAv[e] = ca;
+        }
         if (dual) {
             if (g1) { sca1 += ca; slb1 += log(beta); } else { sca0 += ca; slb0 += log(beta); }
         }
@@ -708,14 +713,14 @@ __global__ void __launch_bounds__(256) update_CA_kernel(Dev d) {
         if (threadIdx.x == 0) {
             double* p = d.part + (size_t)blockIdx.x * 4;
             p[0] = sca0; p[1] = sca1; p[2] = slb0; p[3] = slb1;
-            if (blockIdx.x == 0) { sc->alpha_g0 = a0; sc->alpha_g1 = a1; }
+            if (blockIdx.x == 0 && !sums_only) { sc->alpha_g0 = a0; sc->alpha_g1 = a1; }
         }
     }
 }
-int k_update_CA(cudaStream_t st, const Dev& d) {
+int k_update_CA(cudaStream_t st, const Dev& d, int sums_only) {
     const long long n = (long long)d.Mloc * d.H;
     const int grid = std::max(1, (int)std::min<long long>((n + 1023) / 1024, MAX_PARTS));
-    update_CA_kernel<<<grid, 256, 0, st>>>(d);
+    update_CA_kernel<<<grid, 256, 0, st>>>(d, sums_only);
     VB_LAUNCH_OK();
     if (d.kind == KIND_DUAL) return sum_partials(st, d.part, grid, 4, 4, d.packed + packed_ex(d), d.sc);
     return 0;
@@ -824,6 +829,7 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
     const int H = d.H, n = 2 * H * H + 1;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         double s = 0.0;
+#pragma unroll 8
         for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * n + e];
         if (e < H * H) d.BtB[e] = s;
         else if (e < 2 * H * H) d.DtD[e - H * H] = s;
@@ -832,7 +838,7 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
 }
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H, dv = (flags & F_DIAG_VAR) ? 1 : 0;
-    const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), 148));
+    const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), H > 64 ? 148 : 296));
 #define BEPI(RR, TDD, TRR)                                                                                                   \
     {                                                                                                                        \
         static bool done = false;                                                                                            \

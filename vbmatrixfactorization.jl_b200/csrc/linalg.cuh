@@ -197,10 +197,18 @@ __device__ inline double sym_lambda_max(double* A, int ld, int n, double* work) 
         __syncthreads();
         const double beta = s_sc[0];
         if (beta != 0.0) {
-            if (t < m) {                          // p = beta * Asub * v   (column access: A is symmetric)
-                double s = 0.0;
-                for (int j = 0; j < m; ++j) s = fma(Asub[j * ld + t], v[j], s);
-                p[t] = beta * s;
+            // p = beta * Asub * v : TPR threads per row, partial dots combined by shuffles (column access: A is symmetric)
+            {
+                const int TPR = 8, row = t / TPR, sub = t % TPR;
+                for (int r0 = 0; r0 < m; r0 += nt / TPR) {
+                    const int i = r0 + row;
+                    double s = 0.0;
+                    if (i < m) for (int j = sub; j < m; j += TPR) s = fma(Asub[j * ld + i], v[j], s);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    if (i < m && sub == 0) p[i] = beta * s;
+                }
             }
             __syncthreads();
             if (warp == 0) {                      // K = beta/2 * p'v ; q = p - K v
@@ -211,9 +219,10 @@ __device__ inline double sym_lambda_max(double* A, int ld, int n, double* work) 
                 for (int i = lane; i < m; i += 32) p[i] -= K * v[i];
             }
             __syncthreads();
-            for (int e = t; e < m * m; e += nt) { // Asub -= v q' + q v'
-                const int i = e / m, j = e - i * m;
-                Asub[i * ld + j] -= v[i] * p[j] + p[i] * v[j];
+            // Asub -= v q' + q v'  (2-D thread mapping, no integer division)
+            for (int i = warp; i < m; i += nt / 32) {
+                const double vi = v[i], pi = p[i];
+                for (int j = lane; j < m; j += 32) Asub[i * ld + j] -= vi * p[j] + pi * v[j];
             }
         }
         if (t == 0) { dv[k] = A[k * ld + k]; ev[k] = s_sc[1]; }
@@ -232,18 +241,29 @@ __device__ inline double sym_lambda_max(double* A, int ld, int n, double* work) 
         s_lo = lo - pad; s_hi = hi + pad;
     }
     __syncthreads();
-    // multisection: count(x) = #eigenvalues < x ; lambda_max is where count steps from n-1 to n
-    const double tiny = 1e-300;
-    for (int iter = 0; iter < 16; ++iter) {
+    // multisection: count(x) = #eigenvalues < x = sign changes of the Sturm sequence p_0 = 1, p_1 = d_0 - x,
+    // p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1} (division-free; rescaled every 4 steps); lambda_max is where count
+    // steps from n-1 to n.  Every thread evaluates one sample point per round, the bracket shrinks (blockDim+1)-fold.
+    double* ev2 = v;                              // v, p are free after the tridiagonalisation
+    for (int i = t; i < n - 1; i += nt) ev2[i] = ev[i] * ev[i];
+    __syncthreads();
+    for (int iter = 0; iter < 12; ++iter) {
         const double lo = s_lo, hi = s_hi;
-        if (!(hi - lo > 4.5e-16 * fmax(fabs(lo), fabs(hi)))) break;
+        if (!(hi - lo > 2e-15 * fmax(fabs(lo), fabs(hi)))) break;
         const double x = lo + (hi - lo) * ((double)(t + 1) / (double)(nt + 1));
-        double q = dv[0] - x;
-        int cnt = q < 0.0;
+        double pm = 1.0, pc = dv[0] - x;
+        int cnt = pc < 0.0;
         for (int i = 1; i < n; ++i) {
-            if (q == 0.0) q = tiny;
-            q = dv[i] - x - ev[i - 1] * ev[i - 1] / q;
-            cnt += q < 0.0;
+            const double pn = (dv[i] - x) * pc - ev2[i - 1] * pm;
+            // sign change between pc and pn (a zero inherits the previous sign)
+            const double sc_ = (pc != 0.0) ? pc : pm;
+            cnt += ((pn < 0.0) != (sc_ < 0.0)) && (pn != 0.0);
+            pm = (pc != 0.0) ? pc : pm * 1e-300;          // keep the sign information of pm when pc vanished
+            pc = pn;
+            if ((i & 3) == 0) {                           // rescale: only ratios and signs matter
+                const double sc = fmax(fabs(pm), fabs(pc));
+                if (sc > 0.0 && sc < 1e308) { const double r = 1.0 / sc; pm *= r; pc *= r; }
+            }
         }
         if (t == 0) s_first = nt;
         __syncthreads();
