@@ -363,6 +363,11 @@ struct vbmf_b200_solver {
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
     int* h_flag = nullptr;   // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // The single-CTA tail of an iteration (norms, hyper-parameter updates, convergence test) runs on a side stream so that
+    // the next iteration's K1 -- which only needs BHat -- starts right behind the B epilogue instead of waiting for it.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_p = nullptr;
+    bool post_pending = false;
     Scalars h_sc;
 };
 
@@ -450,7 +455,10 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
     if (!s->k2_simt && d.Mloc > 0) rc |= make_tmap_2d(&s->tmA, d.A, (uint64_t)H, (uint64_t)d.Mloc, (uint64_t)H * 8, 16, 16);
     if (rc) { cudaFree(s->arena); delete s; return -1; }
     if (cudaMallocHost(&s->h_flag, 2 * sizeof(int)) != cudaSuccess || cudaEventCreateWithFlags(&s->ev[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_p, cudaEventDisableTiming) != cudaSuccess) {
         set_error("pinned flag / event allocation failed"); cudaFree(s->arena); delete s; return -1;
     }
     memset(&s->h_sc, 0, sizeof(Scalars));
@@ -462,6 +470,9 @@ extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
     if (!s) return 0;
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st);
+    if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->ev_p) cudaEventDestroy(s->ev_p);
     if (s->arena) cudaFree(s->arena);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     for (int i = 0; i < 2; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -704,19 +715,28 @@ static int copy_sa(vbmf_b200_solver* s) {   // step-level: SigmaA <- all-reduced
     VB_CUDA_OK(cudaMemcpyAsync(d.SigmaA, d.packed + packed_sa(d), (size_t)d.H * d.H * 8, cudaMemcpyDeviceToDevice, s->c->st));
     return 0;
 }
+// main stream waits for the side-stream tail (post) of the previous iteration
+static int wait_post(vbmf_b200_solver* s) {
+    if (s->post_pending) {
+        VB_CUDA_OK(cudaStreamWaitEvent(s->c->st, s->ev_p, 0));
+        s->post_pending = false;
+    }
+    return 0;
+}
 static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
     const Dev& d = s->d;
     cudaStream_t st = s->c->st;
-    if (!s->btb_valid && enq_gram_B(s, flags)) return -1;
+    if (!s->btb_valid) { if (wait_post(s) || enq_gram_B(s, flags)) return -1; }
     if (d.kind == KIND_DENSE) {
         // the epilogue sums the K1 slabs itself, multiplies by SigmaA/sigma2, masks, and leaves the local AHat'AHat in packed
-        if (k_dense_sigmaA(st, d) || enq_k1(s, false, false)) return -1;
+        // K1 needs BHat only; everything after it needs the previous iteration's sigma2 / invCA (post) -> wait there
+        if (enq_k1(s, false, false) || wait_post(s) || k_dense_sigmaA(st, d)) return -1;
         const bool slabs = !s->c->simt && s->S1 > 1;
         if (k_dense_A_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H)) return -1;
         s->ata_local = true;
     } else {
         const bool dv = (flags & F_DIAG_VAR) != 0;
-        if (enq_k1(s, dv)) return -1;
+        if (enq_k1(s, dv) || wait_post(s)) return -1;
         if (flags & F_FULL_COV) { if (k_sparse_A_full(st, d, flags)) return -1; }
         else { if (k_sparse_A_diag(st, d, flags)) return -1; }
         if (k_mask(st, d)) return -1;
@@ -825,7 +845,13 @@ static int enq_iteration(vbmf_b200_solver* s, int flags) {
         if (k_scale_B(st, d)) return -1;
     }
     s->btb_valid = true;
-    return k_post(st, d, flags, true);                                // updateCA!/CB! (dense), updateCB!, updateSigma*!, priors, delta
+    // updateCA!/CB! (dense), updateCB!, updateSigma*!, priors, delta + loop control: on the side stream
+    VB_CUDA_OK(cudaEventRecord(s->ev_b, st));
+    VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_b, 0));
+    if (k_post(s->side, d, flags, true)) return -1;
+    VB_CUDA_OK(cudaEventRecord(s->ev_p, s->side));
+    s->post_pending = true;
+    return 0;
 }
 
 extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode,
@@ -848,8 +874,9 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
         const int64_t c = std::min<int64_t>(CHUNK, niter - enq);
         for (int64_t i = 0; i < c; ++i) if (enq_iteration(s, flags)) return -1;
         enq += c;
-        VB_CUDA_OK(cudaMemcpyAsync(&s->h_flag[slot], &d.sc->active, sizeof(int), cudaMemcpyDeviceToHost, st));
-        VB_CUDA_OK(cudaEventRecord(s->ev[slot], st));
+        // the flag is produced on the side stream; copying it there keeps the main stream free of the dependency
+        VB_CUDA_OK(cudaMemcpyAsync(&s->h_flag[slot], &d.sc->active, sizeof(int), cudaMemcpyDeviceToHost, s->side));
+        VB_CUDA_OK(cudaEventRecord(s->ev[slot], s->side));
         if (pending) {
             VB_CUDA_OK(cudaEventSynchronize(s->ev[slot ^ 1]));
             if (s->h_flag[slot ^ 1] == 0) break;
@@ -857,7 +884,7 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
         pending = true;
         slot ^= 1;
     }
-    if (pull_scalars(s)) return -1;
+    if (wait_post(s) || pull_scalars(s)) return -1;
     if (iters) *iters = s->h_sc.iter;
     if (dout) *dout = s->h_sc.d;
     if (s->h_sc.chol_fail) { set_error("a posterior precision matrix was not positive definite (NaN written, loop ended)"); return -2; }
