@@ -19,7 +19,7 @@ __global__ void cmp(const double* a, const double* b, size_t n, int H, unsigned 
 }
 int main() {
     using namespace vb;
-    int cases[4][3] = {{64, 200000, 64}, {3000, 50000, 64}, {1000, 100000, 32}, {20000, 50000, 64}};
+    int cases[4][3] = {{3000, 50000, 64}, {10000, 100000, 32}, {20000, 100000, 64}, {20000, 25000, 64}};
     for (auto& c : cases) {
         int L = c[0], M = c[1], H = c[2];
         double *Y, *B, *P, *R; unsigned long long* nbad; double* maxerr; int* fb;
@@ -30,9 +30,11 @@ int main() {
         CUtensorMap tmY, tmB;
         make_tmap_2d(&tmY, Y, L, M, (uint64_t)L * 8, 16, 128);
         make_tmap_2d(&tmB, B, L, H, (uint64_t)L * 8, 16, gemm_geometry(H).bn);
-        for (int rep = 0; rep < 5; ++rep) {
+        int S1 = 1, kbs = 1; plan_splitk_ytb(L, M, H, 148, &S1, &kbs);
+        double* Pp; cudaMalloc(&Pp, (size_t)S1 * M * H * 8);
+        for (int rep = 0; rep < 2; ++rep) {
             cudaMemset(P, 0, (size_t)M * H * 8); cudaMemset(nbad, 0, 8);
-            launch_gemm_ytb(0, &tmY, &tmB, P, M, L, H, H, nullptr, 148);
+            launch_gemm_ytb(0, &tmY, &tmB, P, M, L, H, H, 1, (L + 15) / 16, 0, nullptr, 148);
             cmp<<<1024, 256>>>(P, R, (size_t)M * H, H, nbad, maxerr, fb);
             unsigned long long h; int hfb[16];
             cudaMemcpy(&h, nbad, 8, cudaMemcpyDeviceToHost); cudaMemcpy(hfb, fb, 64, cudaMemcpyDeviceToHost);
@@ -43,10 +45,10 @@ int main() {
         {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
-            for (int rep = 0; rep < 5; ++rep) launch_gemm_ytb(0, &tmY, &tmB, P, M, L, H, H, nullptr, 148);
+            for (int rep = 0; rep < 5; ++rep) launch_gemm_ytb(0, &tmY, &tmB, Pp, M, L, H, H, S1, kbs, (size_t)M * H, nullptr, 148);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-            printf("variant %d  L=%d M=%d H=%d  K1 %.3f ms  %.2f TFLOP/s\n", VARIANT, L, M, H, ms, 2.0 * L * M * H / ms * 1e-9);
+            printf("wm64 %d wm32 %d S %d  L=%d M=%d H=%d  K1 %.3f ms  %.2f TFLOP/s\n", K1_WM64, K1_WM32, S1, L, M, H, ms, 2.0 * L * M * H / ms * 1e-9);
         }
         cudaFree(Y); cudaFree(B); cudaFree(P); cudaFree(R);
     }
