@@ -501,15 +501,16 @@ __global__ void __launch_bounds__(256) sparse_A_diag_kernel(Dev d, int diag_var,
         d.part[(size_t)blockIdx.x * H + t] = s;
     }
 }
-__global__ void diag_to_sa_kernel(Dev d, int nparts) {   // packed.SA = diag(sum of partial column sums)
+__global__ void __launch_bounds__(256) diag_to_sa_kernel(Dev d, int nparts) {   // packed.SA = diag(sum of partial column sums)
     ACTIVE_OR_RETURN(d);
-    const int H = d.H;
+    const int H = d.H, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* SA = d.packed + packed_sa(d);
-    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
-        const int i = e / H, j = e - i * H;
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) if (e / H != e % H) SA[e] = 0.0;
+    for (int h = warp; h < H; h += 8) {           // one warp per diagonal entry: lane-strided partial sums + fixed shuffle tree
         double s = 0.0;
-        if (i == j) for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * H + i];
-        SA[e] = s;
+        for (int p = lane; p < nparts; p += 32) s += d.part[(size_t)p * H + h];
+        s = warp_sum(s);
+        if (lane == 0) SA[h * H + h] = s;
     }
 }
 int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags) {
@@ -643,11 +644,17 @@ __global__ void __launch_bounds__(256) sparse_A_full_warp_kernel(Dev d, int diag
         __syncwarp();
     }
     if (!all_ok && lane == 0) d.sc->chol_fail = 1;
-    if (live) {
-        double* out = d.part + (size_t)gw * H * H;
+    // per-CTA sum of the warps' accumulators in fixed warp order (one partial per CTA instead of one per warp)
+    __shared__ double s_acc[32 * 32];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        if (wic == w && live) {
 #pragma unroll
-        for (int q = 0; q < HP; ++q) if (q < H) out[q * H + lane] = acc[q];
+            for (int q = 0; q < HP; ++q) if (q < H) s_acc[q * H + lane] = (w == 0 ? 0.0 : s_acc[q * H + lane]) + acc[q];
+        }
+        __syncthreads();
     }
+    double* out = d.part + (size_t)blockIdx.x * H * H;
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) out[e] = s_acc[e];
 }
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H;
@@ -658,11 +665,11 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     if (H <= 32) {
         const int wpc = 8;
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
-        ngroups = grid * wpc;
-        if (H <= 8) sparse_A_full_warp_kernel<8><<<grid, 256, 0, st>>>(d, dv, ngroups);
-        else if (H <= 16) sparse_A_full_warp_kernel<16><<<grid, 256, 0, st>>>(d, dv, ngroups);
-        else if (H <= 24) sparse_A_full_warp_kernel<24><<<grid, 256, 0, st>>>(d, dv, ngroups);
-        else sparse_A_full_warp_kernel<32><<<grid, 256, 0, st>>>(d, dv, ngroups);
+        ngroups = grid;                                   // one partial per CTA
+        if (H <= 8) sparse_A_full_warp_kernel<8><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
+        else if (H <= 16) sparse_A_full_warp_kernel<16><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
+        else if (H <= 24) sparse_A_full_warp_kernel<24><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
+        else sparse_A_full_warp_kernel<32><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
     } else {
         const size_t smem = (size_t)(H * (H + 1) + 3 * H) * sizeof(double);
         static bool done = false;
@@ -838,7 +845,7 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
 }
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H, dv = (flags & F_DIAG_VAR) ? 1 : 0;
-    const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), H > 64 ? 148 : 296));
+    const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), 148));
 #define BEPI(RR, TDD, TRR)                                                                                                   \
     {                                                                                                                        \
         static bool done = false;                                                                                            \
