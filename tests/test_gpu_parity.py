@@ -389,3 +389,23 @@ def test_error_paths(G, ctx):
     q.invCA = np.asfortranarray(-1e6 * np.eye(2))
     G.vb.vbmf_(Y, q, 5, eps=0.0, ctx=ctx)
     assert q.iterations == 1 and np.isnan(q.d) and np.isnan(q.AHat).all()
+
+
+# ------------------------------------------------------------------------------------------------ trajectory logging (N4) vs the reference's own log
+def test_logged_trajectory_matches_reference_log(G, ctx, tmp_path):
+    """vbmf_ with logdir: every logged field of every one of the 100 iterations against examples/data/vbmf_test/log.jld
+    (create_log / update_log! / save_log, src/data_manip.jl:6-66), then load_log + extract_params! round trip."""
+    g = load_golden("vbmf_test")
+    Y, p = dense_state_from_golden(g)
+    q = G.to_gpu_params(p)
+    G.vb.vbmf_(np.asfortranarray(Y), q, 100, eps=1e-6, est_covs=True, est_var=True, ctx=ctx, logdir=str(tmp_path), desc="run")
+    assert q.iterations == 100
+    log, Yl = G.vb.load_log(str(tmp_path / "run"))
+    assert np.array_equal(Yl, Y) and log["sigma2"].shape == (101,) and log["AHat"].shape == (20, 2, 101)
+    assert G.rel(log["sigma2"], g["log_sigma2"]) < TOL
+    for f in ("AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB"):
+        ref = np.stack([jl(g["log_" + f], t) for t in range(101)], axis=-1)
+        assert G.rel(log[f], ref) < TOL, f
+    r = G.to_gpu_params(p)
+    G.vb.extract_params_(log, r, 37)
+    assert G.rel(r.BHat, jl(g["log_BHat"], 37)) < TOL and abs(r.sigma2 - g["log_sigma2"][37]) < TOL

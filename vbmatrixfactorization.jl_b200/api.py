@@ -27,7 +27,7 @@ __all__ = [
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
-    "vbls_", "vbls_batched_", "preprocess", "VBMFError",
+    "vbls_", "vbls_batched_", "preprocess", "create_log", "update_log_", "save_log", "load_log", "extract_params_", "VBMFError",
 ]
 
 VBMFError = L_.VBMFError
@@ -467,8 +467,15 @@ def _verb(verb, it, d):
 
 
 # ----------------------------------------------------------------------------------------------------------- drivers
-def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False, norm="spectral", ctx=None, yhat=True):
-    """`vbmf!` src/vbmf.jl:175-231: mutates params, returns params.  yhat=False skips the final L x M updateYHat!."""
+def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False, norm="spectral", ctx=None, yhat=True,
+          logdir="", desc=""):
+    """`vbmf!` src/vbmf.jl:175-231: mutates params, returns params.  yhat=False skips the final L x M updateYHat!.
+    logdir != "" logs every field after every iteration (create_log / update_log! / save_log)."""
+    if logdir:
+        it, d, params.log = _run_logged(Y, params, niter, eps, _flags(est_covs=est_covs, est_var=est_var), norm, ctx, logdir, desc)
+        params.iterations, params.d = it, d
+        _verb(verb, it, d)
+        return params
     ctx = _ctx_for(Y, ctx)
     st = _dense_struct(params, yhat)
     it, d = C.c_int64(), C.c_double()
@@ -486,8 +493,14 @@ def vbmf(Y, params_in, niter, **kw):
 
 
 def vbmf_sparse_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_cb=True, norm="spectral",
-                 ctx=None, keep_blocks=False, yhat=True):
+                 ctx=None, keep_blocks=False, yhat=True, logdir="", desc=""):
     """`vbmf_sparse!` src/vbmf_sparse.jl:344-410: mutates params, returns d."""
+    if logdir:
+        it, d, params.log = _run_logged(Y, params, niter, eps, _flags(diag_var=diag_var, full_cov=full_cov, est_cb=est_cb), norm, ctx,
+                                        logdir, desc, keep_blocks)
+        params.iterations = it
+        _verb(verb, it, d)
+        return d
     ctx = _ctx_for(Y, ctx)
     st = _sparse_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
@@ -508,8 +521,14 @@ def vbmf_sparse(Y, params_in, niter, **kw):
 
 
 def vbmf_dual_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_priors=True, est_cb=True,
-               norm="spectral", ctx=None, keep_blocks=False, yhat=True):
+               norm="spectral", ctx=None, keep_blocks=False, yhat=True, logdir="", desc=""):
     """`vbmf_dual!` src/vbmf_dual.jl:455-530: mutates params, returns d."""
+    if logdir:
+        it, d, params.log = _run_logged(Y, params, niter, eps, _flags(diag_var=diag_var, full_cov=full_cov, est_cb=est_cb,
+                                                                      est_priors=est_priors), norm, ctx, logdir, desc, keep_blocks)
+        params.iterations = it
+        _verb(verb, it, d)
+        return d
     ctx = _ctx_for(Y, ctx)
     st = _dual_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
@@ -684,3 +703,85 @@ def preprocess(Y, lam, verb=False, ctx=None):
     out = ctx.download_Y()
     ctx._key = Context._fingerprint(out) + (None, 0)     # the resident matrix IS `out`: the next solver call need not upload it
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------- trajectory logging (N4)
+_LOG_SKIP = ("YHat", "SigmaATVec_blocks", "iterations", "d", "kind")
+
+
+def _log_fields(params):
+    return [k for k, v in vars(params).items() if k not in _LOG_SKIP and v is not None and not k.startswith("_")]
+
+
+def create_log(params):
+    """`create_log` src/data_manip.jl:6-25: one entry per params field; scalars become 1-element vectors.
+    YHat and the (MH)^2 covariance are not logged (the reference logs a stale YHat)."""
+    log = {}
+    for k in _log_fields(params):
+        v = getattr(params, k)
+        log[k] = [np.array(v, dtype=np.float64 if not isinstance(v, (int, np.integer)) else np.int64)]
+    return log
+
+
+def update_log_(log, params):
+    """`update_log!` src/data_manip.jl:32-45: append the current value of every field (new last dimension)."""
+    for k in log:
+        v = getattr(params, k)
+        log[k].append(np.array(v, dtype=log[k][0].dtype))
+
+
+def _stack(log):
+    return {k: (np.stack(v, axis=-1) if v[0].ndim else np.array(v)) for k, v in log.items()}
+
+
+def save_log(log, Y, priors, logdir, desc=""):
+    """`save_log` src/data_manip.jl:53-66: <logdir>/<desc>/log.npz and inputs.npz (NumPy containers instead of JLD)."""
+    import datetime
+    import os
+    desc = desc or datetime.datetime.now().strftime("%Y%m%d_%H%M%S")
+    d = os.path.join(logdir, desc)
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, "log.npz"), **_stack(log))
+    np.savez_compressed(os.path.join(d, "inputs.npz"), Y=np.asarray(Y), **{"prior_" + k: v for k, v in (priors or {}).items()})
+    return d
+
+
+def load_log(path):
+    """`load_log` src/data_manip.jl:74-89 -> (log dict of stacked arrays, Y)."""
+    import os
+    lg = np.load(os.path.join(path, "log.npz"))
+    Y = np.load(os.path.join(path, "inputs.npz"))["Y"]
+    return {k: lg[k] for k in lg.files}, Y
+
+
+def extract_params_(log, params, i):
+    """`extract_params!` src/data_manip.jl:96-118: overwrite params with slice i (0 = initial state) of a stacked log."""
+    for k, v in log.items():
+        if hasattr(params, k):
+            cur = getattr(params, k)
+            val = v[..., i]
+            setattr(params, k, type(cur)(val) if np.ndim(cur) == 0 else np.array(val, order="F" if np.ndim(val) == 2 else "C"))
+    return params
+
+
+def _run_logged(Y, params, niter, eps, flags, norm, ctx, logdir, desc, keep_blocks=False):
+    """The reference's loop with update_log! after every iteration (src/vbmf.jl:206-208): the state stays resident, one
+    device iteration at a time, small fields are downloaded in between."""
+    ctx = _ctx_for(Y, ctx)
+    s = Solver(ctx, params, keep_blocks=keep_blocks)
+    log = create_log(params)
+    it_total, d = 0, eps + 1.0
+    try:
+        s.upload(params)
+        while it_total < niter and d > eps:
+            n, d = s.run(1, eps=eps, flags=flags, norm=norm)
+            if n == 0:
+                break
+            it_total += n
+            s.download(params)
+            update_log_(log, params)
+        s.download(params, want_yhat=True)
+    finally:
+        s.close()
+    save_log(log, Y if Y is not None else np.zeros((0, 0)), {}, logdir, desc)
+    return it_total, d, log
