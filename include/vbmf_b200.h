@@ -27,7 +27,7 @@ extern "C" {
 typedef struct vbmf_b200_ctx vbmf_b200_ctx;       /* one GPU: stream, communicator, resident shard of Y */
 typedef struct vbmf_b200_solver vbmf_b200_solver; /* device-resident parameter state of one problem */
 
-enum { VBMF_B200_DENSE = 0, VBMF_B200_SPARSE = 1, VBMF_B200_DUAL = 2 };
+enum { VBMF_B200_DENSE = 0, VBMF_B200_SPARSE = 1, VBMF_B200_DUAL = 2, VBMF_B200_TRIAL = 3 };
 enum { VBMF_B200_NORM_SPECTRAL = 0,   /* Julia 0.5 norm(::Matrix) in delta(), src/util.jl:27-29 (default) */
        VBMF_B200_NORM_FROBENIUS = 1 };
 /* option bits (keyword arguments of vbmf!/vbmf_sparse!/vbmf_dual! and of the step functions) */
@@ -49,7 +49,10 @@ enum {
     VBMF_B200_STEP_UPDATE_ALPHA00 = 5, /* updateAlpha00! src/vbmf_dual.jl:393 */
     VBMF_B200_STEP_UPDATE_ALPHA01 = 6, /* updateAlpha01! src/vbmf_dual.jl:417 */
     VBMF_B200_STEP_UPDATE_BETA00 = 7,  /* updateBeta00!  src/vbmf_dual.jl:408 */
-    VBMF_B200_STEP_UPDATE_BETA01 = 8   /* updateBeta01!  src/vbmf_dual.jl:432 */
+    VBMF_B200_STEP_UPDATE_BETA01 = 8,  /* updateBeta01!  src/vbmf_dual.jl:432 */
+    /* vbmf_trial numbers its three ARD groups 1..3 (src/vbmf_trial.jl:442-507): updateAlpha01!/02!/03! = ALPHA00/01/02 here */
+    VBMF_B200_STEP_UPDATE_ALPHA02 = 9, /* updateAlpha03! src/vbmf_trial.jl:490 */
+    VBMF_B200_STEP_UPDATE_BETA02 = 10  /* updateBeta03!  src/vbmf_trial.jl:505 */
 };
 
 /* `vbmf_parameters`, src/vbmf.jl:22-40.  M = number of columns of Y held by this ctx. */
@@ -128,6 +131,44 @@ typedef struct {
     double trYTY;
 } vbmf_b200_dual_state;
 
+/* `vbmf_trial_parameters`, src/vbmf_trial.jl:68-129 (unexported in the reference, used by examples/mil_util.jl:194,253-290):
+ * three ARD groups: A1 = AHat[:, 1:H0], A2 = AHat[1:M0, H0+1:H], A3 = AHat[M0+1:M, H0+1:H].  M0 / M1 are GLOBAL row counts of
+ * AHat (columns of Y); with sharding M is the local row count and the shard's rows are split by their global index. */
+typedef struct {
+    int64_t L, M, M0, M1, MH, H, H0, H1;
+    double* AHat;            /* M x H */
+    double* ATVecHat;        /* MH */
+    double* SigmaATVec_blocks;     /* M*H*H or NULL */
+    double* diagSigmaATVec;  /* MH */
+    double* SigmaA;          /* H x H */
+    double* A1Hat;           /* M x H0 */
+    double* A2Hat;           /* (local rows with global index <= M0) x H1 */
+    double* A3Hat;           /* (local rows with global index  > M0) x H1 */
+    double* BHat;            /* L x H */
+    double* SigmaB;          /* H x H */
+    double* CA;              /* MH, per-row interleave [CA1 block m ; CA2 or CA3 block m] */
+    double* alpha;           /* 3 = [alpha1, alpha2, alpha3] */
+    double* beta;            /* MH, interleaved like CA */
+    double* CA1;             /* M*H0 */
+    double alpha01, beta01, alpha1;
+    double* beta1;           /* M*H0 */
+    double* CA2;             /* M0*H1 (local part) */
+    double alpha02, beta02, alpha2;
+    double* beta2;
+    double* CA3;             /* M1*H1 (local part) */
+    double alpha03, beta03, alpha3;
+    double* beta3;
+    double* CB;              /* H */
+    double gamma0, delta0, gamma;
+    double* delta;           /* H */
+    double sigmaHat, eta0, zeta0, eta, zeta;
+    double* sigmaVecHat;     /* L */
+    double* etaVec;          /* L */
+    double* zetaVec;         /* L */
+    double* YHat;            /* L x M or NULL */
+    double trYTY;
+} vbmf_b200_trial_state;
+
 /* ---- library ---- */
 int vbmf_b200_version(void);
 const char* vbmf_b200_last_error(void);
@@ -171,6 +212,9 @@ int vbmf_b200_gemm_YA(vbmf_b200_ctx* ctx, const double* A, int64_t H, double* Q)
 /* h_split: H1 (masked trailing columns) for dense/sparse, H0 for dual.  labels: shard-local, 1-based, may be NULL. */
 int vbmf_b200_solver_create(vbmf_b200_ctx* ctx, int kind, int64_t H, int64_t h_split, int64_t n_labels,
                             const int64_t* labels, int keep_blocks, vbmf_b200_solver** out);
+/* vbmf_trial solver: H0 = width of the first column group, M0_global = number of rows of AHat (columns of Y) in group 2 */
+int vbmf_b200_solver_create_trial(vbmf_b200_ctx* ctx, int64_t H, int64_t H0, int64_t M0_global, int keep_blocks,
+                                  vbmf_b200_solver** out);
 int vbmf_b200_solver_destroy(vbmf_b200_solver* s);
 int vbmf_b200_dense_upload(vbmf_b200_solver* s, const vbmf_b200_dense_state* st);
 int vbmf_b200_dense_download(vbmf_b200_solver* s, vbmf_b200_dense_state* st);
@@ -178,6 +222,8 @@ int vbmf_b200_sparse_upload(vbmf_b200_solver* s, const vbmf_b200_sparse_state* s
 int vbmf_b200_sparse_download(vbmf_b200_solver* s, vbmf_b200_sparse_state* st);
 int vbmf_b200_dual_upload(vbmf_b200_solver* s, const vbmf_b200_dual_state* st);
 int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state* st);
+int vbmf_b200_trial_upload(vbmf_b200_solver* s, const vbmf_b200_trial_state* st);
+int vbmf_b200_trial_download(vbmf_b200_solver* s, vbmf_b200_trial_state* st);
 /* one reference step function on the resident state */
 int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags);
 /* the while-loop of vbmf! (src/vbmf.jl:193-214), vbmf_sparse! (src/vbmf_sparse.jl:368-393), vbmf_dual!
@@ -207,6 +253,10 @@ int vbmf_b200_sparse_run(vbmf_b200_ctx* ctx, vbmf_b200_sparse_state* st, int64_t
 /* vbmf_dual!(Y, params, niter; eps, diag_var, full_cov, est_priors, est_cb)   src/vbmf_dual.jl:455 */
 int vbmf_b200_dual_run(vbmf_b200_ctx* ctx, vbmf_b200_dual_state* st, int64_t niter, double eps, int diag_var, int full_cov,
                        int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
+
+/* vbmf_trial!(Y, params, niter; eps, diag_var, full_cov, est_priors, est_cb)   src/vbmf_trial.jl:528 */
+int vbmf_b200_trial_run(vbmf_b200_ctx* ctx, vbmf_b200_trial_state* st, int64_t niter, double eps, int diag_var, int full_cov,
+                        int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
 
 #ifdef __cplusplus
 }

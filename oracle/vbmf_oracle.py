@@ -752,6 +752,140 @@ def dual_lowerBoundTrimmed(Y, p_in, trim=1e-1):
     return dual_lowerBound(Y, _trim(p_in, trim))
 
 
+# ----------------------------------------------------------------------------- vbmf_trial (src/vbmf_trial.jl, unexported)
+def _interleave3(p, v1, v2, v3):
+    """[CA1 block m ; CA2 block m] for m <= M0, [CA1 block m ; CA3 block m-M0] after (src/vbmf_trial.jl:176-183,383-390)."""
+    M, H0, H1, M0 = p.M, p.H0, p.H1, p.M0
+    out = np.empty((M, H0 + H1))
+    out[:, :H0] = v1.reshape(M, H0)
+    out[:M0, H0:] = v2.reshape(M0, H1)
+    out[M0:, H0:] = v3.reshape(M - M0, H1)
+    return out.reshape(M * (H0 + H1))
+
+
+def vbmf_trial_init(Y, H, H0, M0, ca=1.0, alpha0=1e-10, beta0=1e-10, cb=1.0, gamma0=1e-10, delta0=1e-10, sigma=1.0,
+                    eta0=1e-10, zeta0=1e-10, rng=None, AHat=None, BHat=None):
+    """src/vbmf_trial.jl:139-227."""
+    if H < H0:
+        raise ValueError("H must be at least H0!")
+    p = vbmf_dual_init(Y, H, H0, ca=ca, alpha0=alpha0, beta0=beta0, cb=cb, gamma0=gamma0, delta0=delta0, sigma=sigma,
+                       eta0=eta0, zeta0=zeta0, rng=rng, AHat=AHat, BHat=BHat)
+    for f in ("A0Hat", "A1Hat", "CA0", "CA1", "alpha00", "alpha01", "beta00", "beta01", "alpha0", "alpha1", "beta0", "beta1"):
+        delattr(p, f)
+    p.kind = "trial"
+    M = p.M
+    p.M0, p.M1 = int(M0), M - int(M0)
+    p.A1Hat = p.AHat[:, :H0].copy()
+    p.A2Hat = p.AHat[:M0, H0:].copy()
+    p.A3Hat = p.AHat[M0:, H0:].copy()
+    p.CA1, p.CA2, p.CA3 = ca * np.ones(M * H0), ca * np.ones(p.M0 * p.H1), ca * np.ones(p.M1 * p.H1)
+    p.CA = _interleave3(p, p.CA1, p.CA2, p.CA3)
+    p.alpha01 = p.alpha02 = p.alpha03 = alpha0
+    p.beta01 = p.beta02 = p.beta03 = beta0
+    p.alpha1 = p.alpha2 = p.alpha3 = alpha0 + 0.5
+    p.beta1, p.beta2, p.beta3 = beta0 * np.ones(M * H0), beta0 * np.ones(p.M0 * p.H1), beta0 * np.ones(p.M1 * p.H1)
+    p.alpha = np.array([p.alpha1, p.alpha2, p.alpha3])
+    p.beta = _interleave3(p, p.beta1, p.beta2, p.beta3)
+    return p
+
+
+def trial_updateA(Y, p, full_cov=False, diag_var=False, literal=False):
+    """src/vbmf_trial.jl:250-320."""
+    _sparse_updateA_core(Y, p, full_cov, diag_var, literal)
+    p.AHat = p.ATVecHat.reshape(p.M, p.H).copy()
+    p.A1Hat = p.AHat[:, :p.H0].copy()
+    p.A2Hat = p.AHat[:p.M0, p.H0:].copy()
+    p.A3Hat = p.AHat[p.M0:, p.H0:].copy()
+
+
+def trial_updateCA(p):
+    """src/vbmf_trial.jl:357-400."""
+    M, H, H0, H1, M0, M1 = p.M, p.H, p.H0, p.H1, p.M0, p.M1
+    p.alpha1, p.alpha2, p.alpha3 = p.alpha01 + 0.5, p.alpha02 + 0.5, p.alpha03 + 0.5
+    dS = p.diagSigmaATVec.reshape(M, H)
+    p.beta1 = p.beta01 * np.ones(M * H0) + 0.5 * (p.A1Hat * p.A1Hat + dS[:, :H0]).reshape(M * H0)
+    p.beta2 = p.beta02 * np.ones(M0 * H1) + 0.5 * (p.A2Hat * p.A2Hat).reshape(M0 * H1) + 0.5 * dS[:M0, H0:].reshape(M0 * H1)
+    p.beta3 = p.beta03 * np.ones(M1 * H1) + 0.5 * (p.A3Hat * p.A3Hat + dS[M0:, H0:]).reshape(M1 * H1)
+    p.CA1 = p.alpha1 * np.ones(M * H0) / p.beta1
+    p.CA2 = p.alpha2 * np.ones(M0 * H1) / p.beta2
+    p.CA3 = p.alpha3 * np.ones(M1 * H1) / p.beta3
+    p.CA = _interleave3(p, p.CA1, p.CA2, p.CA3)
+    p.alpha = np.array([p.alpha1, p.alpha2, p.alpha3])
+    p.beta = _interleave3(p, p.beta1, p.beta2, p.beta3)
+
+
+def trial_update_priors(p):
+    """updateAlpha01!/02!/03! then updateBeta01!/02!/03! (src/vbmf_trial.jl:442-507, order :566-573)."""
+    N = (p.M * p.H0, p.M0 * p.H1, p.M1 * p.H1)
+    p.alpha01 = _update_alpha0x(N[0], p.beta01, p.alpha1, p.beta1, p.alpha01)
+    p.alpha02 = _update_alpha0x(N[1], p.beta02, p.alpha2, p.beta2, p.alpha02)
+    p.alpha03 = _update_alpha0x(N[2], p.beta03, p.alpha3, p.beta3, p.alpha03)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p.beta01 = float(np.float64(N[0] * p.alpha01) / np.sum(p.CA1))
+        p.beta02 = float(np.float64(N[1] * p.alpha02) / np.sum(p.CA2))
+        p.beta03 = float(np.float64(N[2] * p.alpha03) / np.sum(p.CA3))
+
+
+def vbmf_trial_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_priors=True, est_cb=True, norm="spectral", trace=None):
+    """`vbmf_trial!` src/vbmf_trial.jl:528-604.  Returns (d, iterations_done)."""
+    old = p.BHat.copy()
+    d = eps + 1.0
+    i = 1
+    while i <= niter and d > eps:
+        trial_updateA(Y, p, full_cov=full_cov, diag_var=diag_var)
+        sparse_updateB(Y, p, diag_var=diag_var)          # src/vbmf_trial.jl:327-341 == sparse
+        trial_updateCA(p)
+        if est_cb:
+            sparse_updateCB(p)                           # :407-412
+        sparse_updateSigma(Y, p, diag_var=diag_var)      # :419-435
+        if est_priors:
+            trial_update_priors(p)
+        if trace is not None:
+            trace(p, i)
+        d = delta(p.BHat, old, norm)
+        old = p.BHat.copy()
+        i += 1
+    sparse_updateYHat(p)
+    return d, i - 1
+
+
+def trial_lowerBound(Y, p):
+    """src/vbmf_trial.jl:630-681."""
+    Lb, GB = _lb_common(Y, p)
+    groups = ((p.alpha1, p.beta1, p.alpha01, p.beta01, p.CA1, p.M * p.H0), (p.alpha2, p.beta2, p.alpha02, p.beta02, p.CA2, p.M0 * p.H1),
+              (p.alpha3, p.beta3, p.alpha03, p.beta03, p.CA3, p.M1 * p.H1))
+    eln = [float(np.sum(gammaELn(a * np.ones(b.shape), b))) for a, b, _, _, _, _ in groups]
+    eln_d = float(np.sum(gammaELn(p.gamma * np.ones(p.delta.shape), p.delta)))
+    Lb += -p.MH / 2 * ln2pi + 0.5 * eln[0]
+    Lb += 0.5 * eln[1]
+    Lb += 0.5 * eln[2]
+    Lb += -(0.5 * float(p.CA @ (p.ATVecHat ** 2 + p.diagSigmaATVec)))
+    Lb += -p.L * p.H / 2 * ln2pi
+    Lb += p.L / 2 * eln_d
+    Lb += -0.5 * traceXTY(np.diag(p.CB), GB)
+    Lb += p.eta0 * math.log(p.zeta0) - gammaln(p.eta0)
+    Lb += (p.eta0 - 1) * gammaELn(p.eta, p.zeta) - p.zeta0 * p.sigmaHat
+    for (a, b, a0, b0, ca, N), e in zip(groups, eln):
+        Lb += N * (a0 * math.log(b0) - gammaln(a0))
+        Lb += (a0 - 1) * e
+        Lb += -b0 * float(np.sum(ca))
+    Lb += p.H * (p.gamma0 * math.log(p.delta0) - gammaln(p.gamma0))
+    Lb += (p.gamma0 - 1) * eln_d
+    Lb += -p.gamma0 * float(np.sum(p.CB))
+    Lb += normalEntropy_diag(p.diagSigmaATVec)
+    Lb += normalEntropy_kronSigmaB(p.SigmaB, p.L)
+    Lb += gammaEntropy(p.eta, p.zeta)
+    for a, b, _, _, _, _ in groups:
+        Lb += float(np.sum(gammaEntropy(a * np.ones(b.shape), b)))
+    Lb += float(np.sum(gammaEntropy(p.gamma * np.ones(p.delta.shape), p.delta)))
+    return float(Lb)
+
+
+def trial_lowerBoundTrimmed(Y, p_in, trim=1e-1):
+    """src/vbmf_trial.jl:687-697."""
+    return trial_lowerBound(Y, _trim(p_in, trim))
+
+
 # ----------------------------------------------------------------------------- vbls! (examples/mil_util.jl:179-203)
 def vbls(Y, p, niter, diag_var=False, full_cov=False):
     """A-only VB with B fixed (the MIL classification call pattern)."""

@@ -18,7 +18,7 @@ def to_gpu_params(p):
         q.sigma2 = float(p.sigma2)
         q.YHat = None
         return q
-    q = vb.vbmf_sparse_parameters() if p.kind == "sparse" else vb.vbmf_dual_parameters()
+    q = {"sparse": vb.vbmf_sparse_parameters, "dual": vb.vbmf_dual_parameters, "trial": vb.vbmf_trial_parameters}[p.kind]()
     for f in ("L", "M", "H", "MH", "H1"):
         setattr(q, f, int(getattr(p, f)))
     q.labels = np.asarray(getattr(p, "labels", []), dtype=np.int64).copy()
@@ -32,6 +32,14 @@ def to_gpu_params(p):
     q.YHat = None
     if p.kind == "sparse":
         for f in ("alpha0", "beta0", "alpha"):
+            setattr(q, f, float(getattr(p, f)))
+    elif p.kind == "trial":
+        q.H0, q.M0, q.M1 = int(p.H0), int(p.M0), int(p.M1)
+        for f in ("A1Hat", "A2Hat", "A3Hat"):
+            setattr(q, f, np.asfortranarray(np.array(getattr(p, f), dtype=np.float64)))
+        for f in ("CA1", "CA2", "CA3", "beta1", "beta2", "beta3", "alpha"):
+            setattr(q, f, np.array(getattr(p, f), dtype=np.float64).copy())
+        for f in ("alpha01", "beta01", "alpha1", "alpha02", "beta02", "alpha2", "alpha03", "beta03", "alpha3"):
             setattr(q, f, float(getattr(p, f)))
     else:
         q.H0 = int(p.H0)
@@ -61,7 +69,10 @@ def rel(a, b):
     return float(np.max(np.abs(a - b))) / den
 
 
+_SP = ["AHat", "ATVecHat", "diagSigmaATVec", "SigmaA", "BHat", "SigmaB", "CA", "beta", "CB", "delta", "sigmaHat", "zeta", "sigmaVecHat", "zetaVec"]
 FIELDS = {
+    "trial": _SP + ["A1Hat", "A2Hat", "A3Hat", "CA1", "CA2", "CA3", "beta1", "beta2", "beta3", "alpha01", "beta01", "alpha02", "beta02",
+                    "alpha03", "beta03", "alpha1", "alpha2", "alpha3"],
     "dense": ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "invCA", "invCB", "sigma2"],
     "sparse": ["AHat", "ATVecHat", "diagSigmaATVec", "SigmaA", "BHat", "SigmaB", "CA", "beta", "CB", "delta", "sigmaHat",
                "zeta", "sigmaVecHat", "zetaVec"],

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header(vb):
     # 64-bit fields only, so ctypes and the C compiler agree on the layout; guard against drift in the field count
     hdr = open(os.path.join(ROOT, "include", "vbmf_b200.h")).read()
     for cname, cls in (("vbmf_b200_dense_state", vb._lib.DenseState), ("vbmf_b200_sparse_state", vb._lib.SparseState),
-                       ("vbmf_b200_dual_state", vb._lib.DualState)):
+                       ("vbmf_b200_dual_state", vb._lib.DualState), ("vbmf_b200_trial_state", vb._lib.TrialState)):
         body = re.search(r"typedef struct \{([^}]*)\} %s;" % cname, hdr).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

@@ -409,3 +409,33 @@ def test_logged_trajectory_matches_reference_log(G, ctx, tmp_path):
     r = G.to_gpu_params(p)
     G.vb.extract_params_(log, r, 37)
     assert G.rel(r.BHat, jl(g["log_BHat"], 37)) < TOL and abs(r.sigma2 - g["log_sigma2"][37]) < TOL
+
+
+
+# ------------------------------------------------------------------------------------------------ vbmf_trial (N2)
+TRIAL_CASES = [(30, 100, 4, 2, 40, False, False, True), (30, 100, 4, 1, 70, True, False, True), (36, 140, 6, 3, 50, True, True, True),
+               (25, 64, 5, 2, 0, False, False, True), (25, 64, 5, 2, 64, False, False, False)]
+
+
+@pytest.mark.parametrize("L,M,H,H0,M0,full_cov,diag_var,est_priors", TRIAL_CASES)
+def test_trial_vs_oracle(G, ctx, L, M, H, H0, M0, full_cov, diag_var, est_priors):
+    """src/vbmf_trial.jl: three ARD groups (column split H0, row split M0) with learned hyper-priors; incl. the empty-group edges."""
+    Y = synth(L, M, max(1, H // 2), seed=L + 5 * M)
+    p = vo.vbmf_trial_init(Y, H, H0, M0, rng=np.random.default_rng(13))
+    for niter in (1, 2, 6):
+        po = copy.deepcopy(p)
+        d_o, it_o = vo.vbmf_trial_run(Y, po, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov, est_priors=est_priors)
+        q = G.to_gpu_params(p)
+        d = G.vb.vbmf_trial_(np.asfortranarray(Y), q, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov, est_priors=est_priors, ctx=ctx)
+        assert q.iterations == it_o
+        floor = G.sensitivity(lambda s: vo.vbmf_trial_run(Y, s, niter, eps=1e-12, diag_var=diag_var, full_cov=full_cov,
+                                                          est_priors=est_priors), p, ["AHat", "BHat"])
+        G.compare(q, po, max(TOL, 100 * floor))
+        assert abs(d - d_o) <= 1e-8 * abs(d_o) + 1e-9
+    if not diag_var:
+        lb_o, lbt_o = vo.trial_lowerBound(Y, po), vo.trial_lowerBoundTrimmed(Y, po, 1e-1)
+        lb, lbt = G.vb.lowerBound(np.asfortranarray(Y), q, ctx=ctx), G.vb.lowerBoundTrimmed(np.asfortranarray(Y), q, 1e-1, ctx=ctx)
+        if np.isfinite(lb_o):
+            assert abs(lb - lb_o) <= 1e-9 * abs(lb_o) and abs(lbt - lbt_o) <= 1e-9 * abs(lbt_o), (lb, lb_o, lbt, lbt_o)
+        else:
+            assert np.isnan(lb) == np.isnan(lb_o)

@@ -10,11 +10,11 @@ c_f64 = C.c_double
 p_f64 = C.POINTER(C.c_double)
 p_i64 = C.POINTER(C.c_int64)
 
-DENSE, SPARSE, DUAL = 0, 1, 2
+DENSE, SPARSE, DUAL, TRIAL = 0, 1, 2, 3
 NORM_SPECTRAL, NORM_FROBENIUS = 0, 1
 DIAG_VAR, FULL_COV, EST_CB, EST_PRIORS, EST_COVS, EST_VAR = 1, 2, 4, 8, 16, 32
 (STEP_UPDATE_A, STEP_UPDATE_B, STEP_UPDATE_CA, STEP_UPDATE_CB, STEP_UPDATE_SIGMA, STEP_UPDATE_ALPHA00,
- STEP_UPDATE_ALPHA01, STEP_UPDATE_BETA00, STEP_UPDATE_BETA01) = range(9)
+ STEP_UPDATE_ALPHA01, STEP_UPDATE_BETA00, STEP_UPDATE_BETA01, STEP_UPDATE_ALPHA02, STEP_UPDATE_BETA02) = range(11)
 
 
 class DenseState(C.Structure):
@@ -45,6 +45,19 @@ class DualState(C.Structure):
                 ("sigmaVecHat", p_f64), ("etaVec", p_f64), ("zetaVec", p_f64), ("YHat", p_f64), ("trYTY", c_f64)]
 
 
+class TrialState(C.Structure):
+    _fields_ = [("L", c_i64), ("M", c_i64), ("M0", c_i64), ("M1", c_i64), ("MH", c_i64), ("H", c_i64), ("H0", c_i64), ("H1", c_i64),
+                ("AHat", p_f64), ("ATVecHat", p_f64), ("SigmaATVec_blocks", p_f64), ("diagSigmaATVec", p_f64), ("SigmaA", p_f64),
+                ("A1Hat", p_f64), ("A2Hat", p_f64), ("A3Hat", p_f64), ("BHat", p_f64), ("SigmaB", p_f64),
+                ("CA", p_f64), ("alpha", p_f64), ("beta", p_f64),
+                ("CA1", p_f64), ("alpha01", c_f64), ("beta01", c_f64), ("alpha1", c_f64), ("beta1", p_f64),
+                ("CA2", p_f64), ("alpha02", c_f64), ("beta02", c_f64), ("alpha2", c_f64), ("beta2", p_f64),
+                ("CA3", p_f64), ("alpha03", c_f64), ("beta03", c_f64), ("alpha3", c_f64), ("beta3", p_f64),
+                ("CB", p_f64), ("gamma0", c_f64), ("delta0", c_f64), ("gamma", c_f64), ("delta", p_f64),
+                ("sigmaHat", c_f64), ("eta0", c_f64), ("zeta0", c_f64), ("eta", c_f64), ("zeta", c_f64),
+                ("sigmaVecHat", p_f64), ("etaVec", p_f64), ("zetaVec", p_f64), ("YHat", p_f64), ("trYTY", c_f64)]
+
+
 # every symbol include/vbmf_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vbmf_b200_version": (C.c_int, []),
@@ -66,6 +79,7 @@ SYMBOLS = {
     "vbmf_b200_gemm_YtB": (C.c_int, [C.c_void_p, p_f64, c_i64, p_f64]),
     "vbmf_b200_gemm_YA": (C.c_int, [C.c_void_p, p_f64, c_i64, p_f64]),
     "vbmf_b200_solver_create": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, c_i64, p_i64, C.c_int, C.POINTER(C.c_void_p)]),
+    "vbmf_b200_solver_create_trial": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_int, C.POINTER(C.c_void_p)]),
     "vbmf_b200_solver_destroy": (C.c_int, [C.c_void_p]),
     "vbmf_b200_dense_upload": (C.c_int, [C.c_void_p, C.POINTER(DenseState)]),
     "vbmf_b200_dense_download": (C.c_int, [C.c_void_p, C.POINTER(DenseState)]),
@@ -73,6 +87,8 @@ SYMBOLS = {
     "vbmf_b200_sparse_download": (C.c_int, [C.c_void_p, C.POINTER(SparseState)]),
     "vbmf_b200_dual_upload": (C.c_int, [C.c_void_p, C.POINTER(DualState)]),
     "vbmf_b200_dual_download": (C.c_int, [C.c_void_p, C.POINTER(DualState)]),
+    "vbmf_b200_trial_upload": (C.c_int, [C.c_void_p, C.POINTER(TrialState)]),
+    "vbmf_b200_trial_download": (C.c_int, [C.c_void_p, C.POINTER(TrialState)]),
     "vbmf_b200_solver_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vbmf_b200_solver_run": (C.c_int, [C.c_void_p, c_i64, c_f64, C.c_int, C.c_int, p_i64, p_f64]),
     "vbmf_b200_solver_lower_bound": (C.c_int, [C.c_void_p, c_f64, C.c_int, p_f64]),
@@ -81,6 +97,7 @@ SYMBOLS = {
     "vbmf_b200_dense_run": (C.c_int, [C.c_void_p, C.POINTER(DenseState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
     "vbmf_b200_sparse_run": (C.c_int, [C.c_void_p, C.POINTER(SparseState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
     "vbmf_b200_dual_run": (C.c_int, [C.c_void_p, C.POINTER(DualState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_trial_run": (C.c_int, [C.c_void_p, C.POINTER(TrialState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
 }
 
 _lib = None

@@ -23,7 +23,7 @@ from . import _lib as L_
 
 __all__ = [
     "Context", "default_context", "shard_columns",
-    "vbmf_parameters", "vbmf_sparse_parameters", "vbmf_dual_parameters",
+    "vbmf_parameters", "vbmf_sparse_parameters", "vbmf_dual_parameters", "vbmf_trial_parameters", "vbmf_trial_init", "vbmf_trial_", "vbmf_trial",
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
@@ -201,6 +201,11 @@ class vbmf_dual_parameters(_Params):
     kind = L_.DUAL
 
 
+class vbmf_trial_parameters(_Params):
+    """src/vbmf_trial.jl:68-129 (unexported in the reference; used by examples/mil_util.jl)"""
+    kind = L_.TRIAL
+
+
 def copy(params_in):
     """Base.copy for the parameter types (src/vbmf.jl:80 is shallow; results are identical, a deep copy is made)."""
     return _copy.deepcopy(params_in)
@@ -304,6 +309,33 @@ def vbmf_dual_init(Y, H, H0, ca=1.0, alpha0=1e-10, beta0=1e-10, cb=1.0, gamma0=1
     return p
 
 
+def vbmf_trial_init(Y, H, H0, M0, ca=1.0, alpha0=1e-10, beta0=1e-10, cb=1.0, gamma0=1e-10, delta0=1e-10, sigma=1.0,
+                    eta0=1e-10, zeta0=1e-10, rng=None, trYTY=None):
+    """src/vbmf_trial.jl:139-227"""
+    if H < H0:
+        raise VBMFError("H must be at least H0!")
+    rng = rng or np.random.default_rng()
+    p = vbmf_trial_parameters()
+    p.H0, p.H1 = int(H0), int(H - H0)
+    p.labels = _labels(None)
+    _sparse_common_init(p, Y, H, ca, cb, gamma0, delta0, sigma, eta0, zeta0, rng, trYTY)
+    M = p.M
+    p.M0, p.M1 = int(M0), M - int(M0)
+    p.ATVecHat = np.ascontiguousarray(p.AHat).reshape(p.MH).copy()
+    p.A1Hat = _f(p.AHat[:, :H0])
+    p.A2Hat = _f(p.AHat[:M0, H0:])
+    p.A3Hat = _f(p.AHat[M0:, H0:])
+    p.CA1, p.CA2, p.CA3 = ca * np.ones(M * p.H0), ca * np.ones(p.M0 * p.H1), ca * np.ones(p.M1 * p.H1)
+    p.CA = ca * np.ones(p.MH)
+    p.alpha01 = p.alpha02 = p.alpha03 = float(alpha0)
+    p.beta01 = p.beta02 = p.beta03 = float(beta0)
+    p.alpha1 = p.alpha2 = p.alpha3 = alpha0 + 0.5
+    p.beta1, p.beta2, p.beta3 = beta0 * np.ones(M * p.H0), beta0 * np.ones(p.M0 * p.H1), beta0 * np.ones(p.M1 * p.H1)
+    p.alpha = np.array([p.alpha1, p.alpha2, p.alpha3])
+    p.beta = beta0 * np.ones(p.MH)
+    return p
+
+
 # ----------------------------------------------------------------------------------------------------------- marshalling
 def _ensure(p, name, shape, fortran=True):
     a = getattr(p, name, None)
@@ -383,6 +415,29 @@ def _dual_struct(p, want_yhat, want_blocks):
     return st
 
 
+def _trial_struct(p, want_yhat, want_blocks, m2_local=None):
+    """m2_local: number of this shard's rows that belong to group 2 (global index <= M0); defaults to the unsharded M0."""
+    st = L_.TrialState()
+    _sparse_fill(st, p, want_yhat, want_blocks)
+    M = p.M
+    m2 = p.M0 if m2_local is None else m2_local
+    m2 = max(0, min(int(m2), M))
+    st.M0, st.M1, st.H0, st.H1 = p.M0, p.M1, p.H0, p.H1
+    st.A1Hat = _ptr(_ensure(p, "A1Hat", (M, p.H0)))
+    st.A2Hat = _ptr(_ensure(p, "A2Hat", (m2, p.H1)))
+    st.A3Hat = _ptr(_ensure(p, "A3Hat", (M - m2, p.H1)))
+    for f, n in (("CA1", M * p.H0), ("CA2", m2 * p.H1), ("CA3", (M - m2) * p.H1), ("beta1", M * p.H0), ("beta2", m2 * p.H1),
+                 ("beta3", (M - m2) * p.H1), ("alpha", 3)):
+        a = np.ascontiguousarray(getattr(p, f), dtype=np.float64).reshape(-1)
+        if a.size != n:
+            a = np.zeros(n)
+        setattr(p, f, a)
+        setattr(st, f, _ptr(a))
+    for f in ("alpha01", "beta01", "alpha1", "alpha02", "beta02", "alpha2", "alpha03", "beta03", "alpha3"):
+        setattr(st, f, float(getattr(p, f)))
+    return st
+
+
 def _readback(p, st):
     if p.kind == L_.DENSE:
         p.sigma2 = st.sigma2
@@ -392,6 +447,9 @@ def _readback(p, st):
     if p.kind == L_.DUAL:
         for f in ("alpha00", "beta00", "alpha01", "beta01", "alpha0", "alpha1"):
             setattr(p, f, getattr(st, f))
+    if p.kind == L_.TRIAL:
+        for f in ("alpha01", "beta01", "alpha1", "alpha02", "beta02", "alpha2", "alpha03", "beta03", "alpha3"):
+            setattr(p, f, getattr(st, f))
 
 
 def _struct(p, want_yhat=False, want_blocks=False):
@@ -399,11 +457,15 @@ def _struct(p, want_yhat=False, want_blocks=False):
         return _dense_struct(p, want_yhat)
     if p.kind == L_.SPARSE:
         return _sparse_struct(p, want_yhat, want_blocks)
+    if p.kind == L_.TRIAL:
+        return _trial_struct(p, want_yhat, want_blocks, getattr(p, "_m2_local", None))
     return _dual_struct(p, want_yhat, want_blocks)
 
 
-_UP = {L_.DENSE: "vbmf_b200_dense_upload", L_.SPARSE: "vbmf_b200_sparse_upload", L_.DUAL: "vbmf_b200_dual_upload"}
-_DOWN = {L_.DENSE: "vbmf_b200_dense_download", L_.SPARSE: "vbmf_b200_sparse_download", L_.DUAL: "vbmf_b200_dual_download"}
+_UP = {L_.DENSE: "vbmf_b200_dense_upload", L_.SPARSE: "vbmf_b200_sparse_upload", L_.DUAL: "vbmf_b200_dual_upload",
+       L_.TRIAL: "vbmf_b200_trial_upload"}
+_DOWN = {L_.DENSE: "vbmf_b200_dense_download", L_.SPARSE: "vbmf_b200_sparse_download", L_.DUAL: "vbmf_b200_dual_download",
+         L_.TRIAL: "vbmf_b200_trial_download"}
 
 
 class Solver:
@@ -414,12 +476,15 @@ class Solver:
         p = params
         if (p.L, p.M) != (ctx.L, ctx.M):
             raise VBMFError("params are %d x %d but the attached Y is %d x %d" % (p.L, p.M, ctx.L, ctx.M))
-        split = p.H0 if p.kind == L_.DUAL else p.H1
+        split = p.H0 if p.kind in (L_.DUAL, L_.TRIAL) else p.H1
         labels = _labels(getattr(p, "labels", None))
         h = C.c_void_p()
-        L_.check(self.lib.vbmf_b200_solver_create(ctx.h, p.kind, p.H, split, labels.size,
-                                                  labels.ctypes.data_as(L_.p_i64) if labels.size else None,
-                                                  1 if keep_blocks else 0, C.byref(h)))
+        if p.kind == L_.TRIAL:
+            L_.check(self.lib.vbmf_b200_solver_create_trial(ctx.h, p.H, p.H0, p.M0, 1 if keep_blocks else 0, C.byref(h)))
+        else:
+            L_.check(self.lib.vbmf_b200_solver_create(ctx.h, p.kind, p.H, split, labels.size,
+                                                      labels.ctypes.data_as(L_.p_i64) if labels.size else None,
+                                                      1 if keep_blocks else 0, C.byref(h)))
         self.h, self.kind, self.keep_blocks = h, p.kind, keep_blocks
 
     def upload(self, p):
@@ -544,6 +609,27 @@ def vbmf_dual(Y, params_in, niter, **kw):
     """src/vbmf_dual.jl:538-549 -> (params, d)"""
     p = copy(params_in)
     d = vbmf_dual_(Y, p, niter, **kw)
+    return p, d
+
+
+def vbmf_trial_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_priors=True, est_cb=True,
+                norm="spectral", ctx=None, keep_blocks=False, yhat=True):
+    """`vbmf_trial!` src/vbmf_trial.jl:528-604: mutates params, returns d."""
+    ctx = _ctx_for(Y, ctx)
+    st = _trial_struct(params, yhat, keep_blocks, getattr(params, "_m2_local", None))
+    it, d = C.c_int64(), C.c_double()
+    L_.check(ctx.lib.vbmf_b200_trial_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
+                                         int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
+    _readback(params, st)
+    params.iterations = it.value
+    _verb(verb, it.value, d.value)
+    return d.value
+
+
+def vbmf_trial(Y, params_in, niter, **kw):
+    """src/vbmf_trial.jl:612-623 -> (params, d)"""
+    p = copy(params_in)
+    d = vbmf_trial_(Y, p, niter, **kw)
     return p, d
 
 

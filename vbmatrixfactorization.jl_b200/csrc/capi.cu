@@ -373,15 +373,17 @@ struct vbmf_b200_solver {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_split, int64_t n_labels,
-                                       const int64_t* labels, int keep_blocks, vbmf_b200_solver** out) {
+static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_split, int64_t M0_global, int64_t n_labels,
+                              const int64_t* labels, int keep_blocks, vbmf_b200_solver** out) {
     if (out == nullptr) { set_error("solver_create: out is NULL"); return -1; }
     *out = nullptr;
     if (!c || !c->have_Y) { set_error("solver_create: attach Y first"); return -1; }
-    if (kind < 0 || kind > 2) { set_error("solver_create: unknown kind %d", kind); return -1; }
+    if (kind < 0 || kind > 3) { set_error("solver_create: unknown kind %d", kind); return -1; }
+    if (kind == VBMF_B200_TRIAL && (M0_global < 0 || M0_global > c->Mglob)) { set_error("M0 must be in 0..M"); return -1; }
     if (H < 1 || H > 128) { set_error("H = %lld is outside the supported range 1..128", (long long)H); return -1; }
-    if (kind == VBMF_B200_DUAL && (h_split < 0 || h_split > H)) { set_error("H must be at least H0!"); return -1; }  // src/vbmf_dual.jl:126-128
-    if (kind != VBMF_B200_DUAL && (h_split < 0 || h_split > H)) { set_error("H1 must be in 0..H"); return -1; }
+    const bool grouped = kind == VBMF_B200_DUAL || kind == VBMF_B200_TRIAL;
+    if (grouped && (h_split < 0 || h_split > H)) { set_error("H must be at least H0!"); return -1; }  // src/vbmf_dual.jl:126-128
+    if (!grouped && (h_split < 0 || h_split > H)) { set_error("H1 must be in 0..H"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     vbmf_b200_solver* s = new vbmf_b200_solver();
     s->c = c;
@@ -391,9 +393,10 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
     d.L = c->L; d.ldB = (c->L + 1) & ~1;
     d.Mloc = c->Mloc; d.Mglob = c->Mglob; d.moff = c->moff;
     d.H = (int)H;
-    if (kind == VBMF_B200_DUAL) { d.H0 = (int)h_split; d.H1 = (int)(H - h_split); }
+    if (grouped) { d.H0 = (int)h_split; d.H1 = (int)(H - h_split); }
     else { d.H0 = (int)H; d.H1 = (int)h_split; }
-    d.nlabels = (kind == VBMF_B200_DUAL) ? 0 : (int)n_labels;
+    d.M0 = (kind == VBMF_B200_TRIAL) ? (int)M0_global : c->Mglob;
+    d.nlabels = grouped ? 0 : (int)n_labels;
     d.Y = c->Y; d.ldY = c->ldY; d.rowY2 = c->rowY2;
 
     plan_splitk(d.L, d.Mloc, d.H, c->num_sms, &s->S, &s->kchunk);
@@ -464,6 +467,16 @@ extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, in
     memset(&s->h_sc, 0, sizeof(Scalars));
     *out = s;
     return 0;
+}
+
+extern "C" int vbmf_b200_solver_create(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_split, int64_t n_labels,
+                                       const int64_t* labels, int keep_blocks, vbmf_b200_solver** out) {
+    if (kind == VBMF_B200_TRIAL) { set_error("use vbmf_b200_solver_create_trial for vbmf_trial parameters"); return -1; }
+    return solver_create_impl(c, kind, H, h_split, 0, n_labels, labels, keep_blocks, out);
+}
+extern "C" int vbmf_b200_solver_create_trial(vbmf_b200_ctx* c, int64_t H, int64_t H0, int64_t M0_global, int keep_blocks,
+                                             vbmf_b200_solver** out) {
+    return solver_create_impl(c, VBMF_B200_TRIAL, H, H0, M0_global, 0, nullptr, keep_blocks, out);
 }
 
 extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
@@ -666,6 +679,55 @@ extern "C" int vbmf_b200_dual_download(vbmf_b200_solver* s, vbmf_b200_dual_state
     return down_yhat(s, st->YHat);
 }
 
+extern "C" int vbmf_b200_trial_upload(vbmf_b200_solver* s, const vbmf_b200_trial_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_TRIAL, st->L, st->M, st->H)) return -1;
+    if (st->H0 != s->d.H0 || st->M0 != s->d.M0) { set_error("state H0 / M0 do not match the solver"); return -1; }
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    if (sparse_like_upload(s, st)) return -1;
+    Scalars& h = s->h_sc;
+    h.alpha00 = st->alpha01; h.beta00 = st->beta01; h.alpha01 = st->alpha02; h.beta01 = st->beta02; h.alpha02 = st->alpha03; h.beta02 = st->beta03;
+    h.alpha_g0 = st->alpha1; h.alpha_g1 = st->alpha2; h.alpha_g2 = st->alpha3;
+    return push_scalars(s);
+}
+extern "C" int vbmf_b200_trial_download(vbmf_b200_solver* s, vbmf_b200_trial_state* st) {
+    if (!s || !st) { set_error("NULL argument"); return -1; }
+    if (check_dims(s, VBMF_B200_TRIAL, st->L, st->M, st->H)) return -1;
+    VB_CUDA_OK(cudaSetDevice(s->c->device));
+    std::vector<double> tmpCA, tmpBeta, tmpA;
+    const Dev& d = s->d;
+    const size_t MH = (size_t)d.Mloc * d.H;
+    vbmf_b200_trial_state w = *st;
+    if (w.CA == nullptr) { tmpCA.resize(MH); w.CA = tmpCA.data(); }
+    if (w.beta == nullptr) { tmpBeta.resize(MH); w.beta = tmpBeta.data(); }
+    if (w.AHat == nullptr && (st->A1Hat || st->A2Hat || st->A3Hat)) { tmpA.resize(MH); w.AHat = tmpA.data(); }
+    if (sparse_like_download(s, &w)) return -1;
+    st->sigmaHat = w.sigmaHat; st->zeta = w.zeta; st->eta = w.eta;
+    const Scalars& h = s->h_sc;
+    st->alpha01 = h.alpha00; st->beta01 = h.beta00; st->alpha02 = h.alpha01; st->beta02 = h.beta01; st->alpha03 = h.alpha02; st->beta03 = h.beta02;
+    st->alpha1 = h.alpha_g0; st->alpha2 = h.alpha_g1; st->alpha3 = h.alpha_g2;
+    if (st->alpha) { st->alpha[0] = h.alpha_g0; st->alpha[1] = h.alpha_g1; st->alpha[2] = h.alpha_g2; }
+    // split the interleaved vectors / AHat into the three groups (src/vbmf_trial.jl:316-319, 383-399 in reverse)
+    const size_t M = (size_t)d.Mloc, H = (size_t)d.H, H0 = (size_t)d.H0, H1 = (size_t)d.H1;
+    const long long m0loc = std::min<long long>(std::max<long long>((long long)d.M0 - d.moff, 0), (long long)M);   // local rows in group 2
+    const size_t M2 = (size_t)m0loc, M3 = M - M2;
+    for (size_t m = 0; m < M; ++m) {
+        for (size_t hh = 0; hh < H; ++hh) {
+            const double ca = w.CA[m * H + hh], be = w.beta[m * H + hh];
+            if (hh < H0) { if (st->CA1) st->CA1[m * H0 + hh] = ca; if (st->beta1) st->beta1[m * H0 + hh] = be; }
+            else if (m < M2) { const size_t k = m * H1 + (hh - H0); if (st->CA2) st->CA2[k] = ca; if (st->beta2) st->beta2[k] = be; }
+            else { const size_t k = (m - M2) * H1 + (hh - H0); if (st->CA3) st->CA3[k] = ca; if (st->beta3) st->beta3[k] = be; }
+        }
+    }
+    if (st->A1Hat) memcpy(st->A1Hat, w.AHat, M * H0 * 8);
+    for (size_t hh = H0; hh < H; ++hh) {
+        const double* colp = w.AHat + hh * M;
+        if (st->A2Hat) memcpy(st->A2Hat + (hh - H0) * M2, colp, M2 * 8);
+        if (st->A3Hat) memcpy(st->A3Hat + (hh - H0) * M3, colp + M2, M3 * 8);
+    }
+    return down_yhat(s, st->YHat);
+}
+
 // ---- enqueue helpers ---------------------------------------------------------------------------------------------------
 static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
     vbmf_b200_ctx* c = s->c;
@@ -787,7 +849,7 @@ static int enq_updateCA(vbmf_b200_solver* s, int flags, bool fused) {
         return k_dense_cov_only(s->c->st, d, 0);
     }
     if (k_update_CA(s->c->st, d)) return -1;
-    if (d.kind == KIND_DUAL && !fused) { if (ctx_allreduce(s->c, d.packed + packed_ex(d), 8)) return -1; s->extras_valid = true; }
+    if ((d.kind == KIND_DUAL || d.kind == KIND_TRIAL) && !fused) { if (ctx_allreduce(s->c, d.packed + packed_ex(d), 8)) return -1; s->extras_valid = true; }
     return 0;
 }
 
@@ -815,15 +877,24 @@ extern "C" int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags) {
                 else rc = k_sigma_only(st, d, flags);
             }
             break;
-        case VBMF_B200_STEP_UPDATE_ALPHA00: case VBMF_B200_STEP_UPDATE_ALPHA01:
-        case VBMF_B200_STEP_UPDATE_BETA00: case VBMF_B200_STEP_UPDATE_BETA01:
-            if (d.kind != KIND_DUAL) { set_error("hyper-prior steps exist for vbmf_dual only"); return -1; }
+        case VBMF_B200_STEP_UPDATE_ALPHA00: case VBMF_B200_STEP_UPDATE_ALPHA01: case VBMF_B200_STEP_UPDATE_ALPHA02:
+        case VBMF_B200_STEP_UPDATE_BETA00: case VBMF_B200_STEP_UPDATE_BETA01: case VBMF_B200_STEP_UPDATE_BETA02:
+            if (d.kind != KIND_DUAL && d.kind != KIND_TRIAL) { set_error("hyper-prior steps exist for vbmf_dual / vbmf_trial only"); return -1; }
+            if (d.kind == KIND_DUAL && (step == VBMF_B200_STEP_UPDATE_ALPHA02 || step == VBMF_B200_STEP_UPDATE_BETA02)) { set_error("vbmf_dual has two ARD groups"); return -1; }
             if (!s->extras_valid) {     // sum(CA_g), sum(log(beta_g)) of the CURRENT vectors; CA / beta stay as uploaded
                 rc = k_update_CA(st, d, 1);
                 if (!rc) rc = ctx_allreduce(s->c, d.packed + packed_ex(d), 8);
                 s->extras_valid = true;
             }
-            if (!rc) rc = k_prior_only(st, d, step - VBMF_B200_STEP_UPDATE_ALPHA00);
+            if (!rc) {
+                int which = 0;      // 0..2 alpha of group 0..2, 3..5 beta of group 0..2
+                switch (step) {
+                    case VBMF_B200_STEP_UPDATE_ALPHA00: which = 0; break; case VBMF_B200_STEP_UPDATE_ALPHA01: which = 1; break;
+                    case VBMF_B200_STEP_UPDATE_ALPHA02: which = 2; break; case VBMF_B200_STEP_UPDATE_BETA00: which = 3; break;
+                    case VBMF_B200_STEP_UPDATE_BETA01: which = 4; break; default: which = 5; break;
+                }
+                rc = k_prior_only(st, d, which);
+            }
             break;
         default: set_error("unknown step %d", step); return -1;
     }
@@ -902,7 +973,7 @@ extern "C" int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, in
     if (!s->q_valid && enq_q_ata(s, false)) return -1;
     if (k_trbq(st, d)) return -1;
     if (k_lower_bound(st, d, trim, trimmed, 0)) return -1;
-    if (ctx_allreduce(s->c, d.lbacc, 9)) return -1;
+    if (ctx_allreduce(s->c, d.lbacc, 11)) return -1;
     if (k_lower_bound(st, d, trim, trimmed, 1)) return -1;
     if (pull_scalars(s)) return -1;
     *out = s->h_sc.lb;
@@ -1031,6 +1102,20 @@ extern "C" int vbmf_b200_dual_run(vbmf_b200_ctx* c, vbmf_b200_dual_state* st, in
     const int flags = (diag_var ? F_DIAG_VAR : 0) | (full_cov ? F_FULL_COV : 0) | (est_cb ? F_EST_CB : 0) | (est_priors ? F_EST_PRIORS : 0);
     if (!rc) rc = vbmf_b200_solver_run(s, niter, eps, flags, norm_mode, iters, d);
     if (rc == 0 || rc == -2) { int r2 = vbmf_b200_dual_download(s, st); if (r2) rc = r2; }
+    vbmf_b200_solver_destroy(s);
+    return rc;
+}
+
+extern "C" int vbmf_b200_trial_run(vbmf_b200_ctx* c, vbmf_b200_trial_state* st, int64_t niter, double eps, int diag_var, int full_cov,
+                                   int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d) {
+    if (!c || !st) { set_error("NULL argument"); return -1; }
+    if (st->H < st->H0) { set_error("H must be at least H0!"); return -1; }
+    vbmf_b200_solver* s = nullptr;
+    if (vbmf_b200_solver_create_trial(c, st->H, st->H0, st->M0, st->SigmaATVec_blocks != nullptr, &s)) return -1;
+    int rc = vbmf_b200_trial_upload(s, st);
+    const int flags = (diag_var ? F_DIAG_VAR : 0) | (full_cov ? F_FULL_COV : 0) | (est_cb ? F_EST_CB : 0) | (est_priors ? F_EST_PRIORS : 0);
+    if (!rc) rc = vbmf_b200_solver_run(s, niter, eps, flags, norm_mode, iters, d);
+    if (rc == 0 || rc == -2) { int r2 = vbmf_b200_trial_download(s, st); if (r2) rc = r2; }
     vbmf_b200_solver_destroy(s);
     return rc;
 }

@@ -29,8 +29,9 @@ struct Scalars {
     double alpha0p, beta0p;            // sparse: hyper-prior (alpha0, beta0)
     double alpha;                      // sparse: alpha = alpha0 + 1/2
     double gamma0, delta0, gamma;
-    double alpha00, beta00, alpha01, beta01;   // dual: learned hyper-priors
-    double alpha_g0, alpha_g1;                 // dual: alpha0, alpha1 (= alpha0x + 1/2)
+    double alpha00, beta00, alpha01, beta01;   // dual / trial: learned hyper-priors of groups 0, 1
+    double alpha02, beta02;                    // trial: third group (rows >= M0 of the columns >= H0)
+    double alpha_g0, alpha_g1, alpha_g2;       // posterior shapes alpha_g = alpha0g + 1/2
     double trYTY;                      // global sum(Y.^2)
     double meanSigmaVec;               // mean(sigmaVecHat), diag_var
     double trBQ;                       // sum(BHat .* (Y*AHat))

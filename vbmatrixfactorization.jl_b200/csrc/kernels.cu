@@ -452,7 +452,7 @@ __global__ void mask_kernel(Dev d) {
     }
 }
 int k_mask(cudaStream_t st, const Dev& d) {
-    if (d.kind == KIND_DUAL || d.nlabels <= 0 || d.H1 <= 0) return 0;
+    if (d.kind == KIND_DUAL || d.kind == KIND_TRIAL || d.nlabels <= 0 || d.H1 <= 0) return 0;
     const int n = d.nlabels * d.H1;
     mask_kernel<<<std::max(1, std::min(cdiv(n, 256), 592)), 256, 0, st>>>(d);
     VB_LAUNCH_OK();
@@ -691,36 +691,37 @@ __global__ void __launch_bounds__(256) update_CA_kernel(Dev d, int sums_only) {
     __shared__ double red[32];
     Scalars* sc = d.sc;
     const int H = d.H;
-    const bool dual = d.kind == KIND_DUAL;
-    const double a0 = dual ? sc->alpha00 + 0.5 : sc->alpha;
-    const double a1 = dual ? sc->alpha01 + 0.5 : sc->alpha;
-    const double b0 = dual ? sc->beta00 : sc->beta0p;
-    const double b1 = dual ? sc->beta01 : sc->beta0p;
-    double sca0 = 0.0, sca1 = 0.0, slb0 = 0.0, slb1 = 0.0;
+    const bool grouped = d.kind == KIND_DUAL || d.kind == KIND_TRIAL;
+    const double al[3] = {grouped ? sc->alpha00 + 0.5 : sc->alpha, grouped ? sc->alpha01 + 0.5 : sc->alpha, sc->alpha02 + 0.5};
+    const double be[3] = {grouped ? sc->beta00 : sc->beta0p, grouped ? sc->beta01 : sc->beta0p, sc->beta02};
+    double sca[3] = {0.0, 0.0, 0.0}, slb[3] = {0.0, 0.0, 0.0};
     const long long n = (long long)d.Mloc * H;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int h = (int)(e % H);
-        const bool g1 = dual && h >= d.H0;
+        const int g = (!grouped || h < d.H0) ? 0 : ((d.moff + (int)(e / H) < d.M0) ? 1 : 2);
         double beta, ca;
         if (sums_only) { beta = d.beta[e]; ca = d.CAv[e]; }      // hyper-prior steps right after an upload: state untouched
         else {
             const double a = d.A[e];
-            beta = (g1 ? b1 : b0) + 0.5 * (a * a + d.sdiag[e]);
-            ca = (g1 ? a1 : a0) / beta;
+            beta = (g == 0 ? be[0] : g == 1 ? be[1] : be[2]) + 0.5 * (a * a + d.sdiag[e]);
+            ca = (g == 0 ? al[0] : g == 1 ? al[1] : al[2]) / beta;
             d.beta[e] = beta;
             d.CAv[e] = ca;
         }
-        if (dual) {
-            if (g1) { sca1 += ca; slb1 += log(beta); } else { sca0 += ca; slb0 += log(beta); }
+        if (grouped) {
+            const double lb = log(beta);
+            if (g == 0) { sca[0] += ca; slb[0] += lb; } else if (g == 1) { sca[1] += ca; slb[1] += lb; } else { sca[2] += ca; slb[2] += lb; }
         }
     }
-    if (dual) {
-        sca0 = block_sum(sca0, red); sca1 = block_sum(sca1, red);
-        slb0 = block_sum(slb0, red); slb1 = block_sum(slb1, red);
+    if (grouped) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const double a = block_sum(sca[g], red), b = block_sum(slb[g], red);
+            if (threadIdx.x == 0) { d.part[(size_t)blockIdx.x * 8 + g] = a; d.part[(size_t)blockIdx.x * 8 + 3 + g] = b; }
+        }
         if (threadIdx.x == 0) {
-            double* p = d.part + (size_t)blockIdx.x * 4;
-            p[0] = sca0; p[1] = sca1; p[2] = slb0; p[3] = slb1;
-            if (blockIdx.x == 0 && !sums_only) { sc->alpha_g0 = a0; sc->alpha_g1 = a1; }
+            d.part[(size_t)blockIdx.x * 8 + 6] = 0.0; d.part[(size_t)blockIdx.x * 8 + 7] = 0.0;
+            if (blockIdx.x == 0 && !sums_only) { sc->alpha_g0 = al[0]; sc->alpha_g1 = al[1]; sc->alpha_g2 = al[2]; }
         }
     }
 }
@@ -729,7 +730,7 @@ int k_update_CA(cudaStream_t st, const Dev& d, int sums_only) {
     const int grid = std::max(1, (int)std::min<long long>((n + 1023) / 1024, MAX_PARTS));
     update_CA_kernel<<<grid, 256, 0, st>>>(d, sums_only);
     VB_LAUNCH_OK();
-    if (d.kind == KIND_DUAL) return sum_partials(st, d.part, grid, 4, 4, d.packed + packed_ex(d), d.sc);
+    if (d.kind == KIND_DUAL || d.kind == KIND_TRIAL) return sum_partials(st, d.part, grid, 8, 8, d.packed + packed_ex(d), d.sc);
     return 0;
 }
 
@@ -984,7 +985,7 @@ int k_scale_B(cudaStream_t st, const Dev& d) {
 // ------------------------------------------------------------------------------------------- post step (single CTA)
 // Hyper-parameter / noise updates that only need H x H and scalar data, the convergence test and the loop control.
 enum { POST_CA = 1, POST_CB = 2, POST_SIGMA = 4, POST_A00 = 8, POST_A01 = 16, POST_B00 = 32, POST_B01 = 64, POST_DELTA = 128,
-       POST_NORM_INIT = 256 };
+       POST_NORM_INIT = 256, POST_A02 = 512, POST_B02 = 1024 };
 
 // inverse digamma on [1e-10, 1e10] by Newton from the left (psi is increasing and concave, so the iteration is monotone);
 // stands in for Roots.fzero(f, 1e-10, 1e10) of f(x) = N*log(beta0x) - N*digamma(x) + sum(digamma(alpha) - log(beta_i))
@@ -1092,14 +1093,18 @@ __global__ void __launch_bounds__(256) post_kernel(Dev d, int what, int flags) {
             }
             __syncthreads();
         }
-        if (d.kind == KIND_DUAL && t == 0) {
-            // updateAlpha00!, updateAlpha01!, updateBeta00!, updateBeta01! in this order  src/vbmf_dual.jl:491-497
-            const double N0 = (double)d.Mglob * d.H0, N1 = (double)d.Mglob * d.H1;
+        if ((d.kind == KIND_DUAL || d.kind == KIND_TRIAL) && t == 0) {
+            // alphas of every group first, then the betas (they see the new alphas): src/vbmf_dual.jl:491-497,
+            // src/vbmf_trial.jl:566-573.  EX = [sum(CA_g) g=0..2 | sum(log(beta_g)) g=0..2]
+            const double M1 = (double)d.Mglob - (double)d.M0;
+            const double N[3] = {(double)d.Mglob * d.H0, (double)d.M0 * d.H1, M1 * d.H1};
             double r;
-            if ((what & POST_A00) && solve_alpha(N0, sc->beta00, sc->alpha_g0, EX[2], &r)) sc->alpha00 = r;
-            if ((what & POST_A01) && solve_alpha(N1, sc->beta01, sc->alpha_g1, EX[3], &r)) sc->alpha01 = r;
-            if (what & POST_B00) sc->beta00 = N0 * sc->alpha00 / EX[0];
-            if (what & POST_B01) sc->beta01 = N1 * sc->alpha01 / EX[1];
+            if ((what & POST_A00) && solve_alpha(N[0], sc->beta00, sc->alpha_g0, EX[3], &r)) sc->alpha00 = r;
+            if ((what & POST_A01) && solve_alpha(N[1], sc->beta01, sc->alpha_g1, EX[4], &r)) sc->alpha01 = r;
+            if ((what & POST_A02) && solve_alpha(N[2], sc->beta02, sc->alpha_g2, EX[5], &r)) sc->alpha02 = r;
+            if (what & POST_B00) sc->beta00 = N[0] * sc->alpha00 / EX[0];
+            if (what & POST_B01) sc->beta01 = N[1] * sc->alpha01 / EX[1];
+            if (what & POST_B02) sc->beta02 = N[2] * sc->alpha02 / EX[2];
         }
         __syncthreads();
     }
@@ -1173,6 +1178,7 @@ int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta) {
         if (flags & F_EST_CB) what |= POST_CB;
         what |= POST_SIGMA;
         if (d.kind == KIND_DUAL && (flags & F_EST_PRIORS)) what |= POST_A00 | POST_A01 | POST_B00 | POST_B01;
+        if (d.kind == KIND_TRIAL && (flags & F_EST_PRIORS)) what |= POST_A00 | POST_A01 | POST_A02 | POST_B00 | POST_B01 | POST_B02;
     }
     return post_launch(st, d, what, flags);
 }
@@ -1180,7 +1186,10 @@ int k_norms_init(cudaStream_t st, const Dev& d) { return post_launch(st, d, POST
 int k_updateCB_only(cudaStream_t st, const Dev& d) { return post_launch(st, d, POST_CB, 0); }
 int k_dense_cov_only(cudaStream_t st, const Dev& d, int which) { return post_launch(st, d, which == 0 ? POST_CA : POST_CB, 0); }
 int k_sigma_only(cudaStream_t st, const Dev& d, int flags) { return post_launch(st, d, POST_SIGMA, flags); }
-int k_prior_only(cudaStream_t st, const Dev& d, int which) { return post_launch(st, d, POST_A00 << which, 0); }
+int k_prior_only(cudaStream_t st, const Dev& d, int which) {
+    static const int bits[6] = {POST_A00, POST_A01, POST_A02, POST_B00, POST_B01, POST_B02};
+    return post_launch(st, d, bits[which], 0);
+}
 
 // ------------------------------------------------------------------------------------------- K10: YHat = BHat*AHat'
 // src/vbmf.jl:120-122, src/vbmf_sparse.jl:275-277 -- on demand only (L x M output).
@@ -1219,37 +1228,37 @@ int k_yhat(cudaStream_t st, const Dev& d, double* out, int ldo) {
 // ------------------------------------------------------------------------------------------- K7: lower bound
 // lowerBound / lowerBoundTrimmed: src/vbmf_sparse.jl:435-489, src/vbmf_dual.jl:556-617.  Phase 0 streams the local slice of
 // the MH-length vectors into 9 sums (fixed-order), phase 1 (after the cross-shard all-reduce) assembles the scalar.
-//   acc[0..1] sum(log(beta_g)) all elements, group 0/1      acc[2..3] sum(CA_g) all elements
-//   acc[4] sum(log(beta)) kept   acc[5] sum(CA) kept   acc[6] sum(CA.*(a.^2+s)) kept   acc[7] sum(log(s)) kept   acc[8] #kept
+//   acc[0..2] sum(log(beta_g)) all elements, group 0..2      acc[3..5] sum(CA_g) all elements
+//   acc[6] sum(log(beta)) kept   acc[7] sum(CA) kept   acc[8] sum(CA.*(a.^2+s)) kept   acc[9] sum(log(s)) kept   acc[10] #kept
 __global__ void __launch_bounds__(256) lb_partial_kernel(Dev d, double trim, int trimmed) {
     __shared__ double red[32];
     const int H = d.H;
-    double a[9];
+    const bool grouped = d.kind == KIND_DUAL || d.kind == KIND_TRIAL;
+    double a[11];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) a[i] = 0.0;
+    for (int i = 0; i < 11; ++i) a[i] = 0.0;
     const long long n = (long long)d.Mloc * H;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int h = (int)(e % H);
-        const int g1 = (d.kind == KIND_DUAL && h >= d.H0) ? 1 : 0;
+        const int g = (!grouped || h < d.H0) ? 0 : ((d.moff + (int)(e / H) < d.M0) ? 1 : 2);
         const double av = d.A[e], be = d.beta[e], ca = d.CAv[e], s = d.sdiag[e];
         const double lbv = log(be);
-        a[g1] += lbv;
-        a[2 + g1] += ca;
+        if (g == 0) { a[0] += lbv; a[3] += ca; } else if (g == 1) { a[1] += lbv; a[4] += ca; } else { a[2] += lbv; a[5] += ca; }
         if (!trimmed || fabs(av) > trim) {
-            a[4] += lbv; a[5] += ca; a[6] += ca * (av * av + s); a[7] += log(s); a[8] += 1.0;
+            a[6] += lbv; a[7] += ca; a[8] += ca * (av * av + s); a[9] += log(s); a[10] += 1.0;
         }
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
+    for (int i = 0; i < 11; ++i) {
         const double v = block_sum(a[i], red);
-        if (threadIdx.x == 0) d.part[(size_t)blockIdx.x * 9 + i] = v;
+        if (threadIdx.x == 0) d.part[(size_t)blockIdx.x * 11 + i] = v;
     }
 }
 __global__ void lb_reduce_kernel(Dev d, int nparts) {
     const int i = threadIdx.x;
-    if (i < 9) {
+    if (i < 11) {
         double s = 0.0;
-        for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * 9 + i];
+        for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * 11 + i];
         d.lbacc[i] = s;
     }
 }
@@ -1308,15 +1317,15 @@ __global__ void lb_final_kernel(Dev d, int trimmed) {
     const double elnS = gammaELn_d(sc->eta, log(sc->zeta));
     const double psiG = digamma_pos(sc->gamma);
     const double elnD = H * psiG - sumLogDelta;
-    const double MHk = acc[8];                              // params.MH (kept count when trimmed)
+    const double MHk = acc[10];                             // params.MH (kept count when trimmed)
     double Lb = 0.0;
     Lb += -L * M / 2 * ln2pi + L * M / 2 * elnS;
     Lb += -sc->sigmaHat / 2 * (sc->trYTY - 2 * sc->trBQ + tGAGB);
     if (d.kind == KIND_SPARSE) {
         const double psiA = digamma_pos(sc->alpha);
-        const double elnB = MHk * psiA - acc[4];
+        const double elnB = MHk * psiA - acc[6];
         Lb += -MHk / 2 * ln2pi + 0.5 * elnB;
-        Lb += -(0.5 * acc[6]);
+        Lb += -(0.5 * acc[8]);
         Lb += -L * H / 2 * ln2pi;
         Lb += L / 2 * elnD;
         Lb += -0.5 * trCBGB;
@@ -1324,41 +1333,44 @@ __global__ void lb_final_kernel(Dev d, int trimmed) {
         Lb += (sc->eta0 - 1) * elnS - sc->zeta0 * sc->sigmaHat;
         Lb += MHk * (sc->alpha0p * log(sc->beta0p) - lgamma(sc->alpha0p));
         Lb += (sc->alpha0p - 1) * elnB;
-        Lb += -sc->beta0p * acc[5];
+        Lb += -sc->beta0p * acc[7];
         Lb += H * (sc->gamma0 * log(sc->delta0) - lgamma(sc->gamma0));
         Lb += (sc->gamma0 - 1) * elnD;
         Lb += -sc->gamma0 * sumCB;                          // Q13
-        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[7];
+        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[9];
         Lb += normal_entropy_kron(d.SigmaB, H, d.L, W);
         Lb += sc->eta + log(sc->zeta) + lgamma(sc->eta) + (1 - sc->eta) * digamma_pos(sc->eta);
-        Lb += MHk * (sc->alpha + lgamma(sc->alpha) + (1 - sc->alpha) * psiA) + acc[4];
+        Lb += MHk * (sc->alpha + lgamma(sc->alpha) + (1 - sc->alpha) * psiA) + acc[6];
     } else {
-        const double N0 = M * d.H0, N1 = M * d.H1;
-        const double a0 = sc->alpha_g0, a1 = sc->alpha_g1;
-        const double psi0 = digamma_pos(a0), psi1 = digamma_pos(a1);
-        const double eln0 = N0 * psi0 - acc[0], eln1 = N1 * psi1 - acc[1];
-        Lb += -MHk / 2 * ln2pi + 0.5 * eln0;
-        Lb += 0.5 * eln1;
-        Lb += -(0.5 * acc[6]);
+        // dual (src/vbmf_dual.jl:559-597): groups 0, 1; trial (src/vbmf_trial.jl:633-681): groups 0, 1, 2.  Group sums use the
+        // untrimmed beta_g / CA_g vectors even in lowerBoundTrimmed (only CA, ATVecHat, diagSigmaATVec, MH are trimmed).
+        const int ng = d.kind == KIND_TRIAL ? 3 : 2;
+        const double Ng[3] = {M * d.H0, (double)d.M0 * d.H1, (M - (double)d.M0) * d.H1};
+        const double ag[3] = {sc->alpha_g0, sc->alpha_g1, sc->alpha_g2};
+        const double a0g[3] = {sc->alpha00, sc->alpha01, sc->alpha02};
+        const double b0g[3] = {sc->beta00, sc->beta01, sc->beta02};
+        double psig[3], elng[3];
+        for (int g = 0; g < ng; ++g) { psig[g] = digamma_pos(ag[g]); elng[g] = Ng[g] * psig[g] - acc[g]; }
+        Lb += -MHk / 2 * ln2pi + 0.5 * elng[0];
+        for (int g = 1; g < ng; ++g) Lb += 0.5 * elng[g];
+        Lb += -(0.5 * acc[8]);
         Lb += -L * H / 2 * ln2pi;
         Lb += L / 2 * elnD;
         Lb += -0.5 * trCBGB;
         Lb += sc->eta0 * log(sc->zeta0) - lgamma(sc->eta0);
         Lb += (sc->eta0 - 1) * elnS - sc->zeta0 * sc->sigmaHat;
-        Lb += N0 * (sc->alpha00 * log(sc->beta00) - lgamma(sc->alpha00));
-        Lb += (sc->alpha00 - 1) * eln0;
-        Lb += -sc->beta00 * acc[2];
-        Lb += N1 * (sc->alpha01 * log(sc->beta01) - lgamma(sc->alpha01));
-        Lb += (sc->alpha01 - 1) * eln1;
-        Lb += -sc->beta01 * acc[3];
+        for (int g = 0; g < ng; ++g) {
+            Lb += Ng[g] * (a0g[g] * log(b0g[g]) - lgamma(a0g[g]));
+            Lb += (a0g[g] - 1) * elng[g];
+            Lb += -b0g[g] * acc[3 + g];
+        }
         Lb += H * (sc->gamma0 * log(sc->delta0) - lgamma(sc->gamma0));
         Lb += (sc->gamma0 - 1) * elnD;
         Lb += -sc->gamma0 * sumCB;
-        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[7];
+        Lb += MHk / 2 + MHk / 2 * ln2pi + 0.5 * acc[9];
         Lb += normal_entropy_kron(d.SigmaB, H, d.L, W);
         Lb += sc->eta + log(sc->zeta) + lgamma(sc->eta) + (1 - sc->eta) * digamma_pos(sc->eta);
-        Lb += (N0 > 0 ? N0 * (a0 + lgamma(a0) + (1 - a0) * psi0) : 0.0) + acc[0];
-        Lb += (N1 > 0 ? N1 * (a1 + lgamma(a1) + (1 - a1) * psi1) : 0.0) + acc[1];
+        for (int g = 0; g < ng; ++g) Lb += (Ng[g] > 0 ? Ng[g] * (ag[g] + lgamma(ag[g]) + (1 - ag[g]) * psig[g]) : 0.0) + acc[g];
     }
     Lb += H * (sc->gamma + lgamma(sc->gamma) + (1 - sc->gamma) * psiG) + sumLogDelta;
     sc->lb = Lb;

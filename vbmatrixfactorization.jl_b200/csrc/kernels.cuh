@@ -4,14 +4,17 @@
 
 namespace vb {
 
-enum Kind { KIND_DENSE = 0, KIND_SPARSE = 1, KIND_DUAL = 2 };
+enum Kind { KIND_DENSE = 0, KIND_SPARSE = 1, KIND_DUAL = 2, KIND_TRIAL = 3 };
+// ARD groups of vec(A') for dual / trial: 0: h < H0;  1: h >= H0 and global row < M0;  2: h >= H0 and global row >= M0
+// (vbmf_dual is the case M0 = M, src/vbmf_dual.jl:322-351; vbmf_trial src/vbmf_trial.jl:357-400)
 
 // Plain-old-data view of one solver's device state, passed by value to kernels.
 struct Dev {
     int kind;
     int L, ldB;          // rows of Y; leading dimension of the [H][ldB] column-major L x H buffers
     int Mloc, Mglob, moff;   // columns of Y in this shard / in total / global index of the first local column
-    int H, H0, H1;       // rank; dual: first group width H0, second H1 = H - H0; dense/sparse: H1 masked columns
+    int H, H0, H1;       // rank; dual/trial: first group width H0, second H1 = H - H0; dense/sparse: H1 masked columns
+    int M0;              // trial: global row split of the second column group (dual: = Mglob)
     int nlabels;
     Scalars* sc;
     const double* Y; int ldY;
@@ -76,7 +79,7 @@ int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta);   // CA/C
 int k_updateCB_only(cudaStream_t st, const Dev& d);
 int k_dense_cov_only(cudaStream_t st, const Dev& d, int which);  // 0: CA/invCA  1: CB/invCB
 int k_sigma_only(cudaStream_t st, const Dev& d, int flags);
-int k_prior_only(cudaStream_t st, const Dev& d, int which);      // 0 alpha00, 1 alpha01, 2 beta00, 3 beta01
+int k_prior_only(cudaStream_t st, const Dev& d, int which);      // 0..2 alpha of group 0..2, 3..5 beta of group 0..2
 int k_yhat(cudaStream_t st, const Dev& d, double* out, int ldo); // YHat = BHat * AHat'
 int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int phase);
 int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int rank, double noise, uint64_t seed);
