@@ -94,17 +94,6 @@ template <> struct CfgK1<32>  { static constexpr int WM = K1_WM32, WN = 1, STAGE
 template <> struct CfgK1<64>  { static constexpr int WM = K1_WM64, WN = 2, STAGES = 8, CPS = 1; };
 template <> struct CfgK1<128> { static constexpr int WM = 4, WN = 4, STAGES = 6, CPS = 1; };
 
-// K2: a warp may own any subset of the four 8-row mma tiles of a 32-wide permutation group, so 16 consumer warps (MT = 2,
-// K2_WM = 8) are possible at the 128 x 64 CTA tile as well; measured on B200 they are no faster than 8 warps (35.4 vs
-// 35.8 TFLOP/s at 20000 x 200000 x 64), so 8 stays the default.
-#ifndef K2_WM
-#define K2_WM 4
-#endif
-template <int BN> struct CfgK2;
-template <> struct CfgK2<32>  { static constexpr int WM = K2_WM, WN = 1, STAGES = 5, CPS = 2; };
-template <> struct CfgK2<64>  { static constexpr int WM = K2_WM, WN = 2, STAGES = 8, CPS = 1; };
-template <> struct CfgK2<128> { static constexpr int WM = 4, WN = 4, STAGES = 6, CPS = 1; };
-
 template <int BN> struct Sizes {
     static constexpr int STAGE = (BM + BN) * BK * 8;
     static constexpr int SMEM = Cfg<BN>::STAGES * STAGE + 2 * Cfg<BN>::STAGES * 8 + 1024;
@@ -214,15 +203,15 @@ gemm_ytb_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 __device__ __forceinline__ int perm32(int q, int t) { return 16 * (q >> 2) + 8 * ((q >> 1) & 1) + 2 * t + (q & 1); }
 
 template <int BN>
-__global__ void __launch_bounds__((CfgK2<BN>::WM * CfgK2<BN>::WN + 1) * 32, CfgK2<BN>::CPS)
+__global__ void __launch_bounds__((Cfg<BN>::WM * Cfg<BN>::WN + 1) * 32, Cfg<BN>::CPS)
 gemm_ya_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA,
                double* __restrict__ Qpart, int L, int M, int H, int ldQ, int kchunk, int S,
                const Scalars* __restrict__ sc) {
     if (sc != nullptr && !sc->active) return;
-    constexpr int WM = CfgK2<BN>::WM, WN = CfgK2<BN>::WN, STAGES = CfgK2<BN>::STAGES;
+    constexpr int WM = Cfg<BN>::WM, WN = Cfg<BN>::WN, STAGES = Cfg<BN>::STAGES;
     constexpr int NCW = WM * WN;
     constexpr int MT = BM / WM / 8, NT = BN / WN / 8;
-    static_assert((MT == 1 || MT == 2 || MT % 4 == 0) && (NT == 1 || NT == 2 || NT % 4 == 0), "K2 warp tiles: 1, 2 or 4k mma tiles");
+    static_assert(MT % 4 == 0 && NT % 4 == 0, "K2 needs 32-wide warp tiles");
     constexpr int YB = BM * BK * 8, SB = Sizes<BN>::STAGE;
 
     extern __shared__ uint8_t smem_raw[];
@@ -262,16 +251,10 @@ gemm_ya_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     }
     // ---------------- consumers
     const int r = lane >> 2, j = lane & 3;
+    const int wl0 = (warp / WN) * (MT * 8), wn0 = (warp % WN) * (NT * 8);
     const int chi = (r >> 1) & 1;
-    // byte offset of this lane's element for k4-step sp, relative to the base of its 32-wide permutation group
+    // byte offset of this lane's element for k4-step sp and tile-in-group t, relative to the 32-wide group base
     const uint32_t rowoff = j * 128 + ((r & 1) << 3) + (r >> 2) * BOX;
-    // global mma-tile indices of this warp: group = tile >> 2 (two 16-wide boxes), t = tile & 3 (slot inside the group)
-    const int at0 = (warp / WN) * MT, bt0 = (warp % WN) * NT;
-    uint32_t aoff[MT], boff[NT];
-#pragma unroll
-    for (int a = 0; a < MT; ++a) aoff[a] = (uint32_t)(((at0 + a) >> 2) * (2 * BOX)) + ((((at0 + a) & 3) ^ j) << 4);
-#pragma unroll
-    for (int b = 0; b < NT; ++b) boff[b] = (uint32_t)(((bt0 + b) >> 2) * (2 * BOX)) + ((((bt0 + b) & 3) ^ j) << 4);
 
     uint32_t it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -286,16 +269,16 @@ gemm_ya_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         for (int k = k_begin; k < k_end; k += BK, ++it) {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full0 + 8 * s, ph);
-            const uint32_t ys = base + s * SB + rowoff;
-            const uint32_t as = base + s * SB + YB + rowoff;
+            const uint32_t ys = base + s * SB + (wl0 / 16) * BOX + rowoff;
+            const uint32_t as = base + s * SB + YB + (wn0 / 16) * BOX + rowoff;
 #pragma unroll
             for (int sp = 0; sp < 4; ++sp) {
                 double af[MT], bf[NT];
                 const uint32_t hi = (uint32_t)((chi ^ (sp & 1)) << 6) + sp * 512;
 #pragma unroll
-                for (int a = 0; a < MT; ++a) af[a] = lds64(ys + hi + aoff[a]);
+                for (int a = 0; a < MT; ++a) af[a] = lds64(ys + (a >> 2) * (2 * BOX) + hi + (((a & 3) ^ j) << 4));
 #pragma unroll
-                for (int b = 0; b < NT; ++b) bf[b] = lds64(as + hi + boff[b]);
+                for (int b = 0; b < NT; ++b) bf[b] = lds64(as + (b >> 2) * (2 * BOX) + hi + (((b & 3) ^ j) << 4));
 #pragma unroll
                 for (int a = 0; a < MT; ++a)
 #pragma unroll
@@ -307,13 +290,13 @@ gemm_ya_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         double* slab = Qpart + (size_t)kc * H * ldQ;
 #pragma unroll
         for (int a = 0; a < MT; ++a) {
-            const int l = l0 + 32 * ((at0 + a) >> 2) + perm32(r, (at0 + a) & 3);
+            const int l = l0 + wl0 + 32 * (a >> 2) + perm32(r, a & 3);
             if (l < L) {
 #pragma unroll
                 for (int b = 0; b < NT; ++b) {
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const int h = 32 * ((bt0 + b) >> 2) + perm32(2 * j + i, (bt0 + b) & 3);
+                        const int h = wn0 + 32 * (b >> 2) + perm32(2 * j + i, b & 3);
                         if (h < H) slab[(size_t)h * ldQ + l] = acc[a][b][i];
                     }
                 }
@@ -447,8 +430,8 @@ static int launch_ya_t(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMa
         attr_set = true;
     }
     const int ntl = (L + BM - 1) / BM;
-    const int grid = std::max(1, std::min(ntl * S, num_sms * CfgK2<BN>::CPS));
-    const int threads = (CfgK2<BN>::WM * CfgK2<BN>::WN + 1) * 32;
+    const int grid = std::max(1, std::min(ntl * S, num_sms * Cfg<BN>::CPS));
+    const int threads = (Cfg<BN>::WM * Cfg<BN>::WN + 1) * 32;
     gemm_ya_kernel<BN><<<grid, threads, Sizes<BN>::SMEM, st>>>(*tmY, *tmA, Qpart, L, M, H, ldQ, kchunk, S, sc);
     VB_LAUNCH_OK();
     return 0;
