@@ -23,9 +23,36 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int nparts,
         out[e] = s;
     }
 }
+// many partials, few outputs (Grams of per-CTA partials): 32 outputs x 8 partial-subsets per CTA, subsets combined in fixed
+// order through shared memory -- 8x shorter dependent chains and n/32 CTAs instead of n/256
+__global__ void __launch_bounds__(256) sum_partials_wide_kernel(const double* __restrict__ part, int nparts, size_t stride, size_t n,
+                                                                double* __restrict__ out, const Scalars* sc) {
+    if (sc != nullptr && !sc->active) return;
+    __shared__ double sm[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const size_t e = (size_t)blockIdx.x * 32 + x;
+    double s = 0.0;
+    if (e < n) {
+#pragma unroll 4
+        for (int p = y; p < nparts; p += 8) s += part[(size_t)p * stride + e];
+    }
+    sm[y][x] = s;
+    __syncthreads();
+    if (y == 0 && e < n) {
+        double t = sm[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][x];
+        out[e] = t;
+    }
+}
 static int sum_partials(cudaStream_t st, const double* part, int nparts, size_t stride, size_t n, double* out,
                         const Scalars* sc) {
     if (n == 0) return 0;
+    if (nparts >= 16 && n <= (size_t)1 << 20) {
+        sum_partials_wide_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(part, nparts, stride, n, out, sc);
+        VB_LAUNCH_OK();
+        return 0;
+    }
     int grid = std::max(1, std::min(cdiv((long)n, 256), 1184));
     sum_partials_kernel<<<grid, 256, 0, st>>>(part, nparts, stride, n, out, sc);
     VB_LAUNCH_OK();
@@ -834,14 +861,24 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
 // fixed-order reduction of the per-CTA partials: BtB, DtD, sc->trBQ
 __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
     ACTIVE_OR_RETURN(d);
+    __shared__ double sm[8][33];
     const int H = d.H, n = 2 * H * H + 1;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        double s = 0.0;
-#pragma unroll 8
-        for (int p = 0; p < nparts; ++p) s += d.part[(size_t)p * n + e];
-        if (e < H * H) d.BtB[e] = s;
-        else if (e < 2 * H * H) d.DtD[e - H * H] = s;
-        else d.sc->trBQ = s;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + x;
+    double s = 0.0;
+    if (e < n) {
+#pragma unroll 4
+        for (int p = y; p < nparts; p += 8) s += d.part[(size_t)p * n + e];
+    }
+    sm[y][x] = s;
+    __syncthreads();
+    if (y == 0 && e < n) {
+        double t = sm[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][x];
+        if (e < H * H) d.BtB[e] = t;
+        else if (e < 2 * H * H) d.DtD[e - H * H] = t;
+        else d.sc->trBQ = t;
     }
 }
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
@@ -858,7 +895,7 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     if (H <= 16) BEPI(1, 16, 32) else if (H <= 32) BEPI(2, 16, 32) else if (H <= 64) BEPI(4, 16, 32) else BEPI(4, 32, 16)
 #undef BEPI
     VB_LAUNCH_OK();
-    B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 256)), 256, 0, st>>>(d, grid);
+    B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid);
     VB_LAUNCH_OK();
     return 0;
 }
