@@ -95,12 +95,14 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
         const double id = 1.0 / d;
         const double t = myk * id;
         const bool piv = lane == k;
-        const double alpha = piv ? 0.0 : 1.0, beta = piv ? id : -t;
+        // one FMA per element for every lane: the pivot lane's own column IS column k (a[q] == ck), so
+        // ck*(id - 1) + a[q] = ck*id there; elsewhere a[q] - ck*t
+        const double beta = piv ? id - 1.0 : -t;
 #pragma unroll
         for (int q = 0; q < HP; q += 2) {
             const double2 ck = *reinterpret_cast<const double2*>(c + q);
-            a[q] = fma(ck.x, beta, a[q] * alpha);
-            a[q + 1] = fma(ck.y, beta, a[q + 1] * alpha);
+            a[q] = fma(ck.x, beta, a[q]);
+            a[q + 1] = fma(ck.y, beta, a[q + 1]);
         }
         a[k] = piv ? -id : t;
     }
