@@ -112,6 +112,11 @@ def cpu_reference(L, M, H, kind, flags, steps, warmup, budget_s):
     M_s << M columns; one VB iteration is linear in M, so full-size iterations/s = sample iterations/s * M_s/M)."""
     from oracle import vbmf_oracle as vo
     cores = os.cpu_count() or 1
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     # size the sample from a measured GEMM rate so the whole run fits the budget
     n = 1024
     a = np.random.default_rng(0).standard_normal((n, n))

@@ -43,7 +43,7 @@ def _f(a, shape=None):
 
 
 def _ptr(a):
-    return a.ctypes.data_as(L_.p_f64) if a is not None else None
+    return a.ctypes.data if a is not None else None
 
 
 def shard_columns(M, world, rank):
@@ -122,7 +122,7 @@ class Context:
         """`preprocess(Y, lambda)` (src/util.jl:73-87) on the resident Y; returns the kept rows (1-based)."""
         rows = np.zeros(max(self.L, 1), dtype=np.int64)
         Ln = C.c_int64()
-        L_.check(self.lib.vbmf_b200_preprocess_Y(self.h, float(lam), C.byref(Ln), rows.ctypes.data_as(L_.p_i64)))
+        L_.check(self.lib.vbmf_b200_preprocess_Y(self.h, float(lam), C.byref(Ln), rows.ctypes.data))
         self.L = Ln.value
         self._key = None
         return rows[:Ln.value].copy()
@@ -351,7 +351,7 @@ def _dense_struct(p, want_yhat):
     st.L, st.M, st.H, st.H1 = p.L, p.M, H, p.H1
     p.labels = _labels(p.labels)
     st.n_labels = p.labels.size
-    st.labels = p.labels.ctypes.data_as(L_.p_i64) if p.labels.size else None
+    st.labels = p.labels.ctypes.data if p.labels.size else None
     st.AHat = _ptr(_ensure(p, "AHat", (p.M, H)))
     st.BHat = _ptr(_ensure(p, "BHat", (p.L, H)))
     for f in ("SigmaA", "SigmaB", "CA", "CB", "invCA", "invCB"):
@@ -394,7 +394,7 @@ def _sparse_struct(p, want_yhat, want_blocks):
     st.H1 = p.H1
     p.labels = _labels(p.labels)
     st.n_labels = p.labels.size
-    st.labels = p.labels.ctypes.data_as(L_.p_i64) if p.labels.size else None
+    st.labels = p.labels.ctypes.data if p.labels.size else None
     st.alpha0, st.beta0, st.alpha = p.alpha0, p.beta0, p.alpha
     return st
 
@@ -483,7 +483,7 @@ class Solver:
             L_.check(self.lib.vbmf_b200_solver_create_trial(ctx.h, p.H, p.H0, p.M0, 1 if keep_blocks else 0, C.byref(h)))
         else:
             L_.check(self.lib.vbmf_b200_solver_create(ctx.h, p.kind, p.H, split, labels.size,
-                                                      labels.ctypes.data_as(L_.p_i64) if labels.size else None,
+                                                      labels.ctypes.data if labels.size else None,
                                                       1 if keep_blocks else 0, C.byref(h)))
         self.h, self.kind, self.keep_blocks = h, p.kind, keep_blocks
 
