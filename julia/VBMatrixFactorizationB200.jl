@@ -13,9 +13,10 @@
 module VBMatrixFactorizationB200
 
 using VBMatrixFactorization
-import VBMatrixFactorization: vbmf_parameters, vbmf_sparse_parameters, vbmf_dual_parameters
+import VBMatrixFactorization: vbmf_parameters, vbmf_sparse_parameters, vbmf_dual_parameters, vbmf_trial_parameters
 
-export b200_context, b200_close, vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, lowerBound, lowerBoundTrimmed
+export b200_context, b200_close, vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, vbmf_trial!, vbmf_trial,
+       lowerBound, lowerBoundTrimmed, vbls_batched!, preprocess
 
 const LIB = get(ENV, "VBMF_B200_LIB", "libvbmf_b200.so")
 
@@ -49,6 +50,20 @@ immutable DualState         # vbmf_b200_dual_state   <->  vbmf_dual_parameters (
     alpha00::Float64; beta00::Float64; alpha0::Float64; beta0::Ptr{Float64}; CA1::Ptr{Float64}
     alpha01::Float64; beta01::Float64; alpha1::Float64; beta1::Ptr{Float64}; CB::Ptr{Float64}
     gamma0::Float64; delta0::Float64; gamma::Float64; delta::Ptr{Float64}
+    sigmaHat::Float64; eta0::Float64; zeta0::Float64; eta::Float64; zeta::Float64
+    sigmaVecHat::Ptr{Float64}; etaVec::Ptr{Float64}; zetaVec::Ptr{Float64}
+    YHat::Ptr{Float64}; trYTY::Float64
+end
+
+immutable TrialState        # vbmf_b200_trial_state  <->  vbmf_trial_parameters (src/vbmf_trial.jl:68-129)
+    L::Int64; M::Int64; M0::Int64; M1::Int64; MH::Int64; H::Int64; H0::Int64; H1::Int64
+    AHat::Ptr{Float64}; ATVecHat::Ptr{Float64}; SigmaATVec_blocks::Ptr{Float64}; diagSigmaATVec::Ptr{Float64}; SigmaA::Ptr{Float64}
+    A1Hat::Ptr{Float64}; A2Hat::Ptr{Float64}; A3Hat::Ptr{Float64}; BHat::Ptr{Float64}; SigmaB::Ptr{Float64}
+    CA::Ptr{Float64}; alpha::Ptr{Float64}; beta::Ptr{Float64}
+    CA1::Ptr{Float64}; alpha01::Float64; beta01::Float64; alpha1::Float64; beta1::Ptr{Float64}
+    CA2::Ptr{Float64}; alpha02::Float64; beta02::Float64; alpha2::Float64; beta2::Ptr{Float64}
+    CA3::Ptr{Float64}; alpha03::Float64; beta03::Float64; alpha3::Float64; beta3::Ptr{Float64}
+    CB::Ptr{Float64}; gamma0::Float64; delta0::Float64; gamma::Float64; delta::Ptr{Float64}
     sigmaHat::Float64; eta0::Float64; zeta0::Float64; eta::Float64; zeta::Float64
     sigmaVecHat::Ptr{Float64}; etaVec::Ptr{Float64}; zetaVec::Ptr{Float64}
     YHat::Ptr{Float64}; trYTY::Float64
@@ -158,6 +173,67 @@ function vbmf_dual(ctx::B200Context, Y, p_in::vbmf_dual_parameters, niter::Int; 
     p = deepcopy(p_in)
     d = vbmf_dual!(ctx, Y, p, niter; kw...)
     return p, d
+end
+
+# ---- vbmf_trial! (src/vbmf_trial.jl:528) -----------------------------------------------------------------------------------------
+function trial_state(p::vbmf_trial_parameters)
+    TrialState(p.L, p.M, p.M0, p.M1, p.MH, p.H, p.H0, p.H1, pointer(p.AHat), pointer(p.ATVecHat), convert(Ptr{Float64}, C_NULL),
+               pointer(p.diagSigmaATVec), pointer(p.SigmaA), pointer(p.A1Hat), pointer(p.A2Hat), pointer(p.A3Hat), pointer(p.BHat),
+               pointer(p.SigmaB), pointer(p.CA), pointer(p.alpha), pointer(p.beta),
+               pointer(p.CA1), p.alpha01, p.beta01, p.alpha1, pointer(p.beta1), pointer(p.CA2), p.alpha02, p.beta02, p.alpha2, pointer(p.beta2),
+               pointer(p.CA3), p.alpha03, p.beta03, p.alpha3, pointer(p.beta3), pointer(p.CB), p.gamma0, p.delta0, p.gamma, pointer(p.delta),
+               p.sigmaHat, p.eta0, p.zeta0, p.eta, p.zeta, pointer(p.sigmaVecHat), pointer(p.etaVec), pointer(p.zetaVec), pointer(p.YHat), p.trYTY)
+end
+function vbmf_trial!(ctx::B200Context, Y::Array{Float64,2}, p::vbmf_trial_parameters, niter::Int; eps::Float64 = 1e-6,
+                     diag_var::Bool = false, full_cov::Bool = false, verb = false, est_priors = true, est_cb::Bool = true,
+                     norm = :spectral)
+    attach!(ctx, Y)
+    p.YHat = Array{Float64}(p.L, p.M)
+    st = Ref(trial_state(p))
+    iters = Ref{Int64}(0); d = Ref{Float64}(0.0)
+    check(ccall((:vbmf_b200_trial_run, LIB), Cint,
+                (Ptr{Void}, Ref{TrialState}, Int64, Float64, Cint, Cint, Cint, Cint, Cint, Ref{Int64}, Ref{Float64}),
+                ctx.handle, st, niter, eps, diag_var, full_cov, est_priors, est_cb, NORM[norm], iters, d))
+    s = st[]
+    p.sigmaHat = s.sigmaHat; p.zeta = s.zeta
+    p.alpha01 = s.alpha01; p.beta01 = s.beta01; p.alpha02 = s.alpha02; p.beta02 = s.beta02; p.alpha03 = s.alpha03; p.beta03 = s.beta03
+    p.alpha1 = s.alpha1; p.alpha2 = s.alpha2; p.alpha3 = s.alpha3
+    verb && print("Factorization finished after ", iters[], " iterations, eps = ", d[], "\n")
+    return d[]
+end
+function vbmf_trial(ctx::B200Context, Y, p_in::vbmf_trial_parameters, niter::Int; kw...)
+    p = deepcopy(p_in)
+    d = vbmf_trial!(ctx, Y, p, niter; kw...)
+    return p, d
+end
+
+# ---- vbls! for many bags in one launch (examples/mil_util.jl:179-203, 504-511) --------------------------------------------------
+# Ys[k] is the L x M_k matrix of problem k, ps[k] its vbmf_dual_parameters (all with the same L, H, H0).
+function vbls_batched!(ctx::B200Context, Ys::Vector{Array{Float64,2}}, ps::Vector{vbmf_dual_parameters}, niter::Int; full_cov::Bool = false)
+    n = length(ps)
+    for p in ps; p.YHat = Array{Float64}(p.L, p.M); end
+    sts = [Ref(dual_state(p)) for p in ps]
+    yptr = Ptr{Float64}[pointer(Y) for Y in Ys]
+    sptr = Ptr{Void}[Base.unsafe_convert(Ptr{Void}, Base.unsafe_convert(Ptr{DualState}, r)) for r in sts]
+    check(ccall((:vbmf_b200_batched_vbls, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Ptr{Float64}}, Ptr{Ptr{Void}}, Int64, Cint),
+                ctx.handle, 2, n, yptr, sptr, niter, full_cov ? 2 : 0))
+    for (p, r) in zip(ps, sts)
+        p.sigmaHat = r[].sigmaHat; p.zeta = r[].zeta; p.alpha0 = r[].alpha0; p.alpha1 = r[].alpha1
+    end
+    return [p.AHat for p in ps]
+end
+
+# ---- preprocess(Y, lambda) (src/util.jl:73-87) on the device; the processed matrix stays resident -----------------------------------
+function preprocess(ctx::B200Context, Y::Array{Float64,2}, lambda::Float64; verb = false)
+    attach!(ctx, Y, force = true)
+    L, M = size(Y)
+    Lnew = Ref{Int64}(0); rows = Array{Int64}(L)
+    check(ccall((:vbmf_b200_preprocess_Y, LIB), Cint, (Ptr{Void}, Float64, Ref{Int64}, Ptr{Int64}), ctx.handle, lambda, Lnew, rows))
+    verb && println("Original problem size: $L rows, $(L - Lnew[]) rows not relevant and are not used.")
+    out = Array{Float64}(Lnew[], M)
+    check(ccall((:vbmf_b200_download_Y, LIB), Cint, (Ptr{Void}, Ptr{Float64}, Int64), ctx.handle, out, Lnew[]))
+    ctx.Yid = object_id(out)          # the resident matrix is `out`
+    return out
 end
 
 # ---- lowerBound / lowerBoundTrimmed (src/vbmf_sparse.jl:435,478; src/vbmf_dual.jl:556,606) and the step functions -------------
