@@ -439,3 +439,30 @@ def test_trial_vs_oracle(G, ctx, L, M, H, H0, M0, full_cov, diag_var, est_priors
             assert abs(lb - lb_o) <= 1e-9 * abs(lb_o) and abs(lbt - lbt_o) <= 1e-9 * abs(lbt_o), (lb, lb_o, lbt, lbt_o)
         else:
             assert np.isnan(lb) == np.isnan(lb_o)
+
+
+# ------------------------------------------------------------------------------------------------ wide ranks (BN = 128 tiles, padded epilogues)
+@pytest.mark.parametrize("kind,L,M,H", [("dense", 300, 700, 100), ("dense", 1024, 4096, 128), ("dual", 2048, 8192, 128),
+                                        ("sparse", 200, 900, 77), ("sparse_full", 150, 260, 48)])
+def test_wide_rank(G, ctx, kind, L, M, H):
+    """H up to 128 (config 5's rank), H not a multiple of 8 / 16 (padded DMMA epilogues), odd H (SIMT K2), CTA-per-matrix K4."""
+    Y = synth(L, M, max(2, H // 4), seed=H)
+    Yf = np.asfortranarray(Y)
+    rng = np.random.default_rng(H)
+    if kind == "dense":
+        p = vo.vbmf_init(Y, H, rng=rng)
+        q = G.to_gpu_params(p)
+        vo.vbmf_run(Y, p, 2, eps=0.0, est_covs=True, est_var=True)
+        G.vb.vbmf_(Yf, q, 2, eps=0.0, est_covs=True, est_var=True, ctx=ctx, yhat=False)
+    elif kind == "dual":
+        p = vo.vbmf_dual_init(Y, H, H // 2, rng=rng)
+        q = G.to_gpu_params(p)
+        vo.vbmf_dual_run(Y, p, 2, eps=0.0)
+        G.vb.vbmf_dual_(Yf, q, 2, eps=0.0, ctx=ctx, yhat=False)
+    else:
+        full = kind == "sparse_full"
+        p = vo.vbmf_sparse_init(Y, H, rng=rng)
+        q = G.to_gpu_params(p)
+        vo.vbmf_sparse_run(Y, p, 2, eps=0.0, full_cov=full)
+        G.vb.vbmf_sparse_(Yf, q, 2, eps=0.0, full_cov=full, ctx=ctx, yhat=False)
+    G.compare(q, p, 1e-9)
