@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "linalg.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace vb {
 
@@ -859,6 +860,100 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
     tr = block_sum(tr, red);
     if (threadIdx.x == 0) out[2 * H * H] = tr;
 }
+// DMMA version of the same epilogue for H <= 64 (HP8 = H rounded up to 8, shared pitch = 4 mod 16 as in the A epilogue):
+//   Bn = (c .* Qtile) * SigmaB [/ sigma2]        32 x HP8 x HP8 product, 4 x HP8/8 mma tiles over 8 warps
+//   G_B += Bn' Bn,  G_D += Dn' Dn                 accumulators in registers across the CTA's tiles
+template <int TPW>   // Gram tiles per warp: ceil((HP8/8)^2 / 8)
+__global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
+    double* Ss = sm;                 // [HP8][ld] SigmaB, zero padded
+    double* T = Ss + HP8 * ld;       // [32][ld]  scaled Q tile
+    double* Bn = T + 32 * ld;        // [32][ld]
+    double* Dn = Bn + 32 * ld;       // [32][ld]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+    const Scalars* sc = d.sc;
+    const double* Q = d.packed + packed_q(d);
+    for (int e = threadIdx.x; e < HP8 * ld; e += 256) {
+        const int i = e / ld, c = e - i * ld;
+        Ss[e] = (i < H && c < H) ? d.SigmaB[i * H + c] : 0.0;
+    }
+    const bool dense = d.kind == KIND_DENSE;
+    const double s2 = sc->sigma2, sh = sc->sigmaHat;
+    double gB[TPW][2], gD[TPW][2];
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) { gB[q][0] = gB[q][1] = 0.0; gD[q][0] = gD[q][1] = 0.0; }
+    double tr = 0.0;
+    const int ntiles = (d.L + 31) / 32;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int l0 = tile * 32, nr = min(32, d.L - l0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
+            const int h = e >> 5, i = e & 31;
+            double q = 0.0;
+            if (i < nr && h < H) {
+                q = Q[(size_t)h * d.ldB + l0 + i];
+                if (!dense) q *= diag_var ? d.sigmaVec[l0 + i] : sh;
+            }
+            T[i * ld + h] = q;
+        }
+        __syncthreads();
+        for (int idx = warp; idx < 4 * nt8; idx += 8) {
+            const int mt = idx & 3, nt = idx >> 2;
+            double c2[2] = {0.0, 0.0};
+#pragma unroll 8
+            for (int k0 = 0; k0 < HP8; k0 += 4) dmma_acc(c2, T[(8 * mt + r) * ld + k0 + j], Ss[(k0 + j) * ld + 8 * nt + r]);
+            const int row = 8 * mt + r;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int col = 8 * nt + 2 * j + i;
+                double bn = 0.0, dn = 0.0;
+                if (row < nr && col < H) {
+                    double v = c2[i];
+                    if (dense) v /= s2;
+                    const size_t g = (size_t)col * d.ldB + l0 + row;
+                    const double old = d.B[g];
+                    d.Bold[g] = old;
+                    dn = v - old;
+                    d.D[g] = dn;
+                    d.B[g] = v;
+                    tr = fma(v, Q[g], tr);
+                    bn = v;
+                }
+                Bn[row * ld + col] = bn;
+                Dn[row * ld + col] = dn;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            const int idx = warp + 8 * q;
+            if (idx < nt8 * nt8) {
+                const int at = idx / nt8, bt = idx - at * nt8;
+#pragma unroll
+                for (int i0 = 0; i0 < 32; i0 += 4) {
+                    dmma_acc(gB[q], Bn[(i0 + j) * ld + 8 * at + r], Bn[(i0 + j) * ld + 8 * bt + r]);
+                    dmma_acc(gD[q], Dn[(i0 + j) * ld + 8 * at + r], Dn[(i0 + j) * ld + 8 * bt + r]);
+                }
+            }
+        }
+    }
+    double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+        const int idx = warp + 8 * q;
+        if (idx < nt8 * nt8) {
+            const int at = idx / nt8, bt = idx - at * nt8;
+            const int a = 8 * at + r, b = 8 * bt + 2 * j;
+            if (a < H && b < H) { out[a * H + b] = gB[q][0]; out[H * H + a * H + b] = gD[q][0]; }
+            if (a < H && b + 1 < H) { out[a * H + b + 1] = gB[q][1]; out[H * H + a * H + b + 1] = gD[q][1]; }
+        }
+    }
+    tr = block_sum(tr, red);
+    if (threadIdx.x == 0) out[2 * H * H] = tr;
+}
 // fixed-order reduction of the per-CTA partials: BtB, DtD, sc->trBQ
 __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
     ACTIVE_OR_RETURN(d);
@@ -885,6 +980,24 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H, dv = (flags & F_DIAG_VAR) ? 1 : 0;
     const int grid = std::max(1, std::min(cdiv(d.L, H > 64 ? 16 : 32), 148));
+    if (H <= 64 && getenv("VBMF_B200_BEPI_SIMT") == nullptr) {
+        const int HP8 = (H + 7) & ~7;
+        const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
+        static bool done = false;
+        if (!done) {
+            const int mx = (int)((64 + 96) * pitch4(64) * 8);
+            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            done = true;
+        }
+        const int grid2 = std::max(1, std::min(cdiv(d.L, 32), 296));      // two CTAs per SM: the tile chain is latency bound
+        if (HP8 <= 32) B_epilogue_dmma_kernel<2><<<grid2, 256, smem, st>>>(d, dv);
+        else B_epilogue_dmma_kernel<8><<<grid2, 256, smem, st>>>(d, dv);
+        VB_LAUNCH_OK();
+        B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2);
+        VB_LAUNCH_OK();
+        return 0;
+    }
 #define BEPI(RR, TDD, TRR)                                                                                                   \
     {                                                                                                                        \
         static bool done = false;                                                                                            \
