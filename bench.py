@@ -224,7 +224,6 @@ def run_c2(args):
     cpu = None
     if not args.no_cpu:
         from oracle import vbmf_oracle as vo
-        from tests.gpu_helpers import to_gpu_params  # noqa: F401  (only to keep the import graph obvious)
         rngc = np.random.default_rng(SEED)
         k = 24
         t0 = time.perf_counter()
