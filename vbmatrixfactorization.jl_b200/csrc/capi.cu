@@ -368,6 +368,9 @@ struct vbmf_b200_solver {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_b = nullptr, ev_p = nullptr;
     bool post_pending = false;
+    // small problems are launch bound: one iteration is captured into a CUDA graph and replayed
+    cudaGraphExec_t gexec = nullptr;
+    int gexec_flags = -1;
     Scalars h_sc;
 };
 
@@ -484,6 +487,7 @@ extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st);
     if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->gexec) cudaGraphExecDestroy(s->gexec);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
     if (s->ev_p) cudaEventDestroy(s->ev_p);
     if (s->arena) cudaFree(s->arena);
@@ -937,11 +941,45 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
     if (k_set_control(st, d, (int)niter, eps, norm_mode, 0)) return -1;
     s->btb_valid = false;
     if (enq_gram_B(s, flags) || k_norms_init(st, d)) return -1;      // old = BHat, src/vbmf.jl:188
-    const int CHUNK = 4;
     int64_t enq = 0;
     int slot = 0;
     bool pending = false;
-    while (enq < niter) {
+    // Launch-bound regime (one iteration is ~12 launches of a few microseconds each): replay one captured iteration.
+    const bool graph_mode = s->c->world == 1 && !s->c->profile && niter >= 4 && getenv("VBMF_B200_NO_GRAPH") == nullptr &&
+                            (double)d.L * (double)std::max(d.Mloc, 1) * (double)d.H < 4e9;
+    if (graph_mode) {
+        if (enq_iteration(s, flags) || wait_post(s)) return -1;       // first iteration eagerly (also settles one-time kernel attributes)
+        enq = 1;
+        if (s->gexec == nullptr || s->gexec_flags != flags) {
+            if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            VB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = enq_iteration(s, flags);
+            if (!rc) rc = wait_post(s);                              // joins the side stream back into the capture
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc || e != cudaSuccess || graph == nullptr) { if (!rc) set_error("CUDA graph capture failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+            e = cudaGraphInstantiate(&s->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); s->gexec = nullptr; return -1; }
+            s->gexec_flags = flags;
+        }
+        const int CHUNK_G = 8;
+        while (enq < niter) {
+            const int64_t c = std::min<int64_t>(CHUNK_G, niter - enq);
+            for (int64_t i = 0; i < c; ++i) VB_CUDA_OK(cudaGraphLaunch(s->gexec, st));
+            enq += c;
+            VB_CUDA_OK(cudaMemcpyAsync(&s->h_flag[slot], &d.sc->active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            VB_CUDA_OK(cudaEventRecord(s->ev[slot], st));
+            if (pending) {
+                VB_CUDA_OK(cudaEventSynchronize(s->ev[slot ^ 1]));
+                if (s->h_flag[slot ^ 1] == 0) break;
+            }
+            pending = true;
+            slot ^= 1;
+        }
+    }
+    const int CHUNK = 4;
+    while (!graph_mode && enq < niter) {
         const int64_t c = std::min<int64_t>(CHUNK, niter - enq);
         for (int64_t i = 0; i < c; ++i) if (enq_iteration(s, flags)) return -1;
         enq += c;
