@@ -154,7 +154,7 @@ def run_reference(args, L, M, H, kind, flags, desc):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    cb = cpu_reference(L, M, H, kind, flags, args.steps, args.warmup, budget_s=150.0)
+    cb = cpu_reference(L, M, H, kind, flags, args.steps, args.warmup, budget_s=float(os.environ.get("VBMF_BENCH_CPU_BUDGET_S", 150.0)))
     line = {"impl": "reference", "metric": "VB iterations/s at %dx%dx%d (dense vbmf, Float64)" % (L, M, H) if kind == "dense" else
             "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, kind),
             "value": cb["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
