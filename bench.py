@@ -383,7 +383,7 @@ def main():
             traffic = None
     achieved = flops_per_launch / (dom_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic, "frac_of_nominal_40_tflops": achieved / 40.0,
                 "peak_source": "measured FP64 DMMA issue-rate microbenchmark on this pool's B200 (tools/microbench, profiles/"
                                "r01_fp64_peak_microbench.jsonl); MEASURED_PEAKS.json carries no FP64 figure; cuBLAS DGEMM reaches 35.4",
                 "algorithmic_flops_per_launch": flops_per_launch,
