@@ -226,9 +226,14 @@ extern "C" int vbmf_b200_attach_Y(vbmf_b200_ctx* c, const double* Y, int64_t L, 
     if (!c || (!Y && M_local > 0)) { set_error("attach_Y: NULL argument"); return -1; }
     if (ldY < L) { set_error("attach_Y: ldY < L"); return -1; }
     if (ctx_alloc_Y(c, L, M_local, M_global, col_offset)) return -1;
-    if (M_local > 0)
-        VB_CUDA_OK(cudaMemcpy2DAsync(c->Y, (size_t)c->ldY * 8, Y, (size_t)ldY * 8, (size_t)L * 8, (size_t)M_local,
-                                     cudaMemcpyHostToDevice, c->st));
+    if (M_local > 0) {
+        if (ldY == L && c->ldY == L) {       // contiguous on both sides: one plain copy (full PCIe rate from pinned memory)
+            VB_CUDA_OK(cudaMemcpyAsync(c->Y, Y, (size_t)L * (size_t)M_local * 8, cudaMemcpyHostToDevice, c->st));
+        } else {
+            VB_CUDA_OK(cudaMemcpy2DAsync(c->Y, (size_t)c->ldY * 8, Y, (size_t)ldY * 8, (size_t)L * 8, (size_t)M_local,
+                                         cudaMemcpyHostToDevice, c->st));
+        }
+    }
     return ctx_finish_Y(c);
 }
 
