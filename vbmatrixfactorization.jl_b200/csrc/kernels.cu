@@ -275,6 +275,76 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restr
         }
 }
 
+// DMMA Gram: G = X'X over 32-row tiles staged in shared memory with the pitch-4 layout (see the A epilogue); accumulators
+// in registers across the CTA's tiles, one partial per CTA.
+__device__ __forceinline__ void dmma_acc2(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int pitch4g(int hp8) { return ((hp8 + 11) / 16) * 16 + 4; }
+template <int TPW, bool AMAT>
+__global__ void __launch_bounds__(256) gram_dmma_kernel(const double* __restrict__ X, int n, int H, int ldx, double* __restrict__ part,
+                                                        const Scalars* sc) {
+    if (!sc->active) return;
+    extern __shared__ double sm[];
+    const int HP8 = (H + 7) & ~7, ld = pitch4g(HP8), nt8 = HP8 / 8;
+    double* T = sm;     // [32][ld]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+    double g[TPW][2];
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) { g[q][0] = 0.0; g[q][1] = 0.0; }
+    const int ntiles = (n + 31) / 32;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * 32, nr = min(32, n - r0);
+        __syncthreads();
+        if (AMAT) {
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
+                const int i = e / HP8, c = e - i * HP8;
+                T[i * ld + c] = (i < nr && c < H) ? X[(size_t)(r0 + i) * H + c] : 0.0;
+            }
+        } else {
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
+                const int c = e >> 5, i = e & 31;
+                T[i * ld + c] = (i < nr && c < H) ? X[(size_t)c * ldx + r0 + i] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            const int idx = warp + 8 * q;
+            if (idx < nt8 * nt8) {
+                const int at = idx / nt8, bt = idx - at * nt8;
+#pragma unroll
+                for (int i0 = 0; i0 < 32; i0 += 4) dmma_acc2(g[q], T[(i0 + j) * ld + 8 * at + r], T[(i0 + j) * ld + 8 * bt + r]);
+            }
+        }
+    }
+    double* out = part + (size_t)blockIdx.x * H * H;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+        const int idx = warp + 8 * q;
+        if (idx < nt8 * nt8) {
+            const int at = idx / nt8, bt = idx - at * nt8;
+            const int a = 8 * at + r, b = 8 * bt + 2 * j;
+            if (a < H && b < H) out[a * H + b] = g[q][0];
+            if (a < H && b + 1 < H) out[a * H + b + 1] = g[q][1];
+        }
+    }
+}
+static int gram_dmma(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, double* out) {
+    const int H = d.H, HP8 = (H + 7) & ~7;
+    const size_t smem = (size_t)32 * pitch4g(HP8) * sizeof(double);
+    const int grid = std::max(1, std::min(cdiv(std::max(n, 1), 32), 148 * (HP8 <= 64 ? 3 : 1)));
+#define GD(TP)                                                                                                          \
+    if (amat) gram_dmma_kernel<TP, true><<<grid, 256, smem, st>>>(X, n, H, d.ldB, d.part, d.sc);                       \
+    else gram_dmma_kernel<TP, false><<<grid, 256, smem, st>>>(X, n, H, d.ldB, d.part, d.sc);
+    if (HP8 <= 32) { GD(2) } else if (HP8 <= 64) { GD(8) } else { GD(32) }
+#undef GD
+    VB_LAUNCH_OK();
+    return sum_partials(st, d.part, grid, (size_t)H * H, (size_t)H * H, out, d.sc);
+}
 static int gram_impl(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, const double* w, int wpow, double* out) {
     const int H = d.H;
     const int nblk = std::max(1, std::min(296, cdiv(std::max(n, 1), 256)));
@@ -290,6 +360,7 @@ static int gram_impl(cudaStream_t st, const Dev& d, const double* X, bool amat, 
     return sum_partials(st, d.part, nblk, (size_t)H * H, (size_t)H * H, out, d.sc);
 }
 int k_gram(cudaStream_t st, const Dev& d, const double* X, bool amat, int n, const double* w, double* out) {
+    if (w == nullptr && n >= 64) return gram_dmma(st, d, X, amat, n, out);     // unweighted: tensor-core path
     return gram_impl(st, d, X, amat, n, w, 1, out);
 }
 int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const double* w, double* out) {
@@ -301,23 +372,23 @@ int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const doubl
 // mode 1: SigmaB = sigma2*inv(A'A + M*SigmaA + sigma2*invCB)            src/vbmf.jl:110-111
 // mode 2: SigmaA <- all-reduced sum of per-column blocks; SigmaB = inv(diag(CB) + c*(A'A + SigmaA)),
 //         c = sigmaHat or mean(sigmaVecHat)                             src/vbmf_sparse.jl:256-265, src/vbmf_dual.jl:294-303
-template <int Q, int NT>   // Q * NT >= H * H
-__global__ void __launch_bounds__(NT, 1) hxh_kernel(Dev d, int mode, int diag_var) {
+template <int HP2>   // H rounded up to a power of two (32, 64, 128); thread t owns column t % HP2, rows t / HP2 + q * (1024 / HP2)
+__global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_var) {
     ACTIVE_OR_RETURN(d);
     __shared__ double cbuf[2 * 128], sbuf[128];
+    constexpr int Q = HP2 * HP2 / 1024, RP = 1024 / HP2;
     const int H = d.H;
     Scalars* sc = d.sc;
     const double* AtA = d.packed + packed_ata(d);
     const double* SA = d.packed + packed_sa(d);
+    const int j = threadIdx.x % HP2, i0 = threadIdx.x / HP2;
     double a[Q];
-    int eij[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const int e = threadIdx.x + q * NT;
-        if (e < H * H) {
-            const int i = e / H, j = e - i * H;
-            eij[q] = i | (j << 8);
-            double v;
+        const int i = i0 + q * RP;
+        double v = (i == j) ? 1.0 : 0.0;               // padding: identity
+        if (i < H && j < H) {
+            const int e = i * H + j;
             if (mode == 0) v = d.BtB[e] + (double)d.L * d.SigmaB[e] + sc->sigma2 * d.invCA[e];
             else if (mode == 1) v = AtA[e] + (double)d.Mglob * d.SigmaA[e] + sc->sigma2 * d.invCB[e];
             else {
@@ -326,25 +397,56 @@ __global__ void __launch_bounds__(NT, 1) hxh_kernel(Dev d, int mode, int diag_va
                 const double c = diag_var ? sc->meanSigmaVec : sc->sigmaHat;
                 v = ((i == j) ? d.CBv[i] : 0.0) + c * (AtA[e] + sa);
             }
-            a[q] = v;
-        } else { eij[q] = -1; a[q] = 0.0; }
+        }
+        a[q] = v;
     }
-    const bool ok = block_spd_inverse_reg<Q>(a, eij, H, cbuf, sbuf);
+    // equilibrated symmetric Gauss-Jordan, matrix in registers, column k through a double-buffered shared vector
+    bool ok = true;
+    const bool live = j < H;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) if (live && i0 + q * RP == j) sbuf[j] = 1.0 / sqrt(a[q]);
+    __syncthreads();
+    const double sj = live ? sbuf[j] : 1.0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { const int i = i0 + q * RP; if (live && i < H) a[q] *= sbuf[i] * sj; }
+    for (int k = 0; k < H; ++k) {
+        double* col = cbuf + (k & 1) * 128;
+        if (j == k) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { const int i = i0 + q * RP; if (i < H) col[i] = a[q]; }
+        }
+        __syncthreads();
+        const double dk = col[k];
+        if (!(dk > 0.0) || !(dk < 1e300)) ok = false;
+        const double id = 1.0 / dk;
+        const double cj = live ? col[j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int i = i0 + q * RP;
+            if (live && i < H) {
+                double v;
+                if (i == k) v = (j == k) ? -id : cj * id;
+                else if (j == k) v = col[i] * id;
+                else v = a[q] - (col[i] * cj) * id;
+                a[q] = v;
+            }
+        }
+    }
     if (!ok && threadIdx.x == 0) sc->chol_fail = 1;
     double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
     const double scale = (mode == 2) ? 1.0 : sc->sigma2;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const int e = threadIdx.x + q * NT;
-        if (e < H * H) out[e] = ok ? scale * a[q] : nan("");
+        const int i = i0 + q * RP;
+        if (live && i < H) out[i * H + j] = ok ? scale * (-a[q] * sbuf[i] * sj) : nan("");
     }
 }
 static int hxh_launch(cudaStream_t st, const Dev& d, int mode, int dv) {
     const int hh = d.H * d.H;
     // 1024 threads beat 256 (0.060 vs 0.099 ms at H = 64): the sweep is latency bound, more warps hide it
-    if (hh <= 1024) hxh_kernel<1, 1024><<<1, 1024, 0, st>>>(d, mode, dv);
-    else if (hh <= 4096) hxh_kernel<4, 1024><<<1, 1024, 0, st>>>(d, mode, dv);
-    else hxh_kernel<16, 1024><<<1, 1024, 0, st>>>(d, mode, dv);
+    if (hh <= 1024) hxh_kernel<32><<<1, 1024, 0, st>>>(d, mode, dv);
+    else if (hh <= 4096) hxh_kernel<64><<<1, 1024, 0, st>>>(d, mode, dv);
+    else hxh_kernel<128><<<1, 1024, 0, st>>>(d, mode, dv);
     VB_LAUNCH_OK();
     return 0;
 }
@@ -773,6 +875,7 @@ int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
 }
 
 // ------------------------------------------------------------------------------------------- B epilogue
+__global__ void trbq_kernel(Dev d, int nparts);
 // dense : BHat = ((Y*AHat)*SigmaB)/sigma2                       src/vbmf.jl:112
 // sparse: BHat = ((sigmaHat*Y)*AHat)*SigmaB                     src/vbmf_sparse.jl:266   (diag_var: diagm(sv)*Y*AHat*SigmaB, :261)
 // Fused with everything that needs the new rows while they sit in shared memory: Bold, D = BHat - Bold and the Grams
@@ -863,7 +966,7 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
 // DMMA version of the same epilogue for H <= 64 (HP8 = H rounded up to 8, shared pitch = 4 mod 16 as in the A epilogue):
 //   Bn = (c .* Qtile) * SigmaB [/ sigma2]        32 x HP8 x HP8 product, 4 x HP8/8 mma tiles over 8 warps
 //   G_B += Bn' Bn,  G_D += Dn' Dn                 accumulators in registers across the CTA's tiles
-template <int TPW>   // Gram tiles per warp: ceil((HP8/8)^2 / 8)
+template <int TPW, bool GRAM>   // Gram tiles per warp: ceil((HP8/8)^2 / 8); GRAM = false (H > 64): the Grams come from gram_dmma
 __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_var) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
@@ -871,8 +974,8 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
     const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
     double* Ss = sm;                 // [HP8][ld] SigmaB, zero padded
     double* T = Ss + HP8 * ld;       // [32][ld]  scaled Q tile
-    double* Bn = T + 32 * ld;        // [32][ld]
-    double* Dn = Bn + 32 * ld;       // [32][ld]
+    double* Bn = T + 32 * ld;        // [32][ld]   (GRAM only)
+    double* Dn = Bn + 32 * ld;       // [32][ld]   (GRAM only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
     const Scalars* sc = d.sc;
     const double* Q = d.packed + packed_q(d);
@@ -882,9 +985,9 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
     }
     const bool dense = d.kind == KIND_DENSE;
     const double s2 = sc->sigma2, sh = sc->sigmaHat;
-    double gB[TPW][2], gD[TPW][2];
+    double gB[GRAM ? TPW : 1][2], gD[GRAM ? TPW : 1][2];
 #pragma unroll
-    for (int q = 0; q < TPW; ++q) { gB[q][0] = gB[q][1] = 0.0; gD[q][0] = gD[q][1] = 0.0; }
+    for (int q = 0; q < (GRAM ? TPW : 1); ++q) { gB[q][0] = gB[q][1] = 0.0; gD[q][0] = gD[q][1] = 0.0; }
     double tr = 0.0;
     const int ntiles = (d.L + 31) / 32;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -922,37 +1025,43 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
                     tr = fma(v, Q[g], tr);
                     bn = v;
                 }
-                Bn[row * ld + col] = bn;
-                Dn[row * ld + col] = dn;
+                if (GRAM) { Bn[row * ld + col] = bn; Dn[row * ld + col] = dn; }
             }
         }
-        __syncthreads();
+        if (GRAM) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < TPW; ++q) {
+                const int idx = warp + 8 * q;
+                if (idx < nt8 * nt8) {
+                    const int at = idx / nt8, bt = idx - at * nt8;
+#pragma unroll
+                    for (int i0 = 0; i0 < 32; i0 += 4) {
+                        dmma_acc(gB[q], Bn[(i0 + j) * ld + 8 * at + r], Bn[(i0 + j) * ld + 8 * bt + r]);
+                        dmma_acc(gD[q], Dn[(i0 + j) * ld + 8 * at + r], Dn[(i0 + j) * ld + 8 * bt + r]);
+                    }
+                }
+            }
+        }
+    }
+    if (GRAM) {
+        double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
 #pragma unroll
         for (int q = 0; q < TPW; ++q) {
             const int idx = warp + 8 * q;
             if (idx < nt8 * nt8) {
                 const int at = idx / nt8, bt = idx - at * nt8;
-#pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += 4) {
-                    dmma_acc(gB[q], Bn[(i0 + j) * ld + 8 * at + r], Bn[(i0 + j) * ld + 8 * bt + r]);
-                    dmma_acc(gD[q], Dn[(i0 + j) * ld + 8 * at + r], Dn[(i0 + j) * ld + 8 * bt + r]);
-                }
+                const int a = 8 * at + r, b = 8 * bt + 2 * j;
+                if (a < H && b < H) { out[a * H + b] = gB[q][0]; out[H * H + a * H + b] = gD[q][0]; }
+                if (a < H && b + 1 < H) { out[a * H + b + 1] = gB[q][1]; out[H * H + a * H + b + 1] = gD[q][1]; }
             }
         }
+        tr = block_sum(tr, red);
+        if (threadIdx.x == 0) out[2 * H * H] = tr;
+    } else {
+        tr = block_sum(tr, red);
+        if (threadIdx.x == 0) d.part[blockIdx.x] = tr;         // Grams follow from gram_dmma on B and D
     }
-    double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
-#pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-        const int idx = warp + 8 * q;
-        if (idx < nt8 * nt8) {
-            const int at = idx / nt8, bt = idx - at * nt8;
-            const int a = 8 * at + r, b = 8 * bt + 2 * j;
-            if (a < H && b < H) { out[a * H + b] = gB[q][0]; out[H * H + a * H + b] = gD[q][0]; }
-            if (a < H && b + 1 < H) { out[a * H + b + 1] = gB[q][1]; out[H * H + a * H + b + 1] = gD[q][1]; }
-        }
-    }
-    tr = block_sum(tr, red);
-    if (threadIdx.x == 0) out[2 * H * H] = tr;
 }
 // fixed-order reduction of the per-CTA partials: BtB, DtD, sc->trBQ
 __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
@@ -986,16 +1095,30 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
         static bool done = false;
         if (!done) {
             const int mx = (int)((64 + 96) * pitch4(64) * 8);
-            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             done = true;
         }
         const int grid2 = std::max(1, std::min(cdiv(d.L, 32), 296));      // two CTAs per SM: the tile chain is latency bound
-        if (HP8 <= 32) B_epilogue_dmma_kernel<2><<<grid2, 256, smem, st>>>(d, dv);
-        else B_epilogue_dmma_kernel<8><<<grid2, 256, smem, st>>>(d, dv);
+        if (HP8 <= 32) B_epilogue_dmma_kernel<2, true><<<grid2, 256, smem, st>>>(d, dv);
+        else B_epilogue_dmma_kernel<8, true><<<grid2, 256, smem, st>>>(d, dv);
         VB_LAUNCH_OK();
         B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2);
         VB_LAUNCH_OK();
+        return 0;
+    }
+    if (getenv("VBMF_B200_BEPI_SIMT") == nullptr) {
+        // H > 64: product-only DMMA epilogue (the Gram accumulators would not fit in registers), Grams by gram_dmma
+        const int HP8 = (H + 7) & ~7;
+        const size_t smem = (size_t)((HP8 + 32) * pitch4(HP8)) * sizeof(double);
+        static bool done2 = false;
+        if (!done2) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * pitch4(128) * 8))); done2 = true; }
+        const int grid3 = std::max(1, std::min(cdiv(d.L, 32), 148));
+        B_epilogue_dmma_kernel<1, false><<<grid3, 256, smem, st>>>(d, dv);
+        VB_LAUNCH_OK();
+        trbq_kernel<<<1, 256, 0, st>>>(d, grid3);
+        VB_LAUNCH_OK();
+        if (gram_dmma(st, d, d.B, false, d.L, d.BtB) || gram_dmma(st, d, d.D, false, d.L, d.DtD)) return -1;
         return 0;
     }
 #define BEPI(RR, TDD, TRR)                                                                                                   \
