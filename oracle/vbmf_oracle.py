@@ -13,6 +13,9 @@ PARITY UNPINNED (no reference fixture or test exercises them; this restatement i
   full_cov=false (diagonal) path, diag_var=true, labels/H1 masking, all of vbmf_dual (incl. the
   Roots.jl `fzero` root, a third-party dependency that is neither vendored nor listed in REQUIRE),
   lowerBound / lowerBoundTrimmed, early convergence exit.
+  These branches are cross-checked (tests/test_oracle_mp.py) against a second, independent restatement of the literal
+  reference formulae in 40-digit arithmetic (oracle/mp_restatement.py): agreement <= 1e-12 per update step.  That guards
+  against a transcription slip in this file; it does not replace a run of the reference itself.
 
 Every function cites the reference file:line (relative to /root/reference) it follows.  Julia 0.5.2
 semantics (the fixtures record JULIA 0.5.2) are honoured: column-major vec/reshape, `inv` = LU with partial

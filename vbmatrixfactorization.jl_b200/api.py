@@ -27,7 +27,7 @@ __all__ = [
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
-    "vbls_", "vbls_batched_", "preprocess", "create_log", "update_log_", "save_log", "load_log", "extract_params_", "VBMFError",
+    "vbls_", "vbls_batched_", "BatchedVbls", "preprocess", "create_log", "update_log_", "save_log", "load_log", "extract_params_", "VBMFError",
 ]
 
 VBMFError = L_.VBMFError
@@ -755,25 +755,45 @@ def vbls_(Y, params, niter, diag_var=False, full_cov=False, ctx=None):
     return params.AHat
 
 
+class BatchedVbls:
+    """Marshalled batch for `vbmf_b200_batched_vbls`: the per-problem state structs and pointer tables are built once here
+    (pure Python/ctypes work, ~70 us per problem), `run` is then the bare C-ABI call on the host arrays the structs point
+    at, and `readback` copies the scalar results back into the Python parameter objects.  A Julia caller pays none of the
+    Python cost; `bench.py --workload c2` times `run` and reports the marshalling separately."""
+
+    def __init__(self, Ys, params_list, ctx=None, yhat=True, keep_blocks=False):
+        self.ctx = ctx or default_context()
+        self.params = list(params_list)
+        self.n = len(self.params)
+        if self.n == 0:
+            return
+        self.kind = self.params[0].kind
+        if self.kind == L_.DENSE or any(p.kind != self.kind for p in self.params):
+            raise VBMFError("vbls_batched_ needs a homogeneous list of vbmf_sparse or vbmf_dual parameters")
+        self.Ys = [_f(Y) for Y in Ys]
+        self.structs = [_struct(p, yhat, keep_blocks) for p in self.params]
+        self.yp = (L_.p_f64 * self.n)(*[_ptr(Y) for Y in self.Ys])
+        self.sp = (C.c_void_p * self.n)(*[C.addressof(st) for st in self.structs])
+
+    def run(self, niter, full_cov=False):
+        if self.n == 0:
+            return 0
+        return L_.check(self.ctx.lib.vbmf_b200_batched_vbls(self.ctx.h, self.kind, self.n, self.yp, self.sp, int(niter),
+                                                           L_.FULL_COV if full_cov else 0), allow=(-2,))
+
+    def readback(self):
+        for p, st in zip(self.params, self.structs):
+            _readback(p, st)
+        return [p.AHat for p in self.params]
+
+
 def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, keep_blocks=False):
     """`vbls!` (examples/mil_util.jl:179-203) for many small problems in ONE kernel launch (one CTA per problem): the MIL
     classification pattern, classify(...; class_alg = "dual") runs it for every test bag and class model.  All params must
     be vbmf_sparse_parameters or all vbmf_dual_parameters with the same L, H (and H0); M may differ per problem."""
-    ctx = ctx or default_context()
-    n = len(params_list)
-    if n == 0:
-        return []
-    kind = params_list[0].kind
-    if kind == L_.DENSE or any(p.kind != kind for p in params_list):
-        raise VBMFError("vbls_batched_ needs a homogeneous list of vbmf_sparse or vbmf_dual parameters")
-    Ys = [_f(Y) for Y in Ys]
-    structs = [_struct(p, yhat, keep_blocks) for p in params_list]
-    yp = (L_.p_f64 * n)(*[_ptr(Y) for Y in Ys])
-    sp = (C.c_void_p * n)(*[C.cast(C.pointer(st), C.c_void_p) for st in structs])
-    L_.check(ctx.lib.vbmf_b200_batched_vbls(ctx.h, kind, n, yp, sp, int(niter), L_.FULL_COV if full_cov else 0), allow=(-2,))
-    for p, st in zip(params_list, structs):
-        _readback(p, st)
-    return [p.AHat for p in params_list]
+    batch = BatchedVbls(Ys, params_list, ctx=ctx, yhat=yhat, keep_blocks=keep_blocks)
+    batch.run(niter, full_cov=full_cov)
+    return batch.readback()
 
 
 def preprocess(Y, lam, verb=False, ctx=None):

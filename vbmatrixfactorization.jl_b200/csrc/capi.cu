@@ -91,6 +91,10 @@ struct vbmf_b200_ctx {
     // profiling of the two contractions
     bool profile = false;
     std::vector<cudaEvent_t> ev_k1, ev_k2;
+    // grow-only staging for the batched small-problem path (device arena + pinned host mirror, same offsets)
+    char* batch_dev = nullptr;
+    char* batch_host = nullptr;
+    size_t batch_bytes = 0;
 };
 
 static int ctx_allreduce(vbmf_b200_ctx* c, double* buf, size_t n) {
@@ -170,6 +174,8 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
     cudaStreamSynchronize(c->st);
     ctx_free_Y(c);
     if (c->d_tr) cudaFree(c->d_tr);
+    if (c->batch_dev) cudaFree(c->batch_dev);
+    if (c->batch_host) cudaFreeHost(c->batch_host);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
     if (c->comm) g_nccl.CommDestroy(c->comm);
@@ -1201,8 +1207,38 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         want_blocks = want_blocks || s->SigmaATVec_blocks != nullptr;
     }
     const size_t Mtot = (size_t)moff[nprob], MH = Mtot * H, HH = (size_t)H * H, LH = (size_t)L * H;
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    // ---- one arena, laid out [inputs | in-out | outputs]; the pinned host mirror uses the same offsets so the whole
+    //      upload is one copy of [0, up_end) and the whole download one copy of [down_begin, total)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_moff = take((size_t)(nprob + 1) * 4), o_Y = take(L * Mtot * 8), o_B = take(nprob * LH * 8), o_SB = take(nprob * HH * 8);
+    const size_t down_begin = off;
+    const size_t o_CA = take(MH * 8), o_sc = take((size_t)nprob * 16 * 8);
+    const size_t up_end = off;
+    const size_t o_A = take(MH * 8), o_beta = take(MH * 8), o_s = take(MH * 8), o_SA = take(nprob * HH * 8);
+    const size_t o_YH = want_yhat ? take(L * Mtot * 8) : 0, o_blk = want_blocks ? take(MH * H * 8) : 0;
+    const size_t total = off;
+    if (total > c->batch_bytes) {
+        VB_CUDA_OK(cudaStreamSynchronize(c->st));
+        if (c->batch_dev) cudaFree(c->batch_dev);
+        if (c->batch_host) cudaFreeHost(c->batch_host);
+        c->batch_dev = c->batch_host = nullptr; c->batch_bytes = 0;
+        const size_t cap = total + total / 4;
+        if (cudaMalloc(&c->batch_dev, cap) != cudaSuccess || cudaHostAlloc(&c->batch_host, cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            if (c->batch_dev) { cudaFree(c->batch_dev); c->batch_dev = nullptr; }
+            set_error("batched vbls: allocating %zu staging bytes failed", cap);
+            return -1;
+        }
+        c->batch_bytes = cap;
+    }
+    char* hb = c->batch_host;
+    char* db = c->batch_dev;
     // ---- pack
-    std::vector<double> hY(L * Mtot), hB(nprob * LH), hSB(nprob * HH), hCA(MH), hsc((size_t)nprob * 16, 0.0);
+    memcpy(hb + o_moff, moff.data(), (size_t)(nprob + 1) * 4);
+    double *hY = (double*)(hb + o_Y), *hB = (double*)(hb + o_B), *hSB = (double*)(hb + o_SB), *hCA = (double*)(hb + o_CA), *hsc = (double*)(hb + o_sc);
+    memset(hsc, 0, (size_t)nprob * 16 * 8);
     for (int64_t p = 0; p < nprob; ++p) {
         const ST* s = (const ST*)states[p];
         memcpy(&hY[(size_t)moff[p] * L], Y[p], (size_t)s->M * L * 8);
@@ -1214,48 +1250,27 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) { sc[7] = s->alpha00; sc[8] = s->beta00; sc[9] = s->alpha01; sc[10] = s->beta01; }
         else { sc[5] = s->alpha; sc[6] = s->beta0; }
     }
-    VB_CUDA_OK(cudaSetDevice(c->device));
-    // ---- device arena
-    struct Item { void** p; size_t bytes; };
-    int* d_moff = nullptr;
-    double *dY = nullptr, *dB = nullptr, *dSB = nullptr, *dA = nullptr, *dCA = nullptr, *dbeta = nullptr, *ds = nullptr, *dSA = nullptr,
-           *dblk = nullptr, *dYH = nullptr, *dsc = nullptr;
-    std::vector<Item> items = {{(void**)&d_moff, (size_t)(nprob + 1) * 4}, {(void**)&dY, L * Mtot * 8}, {(void**)&dB, nprob * LH * 8},
-                               {(void**)&dSB, nprob * HH * 8}, {(void**)&dA, MH * 8}, {(void**)&dCA, MH * 8}, {(void**)&dbeta, MH * 8},
-                               {(void**)&ds, MH * 8}, {(void**)&dSA, nprob * HH * 8}, {(void**)&dsc, (size_t)nprob * 16 * 8}};
-    if (want_blocks) items.push_back({(void**)&dblk, MH * H * 8});
-    if (want_yhat) items.push_back({(void**)&dYH, L * Mtot * 8});
-    size_t total = 0;
-    for (auto& it : items) total += align_up(it.bytes, 256);
-    char* arena = nullptr;
-    if (cudaMalloc(&arena, total) != cudaSuccess) { cudaGetLastError(); set_error("batched vbls: cudaMalloc of %zu bytes failed", total); return -1; }
-    char* q = arena;
-    for (auto& it : items) { *it.p = q; q += align_up(it.bytes, 256); }
     int rc = 0;
     cudaStream_t st = c->st;
-    auto H2D = [&](void* d, const void* h, size_t n) { if (!rc && cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("batched vbls: upload failed"); rc = -1; } };
-    H2D(d_moff, moff.data(), (size_t)(nprob + 1) * 4); H2D(dY, hY.data(), hY.size() * 8); H2D(dB, hB.data(), hB.size() * 8);
-    H2D(dSB, hSB.data(), hSB.size() * 8); H2D(dCA, hCA.data(), hCA.size() * 8); H2D(dsc, hsc.data(), hsc.size() * 8);
+    if (cudaMemcpyAsync(db, hb, up_end, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); set_error("batched vbls: upload failed"); return -1; }
     BatchDesc bd;
     bd.nprob = (int)nprob; bd.L = (int)L; bd.H = (int)H; bd.H0 = (int)H0; bd.kind = kind; bd.niter = (int)std::max<int64_t>(niter, 0);
     bd.full_cov = (flags & F_FULL_COV) ? 1 : 0; bd.Mmax = Mmax;
-    bd.moff = d_moff; bd.Y = dY; bd.B = dB; bd.SigmaB = dSB; bd.A = dA; bd.CA = dCA; bd.beta = dbeta; bd.sdiag = ds; bd.SigmaA = dSA;
-    bd.blocks = dblk; bd.YHat = dYH; bd.scal = dsc;
+    bd.moff = (const int*)(db + o_moff); bd.Y = (const double*)(db + o_Y); bd.B = (const double*)(db + o_B); bd.SigmaB = (const double*)(db + o_SB);
+    bd.A = (double*)(db + o_A); bd.CA = (double*)(db + o_CA); bd.beta = (double*)(db + o_beta); bd.sdiag = (double*)(db + o_s);
+    bd.SigmaA = (double*)(db + o_SA); bd.blocks = want_blocks ? (double*)(db + o_blk) : nullptr; bd.YHat = want_yhat ? (double*)(db + o_YH) : nullptr;
+    bd.scal = (double*)(db + o_sc);
     prof_mark(c, c->ev_k1);       // profiling: the kernel alone (read back through vbmf_b200_ctx_profile_read, K1 slot)
-    if (!rc && bd.niter > 0) rc = k_batched_vbls(st, bd);
+    if (bd.niter > 0) rc = k_batched_vbls(st, bd);
     prof_mark(c, c->ev_k1);
     // ---- download + unpack
-    std::vector<double> hA(MH), hbeta(MH), hs(MH), hSA(nprob * HH), hYH, hblk;
-    auto D2H = [&](void* h, const void* d, size_t n) { if (!rc && cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("batched vbls: download failed"); rc = -1; } };
-    if (bd.niter > 0) {
-        D2H(hA.data(), dA, MH * 8); D2H(hCA.data(), dCA, MH * 8); D2H(hbeta.data(), dbeta, MH * 8); D2H(hs.data(), ds, MH * 8);
-        D2H(hSA.data(), dSA, nprob * HH * 8); D2H(hsc.data(), dsc, hsc.size() * 8);
-        if (want_yhat) { hYH.resize(L * Mtot); D2H(hYH.data(), dYH, hYH.size() * 8); }
-        if (want_blocks) { hblk.resize(MH * H); D2H(hblk.data(), dblk, hblk.size() * 8); }
+    if (!rc && bd.niter > 0 && cudaMemcpyAsync(hb + down_begin, db + down_begin, total - down_begin, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        cudaGetLastError(); set_error("batched vbls: download failed"); rc = -1;
     }
-    if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_error("batched vbls: %s", cudaGetErrorString(e)); rc = -1; } }
-    cudaFree(arena);
+    { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess && !rc) { set_error("batched vbls: %s", cudaGetErrorString(e)); rc = -1; } }
     if (rc || bd.niter == 0) return rc;
+    const double *hA = (const double*)(hb + o_A), *hbeta = (const double*)(hb + o_beta), *hs = (const double*)(hb + o_s), *hSA = (const double*)(hb + o_SA),
+                 *hYH = (const double*)(hb + o_YH), *hblk = (const double*)(hb + o_blk);
     bool failed = false;
     for (int64_t p = 0; p < nprob; ++p) {
         ST* s = (ST*)states[p];
