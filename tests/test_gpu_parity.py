@@ -279,7 +279,7 @@ def test_no_y_attached_errors(G):
 
 # ------------------------------------------------------------------------------------------------ batched small problems (MIL pattern)
 @pytest.mark.parametrize("kind,full_cov,H", [("dual", True, 20), ("dual", False, 20), ("sparse", True, 20), ("sparse", False, 7),
-                                             ("sparse", True, 32), ("dual", True, 4)])
+                                             ("sparse", True, 32), ("dual", True, 4), ("sparse", True, 7), ("dual", True, 13)])
 def test_vbls_batched(G, ctx, kind, full_cov, H):
     """examples/mil_util.jl:504-511: vbls! on every bag x class model; one CTA per problem must equal the oracle's vbls."""
     rng = np.random.default_rng(17)
@@ -481,3 +481,58 @@ def test_bit_reproducible_runs(G, ctx):
         outs.append(q)
     for f in ("AHat", "BHat", "CA", "SigmaA", "SigmaB", "sigmaHat", "zeta"):
         assert np.array_equal(np.asarray(getattr(outs[0], f)), np.asarray(getattr(outs[1], f))), f
+
+
+def test_batched_staging_reuse_and_growth(G, ctx):
+    """The batched path keeps a grow-only device arena + pinned mirror in the context: a small batch, a larger one (regrowth)
+    and the small one again must all give the oracle's answer (no stale bytes from the earlier layout)."""
+    rng = np.random.default_rng(3)
+    L, H, niter = 12, 5, 6
+
+    def make(n, seed):
+        Ys, ps = [], []
+        for b in range(n):
+            Y = synth(L, int(rng.integers(2, 30)), 2, seed=seed + b)
+            p = vo.vbmf_sparse_init(Y, H, rng=rng)
+            p.SigmaB = np.diag(rng.uniform(1e-3, 1e-2, H))
+            Ys.append(np.asfortranarray(Y)); ps.append(p)
+        return Ys, ps
+    for n, seed in ((3, 10), (60, 200), (3, 10), (7, 900)):
+        Ys, ps = make(n, seed)
+        qs = [G.to_gpu_params(p) for p in ps]
+        batch = G.vb.BatchedVbls(Ys, qs, ctx=ctx, yhat=True, keep_blocks=True)
+        batch.run(niter, full_cov=True)
+        batch.readback()
+        for Y, p, q in zip(Ys, ps, qs):
+            vo.vbls(Y, p, niter, full_cov=True)
+            G.compare(q, p, TOL, ["AHat", "diagSigmaATVec", "SigmaA", "CA", "beta", "sigmaHat"])
+            assert G.rel(q.SigmaATVec_blocks, p.SigmaATVec_blocks) < TOL
+
+
+def test_no_device_memory_leak(G):
+    """Contexts, solvers, graphs, side streams and staging buffers are all released: 40 create/run/destroy cycles of every
+    solver kind leave the device's free memory where it was."""
+    import torch
+    Y = synth(200, 3000, 4, seed=5)
+    Yf = np.asfortranarray(Y)
+
+    def cycle():
+        c = G.vb.Context(device=0)
+        p = vo.vbmf_init(Y, 8, rng=np.random.default_rng(0))
+        G.vb.vbmf_(Yf, G.to_gpu_params(p), 3, eps=0.0, est_covs=True, est_var=True, ctx=c, yhat=False)
+        s = vo.vbmf_sparse_init(Y, 8, rng=np.random.default_rng(0))
+        G.vb.vbmf_sparse_(Yf, G.to_gpu_params(s), 3, eps=0.0, full_cov=True, ctx=c, yhat=False)
+        d = vo.vbmf_dual_init(Y, 8, 4, rng=np.random.default_rng(0))
+        G.vb.vbmf_dual_(Yf, G.to_gpu_params(d), 3, eps=0.0, ctx=c, yhat=False)
+        G.vb.vbls_batched_([Yf[:, :20]], [G.to_gpu_params(vo.vbmf_sparse_init(Y[:, :20], 8, rng=np.random.default_rng(0)))], 2,
+                           full_cov=True, ctx=c)
+        c.close()
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(40):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 8 << 20, "device memory shrank by %.1f MB over 40 cycles" % ((free0 - free1) / 2**20)

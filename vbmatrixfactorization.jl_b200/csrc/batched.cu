@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) batched_vbls_kernel(BatchDesc bd) {
     double* AtA = SA + H * H;                // [H][H]
     double* wacc = AtA + H * H;              // [nw][H*H] per-warp sums of Sigma_m
     double* colb = wacc + nw * H * H;        // [nw][64]
+    colb += (colb - sm) & 1;                 // 16-byte aligned: the register inverse reads it as double2 (odd H would misalign it)
     double* pvb = colb + nw * 64;            // [nw][32]
     double* scal = bd.scal + (size_t)p * 16;
     const double* Y = bd.Y + (size_t)m0 * L;
