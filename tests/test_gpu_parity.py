@@ -536,3 +536,39 @@ def test_no_device_memory_leak(G):
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info(0)[0]
     assert free0 - free1 < 8 << 20, "device memory shrank by %.1f MB over 40 cycles" % ((free0 - free1) / 2**20)
+
+
+def _fuzz_shapes():
+    rng = np.random.default_rng(20261018)
+    Hs = [1, 3, 5, 7, 9, 11, 13, 17, 23, 31, 33, 37, 47, 63, 65, 67, 97, 127]
+    out = []
+    for H in Hs:
+        L = int(rng.integers(1, 160)) * 2 + 1                # odd
+        M = int(rng.integers(H + 1, 900))
+        out.append((L, M, H))
+    return out
+
+
+@pytest.mark.parametrize("L,M,H", _fuzz_shapes())
+def test_odd_shape_fuzz(G, ctx, L, M, H):
+    """Odd / prime L, M, H through every kernel family (padding, alignment and tail handling): two teacher-forced iterations
+    of dense, sparse (diagonal and full covariance, heteroscedastic) and dual against the oracle."""
+    Y = synth(L, M, max(1, min(H, L) // 2), seed=L + 7 * M + H)
+    Yf = np.asfortranarray(Y)
+    p = vo.vbmf_init(Y, H, rng=np.random.default_rng(H))
+    q = G.to_gpu_params(p)
+    vo.vbmf_run(Y, p, 2, eps=0.0, est_covs=True, est_var=True)
+    G.vb.vbmf_(Yf, q, 2, eps=0.0, est_covs=True, est_var=True, ctx=ctx, yhat=False)
+    G.compare(q, p, 1e-9, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "sigma2"])
+    for full_cov, diag_var in ((False, False), (True, False), (True, True), (False, True)):
+        ps = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(H + 1))
+        qs = G.to_gpu_params(ps)
+        vo.vbmf_sparse_run(Y, ps, 2, eps=0.0, full_cov=full_cov, diag_var=diag_var)
+        G.vb.vbmf_sparse_(Yf, qs, 2, eps=0.0, full_cov=full_cov, diag_var=diag_var, ctx=ctx, yhat=False)
+        G.compare(qs, ps, 1e-9, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "beta", "CB", "diagSigmaATVec", "sigmaHat", "sigmaVecHat"])
+    H0 = H // 2
+    pd = vo.vbmf_dual_init(Y, H, H0, rng=np.random.default_rng(H + 2))
+    qd = G.to_gpu_params(pd)
+    vo.vbmf_dual_run(Y, pd, 2, eps=0.0, full_cov=(H % 4 == 1))
+    G.vb.vbmf_dual_(Yf, qd, 2, eps=0.0, full_cov=(H % 4 == 1), ctx=ctx, yhat=False)
+    G.compare(qd, pd, 1e-9, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CA0", "CA1", "beta", "CB", "sigmaHat", "alpha00", "alpha01", "beta00", "beta01"])
