@@ -30,7 +30,7 @@ struct BatchDesc {
 };
 
 template <int HP>
-__global__ void __launch_bounds__(128) batched_vbls_kernel(BatchDesc bd) {
+__global__ void __launch_bounds__(128, 3) batched_vbls_kernel(BatchDesc bd) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     __shared__ double s_sig, s_fail;

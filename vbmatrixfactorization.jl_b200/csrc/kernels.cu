@@ -722,36 +722,40 @@ __global__ void __launch_bounds__(256) sparse_A_full_kernel(Dev d, int diag_var,
     }
 }
 // H <= 32: one warp per matrix, the matrix lives in registers (lane l owns column l), see warp_spd_inverse_reg.
+// G and the warps' running sums of Sigma_m live in shared memory so the kernel fits 128 registers and two CTAs (16 warps)
+// share an SM: the sweeps are latency bound and need the extra warps.
 template <int HP>
-__global__ void __launch_bounds__(256) sparse_A_full_warp_kernel(Dev d, int diag_var, int nwarps_total) {
+__global__ void __launch_bounds__(256, 2) sparse_A_full_warp_kernel(Dev d, int diag_var, int nwarps_total) {
     ACTIVE_OR_RETURN(d);
-    __shared__ __align__(16) double s_col[8][64];
-    __shared__ __align__(16) double s_p[8][32];
+    extern __shared__ __align__(16) double wsm[];
+    double* s_G = wsm;                       // [HP][32]  G[q][lane], zero padded
+    double* s_col = s_G + HP * 32;           // [8][64]
+    double* s_p = s_col + 8 * 64;            // [8][32]
+    double* s_accw = s_p + 8 * 32;           // [8][HP][32]
     const int H = d.H;
     const Scalars* sc = d.sc;
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int gw = blockIdx.x * (blockDim.x >> 5) + wic;
-    double* col = s_col[wic];
-    double* pv = s_p[wic];
+    double* col = s_col + wic * 64;
+    double* pv = s_p + wic * 32;
+    double* acc = s_accw + wic * HP * 32;
     const double sh = sc->sigmaHat;
     const bool live = lane < H;
-    constexpr bool KEEP_G = HP <= 16;          // column `lane` of G in registers when they are not needed elsewhere
-    const double* __restrict__ Gm = d.Gm;
-    double g[KEEP_G ? HP : 1], acc[HP];
-#pragma unroll
-    for (int q = 0; q < HP; ++q) {
-        if (KEEP_G) g[q] = (q < H && live) ? Gm[q * H + lane] : 0.0;
-        acc[q] = 0.0;
+    for (int e = threadIdx.x; e < HP * 32; e += blockDim.x) {
+        const int q = e >> 5, l = e & 31;
+        s_G[e] = (q < H && l < H) ? d.Gm[q * H + l] : 0.0;
     }
-    const double gll = live ? d.Gm[lane * H + lane] : 0.0;
+#pragma unroll
+    for (int q = 0; q < HP; ++q) acc[q * 32 + lane] = 0.0;
+    __syncthreads();
+    const double gll = s_G[min(lane, HP - 1) * 32 + lane];
     bool all_ok = true;
     for (int m = gw; m < d.Mloc; m += nwarps_total) {
         const double ca = live ? d.CAv[(size_t)m * H + lane] : 1.0;     // padded lanes: identity
         const double p = live ? d.P[(size_t)m * H + lane] : 0.0;
         double a[HP];
 #pragma unroll
-        for (int q = 0; q < HP; ++q)
-            a[q] = (KEEP_G ? g[q] : ((q < H && live) ? Gm[q * H + lane] : 0.0)) + ((q == lane) ? ca : 0.0);
+        for (int q = 0; q < HP; ++q) a[q] = s_G[q * 32 + lane] + ((q == lane) ? ca : 0.0);
         pv[lane] = p;
         const bool ok = warp_spd_inverse_reg<HP>(a, gll + ca, lane, col);      // ends with __syncwarp (pv visible)
         all_ok = all_ok && ok;
@@ -771,21 +775,19 @@ __global__ void __launch_bounds__(256) sparse_A_full_warp_kernel(Dev d, int diag
             }
         }
 #pragma unroll
-        for (int q = 0; q < HP; ++q) acc[q] += a[q];
+        for (int q = 0; q < HP; ++q) acc[q * 32 + lane] += a[q];
         __syncwarp();
     }
     if (!all_ok && lane == 0) d.sc->chol_fail = 1;
+    __syncthreads();
     // per-CTA sum of the warps' accumulators in fixed warp order (one partial per CTA instead of one per warp)
-    __shared__ double s_acc[32 * 32];
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-        if (wic == w && live) {
-#pragma unroll
-            for (int q = 0; q < HP; ++q) if (q < H) s_acc[q * H + lane] = (w == 0 ? 0.0 : s_acc[q * H + lane]) + acc[q];
-        }
-        __syncthreads();
-    }
     double* out = d.part + (size_t)blockIdx.x * H * H;
-    for (int e = threadIdx.x; e < H * H; e += blockDim.x) out[e] = s_acc[e];
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        const int q = e / H, l = e - q * H;
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_accw[(w * HP + q) * 32 + l];
+        out[e] = t;
+    }
 }
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H;
@@ -797,10 +799,15 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
         const int wpc = 8;
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
         ngroups = grid;                                   // one partial per CTA
-        if (H <= 8) sparse_A_full_warp_kernel<8><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
-        else if (H <= 16) sparse_A_full_warp_kernel<16><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
-        else if (H <= 24) sparse_A_full_warp_kernel<24><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
-        else sparse_A_full_warp_kernel<32><<<grid, 256, 0, st>>>(d, dv, grid * wpc);
+#define WK(HPV)                                                                                                          \
+    {                                                                                                                    \
+        const size_t smem = (size_t)(HPV * 32 + 8 * 64 + 8 * 32 + 8 * HPV * 32) * sizeof(double);                        \
+        static bool done = false;                                                                                        \
+        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_warp_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; } \
+        sparse_A_full_warp_kernel<HPV><<<grid, 256, smem, st>>>(d, dv, grid * wpc);                                      \
+    }
+        if (H <= 8) WK(8) else if (H <= 16) WK(16) else if (H <= 24) WK(24) else WK(32)
+#undef WK
     } else {
         const size_t smem = (size_t)(H * (H + 1) + 3 * H) * sizeof(double);
         static bool done = false;

@@ -84,12 +84,16 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
         a[q] *= sq.x * sl;
         a[q + 1] *= sq.y * sl;
     }
+    // Software-pipelined sweeps: row k+1 is final as soon as its one FMA of sweep k is done, so it is updated FIRST and
+    // published for the next sweep while the other HP-1 FMAs of sweep k still issue; the shared-memory round trip and
+    // the reciprocal of the next pivot then overlap with them instead of heading every sweep's dependency chain.
+    col[32 + lane] = a[0];
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < HP; ++k) {
-        double* c = col + ((k + 1) & 1) * 32;
+        const double* c = col + ((k + 1) & 1) * 32;            // row k == column k (symmetry), published by sweep k-1
+        double* cn = col + (k & 1) * 32;                       // row k+1 goes here
         const double myk = a[k];                               // A[k][l]
-        c[lane] = myk;
-        __syncwarp();
         const double d = c[k];
         if (!(d > 0.0) || !(d < 1e300)) ok = false;
         const double id = 1.0 / d;
@@ -98,13 +102,18 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
         // one FMA per element for every lane: the pivot lane's own column IS column k (a[q] == ck), so
         // ck*(id - 1) + a[q] = ck*id there; elsewhere a[q] - ck*t
         const double beta = piv ? id - 1.0 : -t;
+        if (k + 1 < HP) {
+            a[k + 1] = fma(c[k + 1], beta, a[k + 1]);
+            cn[lane] = a[k + 1];
+        }
 #pragma unroll
         for (int q = 0; q < HP; q += 2) {
             const double2 ck = *reinterpret_cast<const double2*>(c + q);
-            a[q] = fma(ck.x, beta, a[q]);
-            a[q + 1] = fma(ck.y, beta, a[q + 1]);
+            if (q != k + 1) a[q] = fma(ck.x, beta, a[q]);
+            if (q + 1 != k + 1) a[q + 1] = fma(ck.y, beta, a[q + 1]);
         }
         a[k] = piv ? -id : t;
+        __syncwarp();
     }
     __syncwarp();
     col[lane] = sl;
