@@ -80,6 +80,8 @@ struct vbmf_b200_ctx {
     void* comm = nullptr;
     // resident shard of Y (column-major L x Mloc, leading dimension ldY)
     double* Y = nullptr;
+    size_t Y_cap = 0;         // bytes allocated behind Y (the buffer is reused by the next attach when it fits)
+    int L_cap = 0;            // rows rowY2 / stats_part were sized for
     int L = 0, Mloc = 0, Mglob = 0, moff = 0, ldY = 0;
     double* rowY2 = nullptr;
     double* d_tr = nullptr;
@@ -166,6 +168,7 @@ static void ctx_free_Y(vbmf_b200_ctx* c) {
     if (c->rowY2) cudaFree(c->rowY2);
     if (c->stats_part) cudaFree(c->stats_part);
     c->Y = nullptr; c->rowY2 = nullptr; c->stats_part = nullptr; c->have_Y = false;
+    c->Y_cap = 0; c->L_cap = 0;
 }
 
 extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
@@ -195,13 +198,23 @@ static int ctx_alloc_Y(vbmf_b200_ctx* c, int64_t L, int64_t Mloc, int64_t Mglob,
     if (L > 0x7fffff00LL || Mglob > 0x7fffff00LL) { set_error("L and M must fit in 31 bits"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     VB_CUDA_OK(cudaStreamSynchronize(c->st));
-    ctx_free_Y(c);
+    const int ld = (int)((L + 1) & ~1LL);                 // TMA needs a 16-byte pitch
+    const size_t bytes = std::max<size_t>((size_t)ld * (size_t)std::max<int64_t>(Mloc, 1) * 8, 16);
+    // Re-attaching a matrix of the same (or a somewhat smaller) size keeps the allocation: cudaFree + cudaMalloc of tens of
+    // GB costs a few hundred ms, as much as the PCIe copy itself.  A much smaller matrix releases the big buffer.
+    const bool reuse = c->Y != nullptr && c->rowY2 != nullptr && c->stats_part != nullptr && bytes <= c->Y_cap &&
+                       c->Y_cap <= 2 * bytes + (64u << 20) && L <= c->L_cap;
+    if (!reuse) {
+        ctx_free_Y(c);
+        VB_CUDA_OK(cudaMalloc(&c->Y, bytes));
+        c->Y_cap = bytes;
+        VB_CUDA_OK(cudaMalloc(&c->rowY2, (size_t)L * 8));
+        VB_CUDA_OK(cudaMalloc(&c->stats_part, (size_t)(MAX_PARTS / 2) * L * 8));
+        c->L_cap = (int)L;
+    }
+    c->have_Y = false;
     c->L = (int)L; c->Mloc = (int)Mloc; c->Mglob = (int)Mglob; c->moff = (int)off;
-    c->ldY = (int)((L + 1) & ~1LL);                       // TMA needs a 16-byte pitch
-    const size_t bytes = std::max<size_t>((size_t)c->ldY * (size_t)std::max<int64_t>(Mloc, 1) * 8, 16);
-    VB_CUDA_OK(cudaMalloc(&c->Y, bytes));
-    VB_CUDA_OK(cudaMalloc(&c->rowY2, (size_t)L * 8));
-    VB_CUDA_OK(cudaMalloc(&c->stats_part, (size_t)(MAX_PARTS / 2) * L * 8));
+    c->ldY = ld;
     if (c->ldY != L) VB_CUDA_OK(cudaMemsetAsync(c->Y, 0, bytes, c->st));
     return 0;
 }
@@ -309,10 +322,8 @@ extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* 
         if (k_compact_rows(st, c->Y, c->ldY, Yn, ldn, drows, Lnew, M, lambda)) return -1;
         VB_CUDA_OK(cudaStreamSynchronize(st));
         cudaFree(drows);
-        cudaFree(c->Y); cudaFree(c->rowY2); cudaFree(c->stats_part);
-        c->Y = Yn; c->L = Lnew; c->ldY = ldn;
-        VB_CUDA_OK(cudaMalloc(&c->rowY2, (size_t)Lnew * 8));
-        VB_CUDA_OK(cudaMalloc(&c->stats_part, (size_t)(MAX_PARTS / 2) * Lnew * 8));
+        cudaFree(c->Y);                       // rowY2 / stats_part were sized for the larger L and are kept
+        c->Y = Yn; c->Y_cap = bytes; c->L = Lnew; c->ldY = ldn;
     }
     if (L_out) *L_out = Lnew;
     if (used_rows) for (int k = 0; k < Lnew; ++k) used_rows[k] = rows[k] + 1;
