@@ -901,6 +901,10 @@ def vbls(Y, p, niter, diag_var=False, full_cov=False):
             sparse_updateA(Y, p, full_cov=full_cov, diag_var=diag_var)
             sparse_updateCA(p)
             sparse_updateSigma(Y, p, diag_var=diag_var)
+        elif p.kind == "trial":
+            trial_updateA(Y, p, full_cov=full_cov, diag_var=diag_var)
+            trial_updateCA(p)
+            sparse_updateSigma(Y, p, diag_var=diag_var)
         else:
             dual_updateA(Y, p, full_cov=full_cov, diag_var=diag_var)
             dual_updateCA(p)

@@ -279,7 +279,8 @@ def test_no_y_attached_errors(G):
 
 # ------------------------------------------------------------------------------------------------ batched small problems (MIL pattern)
 @pytest.mark.parametrize("kind,full_cov,H", [("dual", True, 20), ("dual", False, 20), ("sparse", True, 20), ("sparse", False, 7),
-                                             ("sparse", True, 32), ("dual", True, 4), ("sparse", True, 7), ("dual", True, 13)])
+                                             ("sparse", True, 32), ("dual", True, 4), ("sparse", True, 7), ("dual", True, 13),
+                                             ("trial", True, 12), ("trial", False, 9), ("dense", False, 20), ("dense", False, 5)])
 def test_vbls_batched(G, ctx, kind, full_cov, H):
     """examples/mil_util.jl:504-511: vbls! on every bag x class model; one CTA per problem must equal the oracle's vbls."""
     rng = np.random.default_rng(17)
@@ -290,15 +291,25 @@ def test_vbls_batched(G, ctx, kind, full_cov, H):
         Y = 10.0 * synth(L, M, 3, seed=100 + b)           # scale = 10 as in examples/mil_data.jl:19
         if kind == "sparse":
             p = vo.vbmf_sparse_init(Y, H, rng=rng)
+        elif kind == "dense":
+            p = vo.vbmf_init(Y, H, sigma2=0.9, rng=rng)   # copy_vbmf_params: vbmf_init(Y, H, sigma2 = old.sigma2), mil_util.jl:216
+        elif kind == "trial":                             # copy_vbmf_params uses M0 = M (:254); also exercise a real row split
+            p = vo.vbmf_trial_init(Y, H, H - 2, M if b % 2 else M // 2, rng=rng)
+            p.alpha01, p.beta01, p.alpha02, p.beta02, p.alpha03, p.beta03 = 0.3, 0.2, 0.7, 0.4, 1e-10, 1e-10
         else:
             p = vo.vbmf_dual_init(Y, H, H - 1, rng=rng)   # H1 = 1 as in examples/mil_data.jl:23
         p.SigmaB = np.diag(rng.uniform(1e-3, 1e-2, H))    # a trained model carries a non-trivial SigmaB
-        p.sigmaHat = 0.7
+        if kind != "dense":
+            p.sigmaHat = 0.7
         Ys.append(np.asfortranarray(Y)); ps.append(p); qs.append(G.to_gpu_params(p))
     G.vb.vbls_batched_(Ys, qs, niter, full_cov=full_cov, ctx=ctx)
     fields = ["AHat", "ATVecHat", "diagSigmaATVec", "SigmaA", "CA", "beta", "sigmaHat", "zeta"]
     if kind == "dual":
         fields += ["A0Hat", "A1Hat", "CA0", "CA1", "beta0", "beta1", "alpha0", "alpha1"]
+    if kind == "trial":
+        fields += ["A1Hat", "A2Hat", "A3Hat", "CA1", "CA2", "CA3", "beta1", "beta2", "beta3", "alpha1", "alpha2", "alpha3"]
+    if kind == "dense":
+        fields = ["AHat", "SigmaA", "CA", "invCA", "sigma2"]
     for Y, p, q in zip(Ys, ps, qs):
         vo.vbls(Y, p, niter, full_cov=full_cov)
         G.compare(q, p, TOL, fields)

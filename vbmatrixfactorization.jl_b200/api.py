@@ -768,8 +768,8 @@ class BatchedVbls:
         if self.n == 0:
             return
         self.kind = self.params[0].kind
-        if self.kind == L_.DENSE or any(p.kind != self.kind for p in self.params):
-            raise VBMFError("vbls_batched_ needs a homogeneous list of vbmf_sparse or vbmf_dual parameters")
+        if any(p.kind != self.kind for p in self.params):
+            raise VBMFError("vbls_batched_ needs a homogeneous list of parameters (all dense, all sparse, all dual or all trial)")
         self.Ys = [_f(Y) for Y in Ys]
         self.structs = [_struct(p, yhat, keep_blocks) for p in self.params]
         self.yp = (L_.p_f64 * self.n)(*[_ptr(Y) for Y in self.Ys])
@@ -790,7 +790,8 @@ class BatchedVbls:
 def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, keep_blocks=False):
     """`vbls!` (examples/mil_util.jl:179-203) for many small problems in ONE kernel launch (one CTA per problem): the MIL
     classification pattern, classify(...; class_alg = "dual") runs it for every test bag and class model.  All params must
-    be vbmf_sparse_parameters or all vbmf_dual_parameters with the same L, H (and H0); M may differ per problem."""
+    be of one type (vbmf_parameters, vbmf_sparse_parameters, vbmf_dual_parameters or vbmf_trial_parameters - the four
+    branches of vbls!) with the same L, H (and H0); M (and M0) may differ per problem."""
     batch = BatchedVbls(Ys, params_list, ctx=ctx, yhat=yhat, keep_blocks=keep_blocks)
     batch.run(niter, full_cov=full_cov)
     return batch.readback()

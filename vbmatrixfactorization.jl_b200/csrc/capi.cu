@@ -1187,6 +1187,30 @@ struct BatchDesc {
     const int* moff; const double* Y; const double* B; const double* SigmaB;
     double* A; double* CA; double* beta; double* sdiag; double* SigmaA; double* blocks; double* YHat; double* scal;
 };
+struct BatchDenseDesc {
+    int nprob, L, H, niter, Mmax;
+    const int* moff; const double* Y; const double* B; const double* SigmaB;
+    double* A; double* SigmaA; double* icA; double* cA; double* YHat; double* scal;
+};
+int k_batched_vbls_dense(cudaStream_t st, const BatchDenseDesc& bd);
+}
+
+// grow-only staging of the batched path: device arena + pinned host mirror with identical offsets
+static int batch_reserve(vbmf_b200_ctx* c, size_t total) {
+    if (total <= c->batch_bytes) return 0;
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (c->batch_dev) cudaFree(c->batch_dev);
+    if (c->batch_host) cudaFreeHost(c->batch_host);
+    c->batch_dev = c->batch_host = nullptr; c->batch_bytes = 0;
+    const size_t cap = total + total / 4;
+    if (cudaMalloc(&c->batch_dev, cap) != cudaSuccess || cudaHostAlloc(&c->batch_host, cap, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->batch_dev) { cudaFree(c->batch_dev); c->batch_dev = nullptr; }
+        set_error("batched vbls: allocating %zu staging bytes failed", cap);
+        return -1;
+    }
+    c->batch_bytes = cap;
+    return 0;
 }
 
 template <class ST> struct BatchView {
@@ -1200,9 +1224,11 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     if (flags & F_DIAG_VAR) { set_error("batched vbls: diag_var is not supported"); return -1; }
     const ST* s0 = (const ST*)states[0];
     const int64_t L = s0->L, H = s0->H;
+    constexpr bool IS_DUAL = std::is_same<ST, vbmf_b200_dual_state>::value, IS_TRIAL = std::is_same<ST, vbmf_b200_trial_state>::value;
     int64_t H0 = H;
-    if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) H0 = s0->H0;
+    if constexpr (IS_DUAL || IS_TRIAL) H0 = s0->H0;
     if (L < 1 || H < 1 || H > 32) { set_error("batched vbls supports 1 <= H <= 32 (got H = %lld)", (long long)H); return -1; }
+    if (H0 < 0 || H0 > H) { set_error("H must be at least H0!"); return -1; }
     std::vector<int> moff(nprob + 1, 0);
     int Mmax = 0;
     bool want_yhat = false, want_blocks = false;
@@ -1210,7 +1236,7 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         const ST* s = (const ST*)states[p];
         if (s == nullptr || Y[p] == nullptr) { set_error("batched vbls: NULL problem %lld", (long long)p); return -1; }
         if (s->L != L || s->H != H || s->M < 1) { set_error("batched vbls: problem %lld has different L/H or M < 1", (long long)p); return -1; }
-        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) { if (s->H0 != H0) { set_error("batched vbls: H0 differs"); return -1; } }
+        if constexpr (IS_DUAL || IS_TRIAL) { if (s->H0 != H0) { set_error("batched vbls: H0 differs"); return -1; } }
         else { if (s->n_labels > 0 && s->H1 > 0) { set_error("batched vbls: labels are not supported"); return -1; } }
         moff[p + 1] = moff[p] + (int)s->M;
         Mmax = std::max<int>(Mmax, (int)s->M);
@@ -1230,20 +1256,7 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     const size_t o_A = take(MH * 8), o_beta = take(MH * 8), o_s = take(MH * 8), o_SA = take(nprob * HH * 8);
     const size_t o_YH = want_yhat ? take(L * Mtot * 8) : 0, o_blk = want_blocks ? take(MH * H * 8) : 0;
     const size_t total = off;
-    if (total > c->batch_bytes) {
-        VB_CUDA_OK(cudaStreamSynchronize(c->st));
-        if (c->batch_dev) cudaFree(c->batch_dev);
-        if (c->batch_host) cudaFreeHost(c->batch_host);
-        c->batch_dev = c->batch_host = nullptr; c->batch_bytes = 0;
-        const size_t cap = total + total / 4;
-        if (cudaMalloc(&c->batch_dev, cap) != cudaSuccess || cudaHostAlloc(&c->batch_host, cap, cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            if (c->batch_dev) { cudaFree(c->batch_dev); c->batch_dev = nullptr; }
-            set_error("batched vbls: allocating %zu staging bytes failed", cap);
-            return -1;
-        }
-        c->batch_bytes = cap;
-    }
+    if (batch_reserve(c, total)) return -1;
     char* hb = c->batch_host;
     char* db = c->batch_dev;
     // ---- pack
@@ -1258,8 +1271,11 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         memcpy(&hCA[(size_t)moff[p] * H], s->CA, (size_t)s->M * H * 8);
         double* sc = &hsc[(size_t)p * 16];
         sc[0] = s->sigmaHat; sc[1] = s->eta; sc[2] = s->zeta; sc[3] = s->zeta0; sc[4] = s->trYTY;
-        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) { sc[7] = s->alpha00; sc[8] = s->beta00; sc[9] = s->alpha01; sc[10] = s->beta01; }
-        else { sc[5] = s->alpha; sc[6] = s->beta0; }
+        if constexpr (IS_DUAL) { sc[7] = s->alpha00; sc[8] = s->beta00; sc[9] = s->alpha01; sc[10] = s->beta01; }
+        else if constexpr (IS_TRIAL) {
+            sc[5] = (double)std::min<int64_t>(std::max<int64_t>(s->M0, 0), s->M);
+            sc[7] = s->alpha01; sc[8] = s->beta01; sc[9] = s->alpha02; sc[10] = s->beta02; sc[14] = s->alpha03; sc[15] = s->beta03;
+        } else { sc[5] = s->alpha; sc[6] = s->beta0; }
     }
     int rc = 0;
     cudaStream_t st = c->st;
@@ -1297,7 +1313,31 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         if (s->YHat) memcpy(s->YHat, &hYH[(size_t)moff[p] * L], M * L * 8);
         if (s->SigmaATVec_blocks) memcpy(s->SigmaATVec_blocks, &hblk[o * H], M * HH * 8);
         s->sigmaHat = sc[0]; s->zeta = sc[2];
-        if constexpr (std::is_same<ST, vbmf_b200_dual_state>::value) {
+        if constexpr (IS_TRIAL) {
+            s->alpha1 = sc[11]; s->alpha2 = sc[12]; s->alpha3 = sc[6];
+            if (s->alpha) { s->alpha[0] = sc[11]; s->alpha[1] = sc[12]; s->alpha[2] = sc[6]; }
+            const size_t h0 = (size_t)H0, h1 = (size_t)(H - H0);
+            const size_t M2 = (size_t)std::min<int64_t>(std::max<int64_t>(s->M0, 0), s->M), M3 = M - M2;
+            for (size_t m = 0; m < M; ++m) for (size_t h = 0; h < (size_t)H; ++h) {
+                const double ca = hCA[o + m * H + h], be = hbeta[o + m * H + h], av = hA[o + m * H + h];
+                if (h < h0) {
+                    if (s->CA1) s->CA1[m * h0 + h] = ca;
+                    if (s->beta1) s->beta1[m * h0 + h] = be;
+                    if (s->A1Hat) s->A1Hat[h * M + m] = av;
+                } else if (m < M2) {
+                    const size_t k = m * h1 + (h - h0);
+                    if (s->CA2) s->CA2[k] = ca;
+                    if (s->beta2) s->beta2[k] = be;
+                    if (s->A2Hat) s->A2Hat[(h - h0) * M2 + m] = av;
+                } else {
+                    const size_t k = (m - M2) * h1 + (h - h0);
+                    if (s->CA3) s->CA3[k] = ca;
+                    if (s->beta3) s->beta3[k] = be;
+                    if (s->A3Hat) s->A3Hat[(h - h0) * M3 + (m - M2)] = av;
+                }
+            }
+        }
+        if constexpr (IS_DUAL) {
             s->alpha0 = sc[11]; s->alpha1 = sc[12];
             if (s->alpha) { s->alpha[0] = sc[11]; s->alpha[1] = sc[12]; }
             const size_t h0 = (size_t)H0, h1 = (size_t)(H - H0);
@@ -1315,11 +1355,95 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     return 0;
 }
 
+
+// dense `vbmf_parameters` problems (class_alg = "vbls", examples/mil_util.jl:470-478)
+static int batched_vbls_dense_impl(vbmf_b200_ctx* c, int64_t nprob, const double* const* Y, void* const* states, int64_t niter) {
+    if (nprob <= 0) return 0;
+    typedef vbmf_b200_dense_state ST;
+    const ST* s0 = (const ST*)states[0];
+    const int64_t L = s0->L, H = s0->H;
+    if (L < 1 || H < 1 || H > 32) { set_error("batched vbls supports 1 <= H <= 32 (got H = %lld)", (long long)H); return -1; }
+    std::vector<int> moff(nprob + 1, 0);
+    int Mmax = 0;
+    bool want_yhat = false;
+    for (int64_t p = 0; p < nprob; ++p) {
+        const ST* s = (const ST*)states[p];
+        if (s == nullptr || Y[p] == nullptr) { set_error("batched vbls: NULL problem %lld", (long long)p); return -1; }
+        if (s->L != L || s->H != H || s->M < 1) { set_error("batched vbls: problem %lld has different L/H or M < 1", (long long)p); return -1; }
+        if (s->n_labels > 0 && s->H1 > 0) { set_error("batched vbls: labels are not supported"); return -1; }
+        for (int64_t a = 0; a < H; ++a) for (int64_t b = 0; b < H; ++b)
+            if (a != b && s->invCA[a + b * H] != 0.0) { set_error("batched vbls: invCA of problem %lld is not diagonal", (long long)p); return -1; }
+        moff[p + 1] = moff[p] + (int)s->M;
+        Mmax = std::max<int>(Mmax, (int)s->M);
+        want_yhat = want_yhat || s->YHat != nullptr;
+    }
+    const size_t Mtot = (size_t)moff[nprob], MH = Mtot * H, HH = (size_t)H * H, LH = (size_t)L * H;
+    VB_CUDA_OK(cudaSetDevice(c->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_moff = take((size_t)(nprob + 1) * 4), o_Y = take(L * Mtot * 8), o_B = take(nprob * LH * 8), o_SB = take(nprob * HH * 8);
+    const size_t down_begin = off;
+    const size_t o_ic = take(nprob * H * 8), o_sc = take((size_t)nprob * 16 * 8);
+    const size_t up_end = off;
+    const size_t o_A = take(MH * 8), o_SA = take(nprob * HH * 8), o_c = take(nprob * H * 8);
+    const size_t o_YH = want_yhat ? take(L * Mtot * 8) : 0;
+    const size_t total = off;
+    if (batch_reserve(c, total)) return -1;
+    char* hb = c->batch_host;
+    char* db = c->batch_dev;
+    memcpy(hb + o_moff, moff.data(), (size_t)(nprob + 1) * 4);
+    double *hY = (double*)(hb + o_Y), *hB = (double*)(hb + o_B), *hSB = (double*)(hb + o_SB), *hic = (double*)(hb + o_ic), *hsc = (double*)(hb + o_sc);
+    memset(hsc, 0, (size_t)nprob * 16 * 8);
+    for (int64_t p = 0; p < nprob; ++p) {
+        const ST* s = (const ST*)states[p];
+        memcpy(&hY[(size_t)moff[p] * L], Y[p], (size_t)s->M * L * 8);
+        memcpy(&hB[p * LH], s->BHat, LH * 8);
+        memcpy(&hSB[p * HH], s->SigmaB, HH * 8);
+        for (int64_t h = 0; h < H; ++h) hic[p * H + h] = s->invCA[h + h * H];
+        hsc[(size_t)p * 16] = s->sigma2;
+    }
+    cudaStream_t st = c->st;
+    if (cudaMemcpyAsync(db, hb, up_end, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); set_error("batched vbls: upload failed"); return -1; }
+    BatchDenseDesc bd;
+    bd.nprob = (int)nprob; bd.L = (int)L; bd.H = (int)H; bd.niter = (int)std::max<int64_t>(niter, 0); bd.Mmax = Mmax;
+    bd.moff = (const int*)(db + o_moff); bd.Y = (const double*)(db + o_Y); bd.B = (const double*)(db + o_B); bd.SigmaB = (const double*)(db + o_SB);
+    bd.A = (double*)(db + o_A); bd.SigmaA = (double*)(db + o_SA); bd.icA = (double*)(db + o_ic); bd.cA = (double*)(db + o_c);
+    bd.YHat = want_yhat ? (double*)(db + o_YH) : nullptr; bd.scal = (double*)(db + o_sc);
+    int rc = 0;
+    prof_mark(c, c->ev_k1);
+    if (bd.niter > 0) rc = k_batched_vbls_dense(st, bd);
+    prof_mark(c, c->ev_k1);
+    if (!rc && bd.niter > 0 && cudaMemcpyAsync(hb + down_begin, db + down_begin, total - down_begin, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        cudaGetLastError(); set_error("batched vbls: download failed"); rc = -1;
+    }
+    { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess && !rc) { set_error("batched vbls: %s", cudaGetErrorString(e)); rc = -1; } }
+    if (rc || bd.niter == 0) return rc;
+    const double *hA = (const double*)(hb + o_A), *hSA = (const double*)(hb + o_SA), *hc = (const double*)(hb + o_c), *hYH = (const double*)(hb + o_YH);
+    bool failed = false;
+    for (int64_t p = 0; p < nprob; ++p) {
+        ST* s = (ST*)states[p];
+        const size_t M = (size_t)s->M, o = (size_t)moff[p] * H;
+        failed = failed || hsc[(size_t)p * 16 + 13] != 0.0;
+        if (s->AHat) for (size_t m = 0; m < M; ++m) for (size_t h = 0; h < (size_t)H; ++h) s->AHat[h * M + m] = hA[o + m * H + h];
+        if (s->SigmaA) memcpy(s->SigmaA, &hSA[p * HH], HH * 8);
+        for (int64_t h = 0; h < H; ++h) {
+            if (s->CA) s->CA[h + h * H] = hc[p * H + h];
+            if (s->invCA) s->invCA[h + h * H] = hic[p * H + h];
+        }
+        if (s->YHat) memcpy(s->YHat, &hYH[(size_t)moff[p] * L], M * L * 8);
+        s->sigma2 = hsc[(size_t)p * 16];
+    }
+    if (failed) { set_error("batched vbls: a posterior precision matrix was not positive definite (NaN written)"); return -2; }
+    return 0;
+}
+
 extern "C" int vbmf_b200_batched_vbls(vbmf_b200_ctx* c, int kind, int64_t nprob, const double* const* Y, void* const* states,
                                       int64_t niter, int flags) {
     if (!c || (nprob > 0 && (!Y || !states))) { set_error("batched vbls: NULL argument"); return -1; }
     if (kind == VBMF_B200_SPARSE) return batched_vbls_impl<vbmf_b200_sparse_state>(c, kind, nprob, Y, states, niter, flags);
     if (kind == VBMF_B200_DUAL) return batched_vbls_impl<vbmf_b200_dual_state>(c, kind, nprob, Y, states, niter, flags);
-    set_error("batched vbls exists for vbmf_sparse / vbmf_dual parameters only");
+    if (kind == VBMF_B200_TRIAL) return batched_vbls_impl<vbmf_b200_trial_state>(c, kind, nprob, Y, states, niter, flags);
+    if (kind == VBMF_B200_DENSE) return batched_vbls_dense_impl(c, nprob, Y, states, niter);
+    set_error("batched vbls: unknown parameter kind %d", kind);
     return -1;
 }
