@@ -583,3 +583,51 @@ def test_odd_shape_fuzz(G, ctx, L, M, H):
     vo.vbmf_dual_run(Y, pd, 2, eps=0.0, full_cov=(H % 4 == 1))
     G.vb.vbmf_dual_(Yf, qd, 2, eps=0.0, full_cov=(H % 4 == 1), ctx=ctx, yhat=False)
     G.compare(qd, pd, 1e-9, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CA0", "CA1", "beta", "CB", "sigmaHat", "alpha00", "alpha01", "beta00", "beta01"])
+
+
+# ------------------------------------------------------------------------------------------------ MIL callers (N1)
+def _oracle_copy_dual(Y, old):
+    p = vo.vbmf_dual_init(Y, old.H, old.H0, gamma0=old.gamma0, delta0=old.delta0, eta0=old.eta0, zeta0=old.zeta0,
+                          rng=np.random.default_rng(0))
+    p.BHat, p.SigmaB, p.CB, p.gamma, p.delta = old.BHat.copy(), old.SigmaB.copy(), old.CB.copy(), old.gamma, old.delta.copy()
+    p.alpha00, p.beta00, p.alpha01, p.beta01 = old.alpha00, old.beta00, old.alpha01, old.beta01
+    return p
+
+
+def test_mil_classify_dual_matches_reference_procedure(G, ctx):
+    """examples/mil_util.jl: copy_vbmf_params (:237-251) + vbls!(..., 20, full_cov = true) on both class models + the
+    spectral-norm decision rule (:513-533), for a whole test set in batched launches, against the same procedure spelled
+    out with the oracle one bag at a time."""
+    rng = np.random.default_rng(99)
+    L, H, H0 = 24, 6, 5
+    models = []
+    for c in range(2):                                     # two "trained" class models
+        Yt = 10.0 * synth(L, 60, 3, seed=500 + c)
+        p = vo.vbmf_dual_init(Yt, H, H0, rng=rng)
+        vo.vbmf_dual_run(Yt, p, 15, eps=0.0, full_cov=True)
+        models.append(p)
+    gm = [G.to_gpu_params(m) for m in models]
+    bags = [np.asfortranarray(10.0 * synth(L, int(rng.integers(3, 25)), 3, seed=(500 if b % 2 == 0 else 501) + 7 * b)) for b in range(30)]
+    labels, e0, e1 = G.vb.mil.classify_bags(gm[0], gm[1], bags, class_alg="dual", ctx=ctx)
+    for b, Y in enumerate(bags):
+        errs = []
+        for m in models:
+            p = _oracle_copy_dual(Y, m)
+            vo.vbls(Y, p, 20, full_cov=True)
+            errs.append(np.linalg.norm(p.YHat - Y, 2) / (Y.shape[0] * Y.shape[1]))
+        assert abs(e0[b] - errs[0]) <= 1e-9 * errs[0] and abs(e1[b] - errs[1]) <= 1e-9 * errs[1]
+        assert labels[b] == (0 if errs[0] < errs[1] else 1)
+    lab1, a0, a1 = G.vb.mil.classify(gm[0], gm[1], bags[3], class_alg="dual", ctx=ctx)
+    assert lab1 == labels[3] and a0 == e0[3] and a1 == e1[3]
+    mer, eer, fp, fn, n0, n1 = G.vb.mil.test_classification(gm[0], gm[1], bags, labels, class_alg="dual", ctx=ctx)
+    assert (mer, fp, fn) == (0.0, 0, 0) and n0 + n1 == len(bags)
+
+
+def test_mil_train_dual_restarts(G, ctx):
+    """train_dual (:327-385): column subsampling to floor(3200/H), vbmf_dual! with full_cov, and a usable (non-collapsed) model."""
+    rng = np.random.default_rng(5)
+    Y0, Y1 = 10.0 * synth(20, 900, 3, seed=1), 10.0 * synth(20, 50, 3, seed=2)
+    p0, p1 = G.vb.mil.train_dual(Y0, Y1, 8, 7, 10, eps=1e-4, ctx=ctx, rng=rng)
+    assert p0.M == 400 and p1.M == 50 and p0.H0 == 7
+    for p in (p0, p1):
+        assert np.linalg.norm(p.AHat, 2) + np.linalg.norm(p.BHat, 2) >= 1e-2 and np.all(np.isfinite(p.BHat))

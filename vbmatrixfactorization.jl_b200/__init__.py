@@ -7,3 +7,4 @@ from . import _lib
 from ._lib import VBMFError, LIB_PATH
 from .api import *  # noqa: F401,F403
 from .api import Solver
+from . import mil  # noqa: F401  (callers of the path in the reference's MIL example)
