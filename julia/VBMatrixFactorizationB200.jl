@@ -208,18 +208,48 @@ function vbmf_trial(ctx::B200Context, Y, p_in::vbmf_trial_parameters, niter::Int
 end
 
 # ---- vbls! for many bags in one launch (examples/mil_util.jl:179-203, 504-511) --------------------------------------------------
-# Ys[k] is the L x M_k matrix of problem k, ps[k] its vbmf_dual_parameters (all with the same L, H, H0).
+# Ys[k] is the L x M_k matrix of problem k, ps[k] its parameters (all of one type, with the same L, H, H0); one method per
+# branch of vbls! (:182-197).  kind: 0 dense, 1 sparse, 2 dual, 3 trial (include/vbmf_b200.h).
+function batched_call(ctx::B200Context, kind::Int, Ys::Vector{Array{Float64,2}}, sts::Vector, niter::Int, flags::Int)
+    yptr = Ptr{Float64}[pointer(Y) for Y in Ys]
+    sptr = Ptr{Void}[convert(Ptr{Void}, Base.unsafe_convert(Ptr{eltype(r)}, r)) for r in sts]
+    check(ccall((:vbmf_b200_batched_vbls, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Ptr{Float64}}, Ptr{Ptr{Void}}, Int64, Cint),
+                ctx.handle, kind, length(sts), yptr, sptr, niter, flags))
+end
 function vbls_batched!(ctx::B200Context, Ys::Vector{Array{Float64,2}}, ps::Vector{vbmf_dual_parameters}, niter::Int; full_cov::Bool = false)
-    n = length(ps)
     for p in ps; p.YHat = Array{Float64}(p.L, p.M); end
     sts = [Ref(dual_state(p)) for p in ps]
-    yptr = Ptr{Float64}[pointer(Y) for Y in Ys]
-    sptr = Ptr{Void}[Base.unsafe_convert(Ptr{Void}, Base.unsafe_convert(Ptr{DualState}, r)) for r in sts]
-    check(ccall((:vbmf_b200_batched_vbls, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Ptr{Float64}}, Ptr{Ptr{Void}}, Int64, Cint),
-                ctx.handle, 2, n, yptr, sptr, niter, full_cov ? 2 : 0))
+    batched_call(ctx, 2, Ys, sts, niter, full_cov ? 2 : 0)
     for (p, r) in zip(ps, sts)
         p.sigmaHat = r[].sigmaHat; p.zeta = r[].zeta; p.alpha0 = r[].alpha0; p.alpha1 = r[].alpha1
     end
+    return [p.AHat for p in ps]
+end
+function vbls_batched!(ctx::B200Context, Ys::Vector{Array{Float64,2}}, ps::Vector{vbmf_sparse_parameters}, niter::Int; full_cov::Bool = false)
+    for p in ps; p.YHat = Array{Float64}(p.L, p.M); end
+    sts = [Ref(sparse_state(p, convert(Ptr{Float64}, C_NULL))) for p in ps]
+    batched_call(ctx, 1, Ys, sts, niter, full_cov ? 2 : 0)
+    for (p, r) in zip(ps, sts)
+        p.sigmaHat = r[].sigmaHat; p.zeta = r[].zeta
+    end
+    return [p.AHat for p in ps]
+end
+function vbls_batched!(ctx::B200Context, Ys::Vector{Array{Float64,2}}, ps::Vector{vbmf_trial_parameters}, niter::Int; full_cov::Bool = false)
+    for p in ps; p.YHat = Array{Float64}(p.L, p.M); end
+    sts = [Ref(trial_state(p)) for p in ps]
+    batched_call(ctx, 3, Ys, sts, niter, full_cov ? 2 : 0)
+    for (p, r) in zip(ps, sts)
+        p.sigmaHat = r[].sigmaHat; p.zeta = r[].zeta; p.alpha1 = r[].alpha1; p.alpha2 = r[].alpha2; p.alpha3 = r[].alpha3
+    end
+    return [p.AHat for p in ps]
+end
+function vbls_batched!(ctx::B200Context, Ys::Vector{Array{Float64,2}}, ps::Vector{vbmf_parameters}, niter::Int)
+    for p in ps; p.YHat = Array{Float64}(p.L, p.M); end
+    sts = [Ref(DenseState(p.L, p.M, p.H, p.H1, length(p.labels), pointer(p.labels), pointer(p.AHat), pointer(p.BHat),
+                          pointer(p.SigmaA), pointer(p.SigmaB), pointer(p.CA), pointer(p.CB), pointer(p.invCA), pointer(p.invCB),
+                          p.sigma2, pointer(p.YHat))) for p in ps]
+    batched_call(ctx, 0, Ys, sts, niter, 0)
+    for (p, r) in zip(ps, sts); p.sigma2 = r[].sigma2; end
     return [p.AHat for p in ps]
 end
 
