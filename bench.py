@@ -31,6 +31,8 @@ WORKLOADS = {
     # name: (L, M, H, kind, flags, description)
     "c3": (20000, 200000, 64, "dense", ("est_covs", "est_var"),
            "configs[2]: synthetic dense Y 20000x200000, rank-32 signal + 0.1 noise, vbmf H=64 with ARD (est_covs, est_var), Float64"),
+    # diagnostic only: the per-GPU shard of c3 at 8 GPUs on ONE GPU (no exchange), to separate kernel time from exchange time
+    "c3shard8": (20000, 25000, 64, "dense", ("est_covs", "est_var"), "diagnostic: one 25000-column shard of configs[2] (what each of 8 GPUs computes)"),
     "c4": (10000, 100000, 32, "sparse", ("est_cb",), "configs[3] (diagonal covariance path): vbmf_sparse 10000x100000 H=32"),
     "c4full": (10000, 100000, 32, "sparse", ("est_cb", "full_cov"), "configs[3]: vbmf_sparse 10000x100000 H=32 full_cov (batched per-row Cholesky)"),
     # configs[4] needs >= 4 GPUs at full size (Y = 400 GB); per SURVEY 8(d) fewer GPUs run M = 125000 columns per GPU
