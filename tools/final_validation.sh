@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
+timeout 300 python bench.py 2>/dev/null | tail -1 > gpurun_out/fin_c3.json; cut -c1-200 gpurun_out/fin_c3.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/fin_ref.json; cut -c1-200 gpurun_out/fin_ref.json
+for w in c4 c4full c5 c2; do timeout 300 python bench.py --workload $w 2>/dev/null | tail -1 > gpurun_out/fin_$w.json; cut -c1-200 gpurun_out/fin_$w.json; done
