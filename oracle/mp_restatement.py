@@ -19,7 +19,11 @@ LN2PI = mp.log(2 * mp.pi)
 
 
 def M_(a):
-    """numpy 2-D array -> mp.matrix"""
+    """numpy 2-D array -> mp.matrix (empty shapes allowed)"""
+    import numpy as np
+    a = np.asarray(a)
+    if a.size == 0:
+        return mp.matrix(int(a.shape[0]), int(a.shape[1]))
     return mp.matrix([[mp.mpf(float(x)) for x in row] for row in a])
 
 
@@ -297,6 +301,68 @@ def dual_update_priors(p):
         p["beta00"] = M * H0 * p["alpha00"] / mp.fsum(p["CA0"])
     if M * H1 > 0:
         p["beta01"] = M * H1 * p["alpha01"] / mp.fsum(p["CA1"])
+
+
+# ------------------------------------------------------------------------------------------------ src/vbmf_trial.jl
+def trial_split(p):
+    """src/vbmf_trial.jl:316-319: the three group views of AHat."""
+    A, H, H0, M, M0 = p["AHat"], p["H"], p["H0"], p["M"], p["M0"]
+    p["A1Hat"] = A[:, 0:H0]
+    p["A2Hat"] = A[0:M0, H0:H] if M0 > 0 and H > H0 else mp.matrix(M0, H - H0)
+    p["A3Hat"] = A[M0:M, H0:H] if M > M0 and H > H0 else mp.matrix(M - M0, H - H0)
+
+
+def _sq_plus(At, dS):
+    """vec(At .* At + dS), column-major, for mp matrices of equal shape (possibly empty)."""
+    if At.rows == 0 or At.cols == 0:
+        return []
+    return vec_colmajor(mp.matrix([[At[i, j] ** 2 + dS[i, j] for j in range(At.cols)] for i in range(At.rows)]))
+
+
+def trial_updateCA(p):
+    """src/vbmf_trial.jl:357-400."""
+    M, H, H0, M0 = p["M"], p["H"], p["H0"], p["M0"]
+    H1, M1 = H - H0, M - M0
+    half = mp.mpf(1) / 2
+    p["alpha1"], p["alpha2"], p["alpha3"] = p["alpha01"] + half, p["alpha02"] + half, p["alpha03"] + half
+    dS = reshape_colmajor(p["diagSigmaATVec"], H, M)
+    z = lambda r, c: mp.matrix(r, c)
+    dS1 = dS[0:H0, :] if H0 else z(0, M)
+    dS2 = dS[H0:H, 0:M0] if (H1 and M0) else z(H1, M0)
+    dS3 = dS[H0:H, M0:M] if (H1 and M1) else z(H1, M1)
+    p["beta1"] = [p["beta01"] + x / 2 for x in _sq_plus(p["A1Hat"].T if H0 else z(0, M), dS1)]
+    p["beta2"] = [p["beta02"] + x / 2 for x in _sq_plus(p["A2Hat"].T if (H1 and M0) else z(H1, M0), dS2)]
+    p["beta3"] = [p["beta03"] + x / 2 for x in _sq_plus(p["A3Hat"].T if (H1 and M1) else z(H1, M1), dS3)]
+    p["CA1"] = [p["alpha1"] / b for b in p["beta1"]]
+    p["CA2"] = [p["alpha2"] / b for b in p["beta2"]]
+    p["CA3"] = [p["alpha3"] / b for b in p["beta3"]]
+    CA, beta = [], []
+    for m in range(M0):
+        CA += p["CA1"][m * H0:(m + 1) * H0] + p["CA2"][m * H1:(m + 1) * H1]
+        beta += p["beta1"][m * H0:(m + 1) * H0] + p["beta2"][m * H1:(m + 1) * H1]
+    for m in range(M0, M):
+        CA += p["CA1"][m * H0:(m + 1) * H0] + p["CA3"][(m - M0) * H1:(m - M0 + 1) * H1]
+        beta += p["beta1"][m * H0:(m + 1) * H0] + p["beta3"][(m - M0) * H1:(m - M0 + 1) * H1]
+    p["CA"], p["beta"] = CA, beta
+    p["alpha"] = [p["alpha1"], p["alpha2"], p["alpha3"]]
+
+
+def trial_update_priors(p):
+    """src/vbmf_trial.jl:442-507 in the loop's order (:565-570): alpha01, alpha02, alpha03, beta01, beta02, beta03."""
+    M, H0, M0 = p["M"], p["H0"], p["M0"]
+    H1, M1 = p["H"] - H0, M - M0
+    groups = ((M * H0, "alpha01", "beta01", "alpha1", "beta1", "CA1"), (M0 * H1, "alpha02", "beta02", "alpha2", "beta2", "CA2"),
+              (M1 * H1, "alpha03", "beta03", "alpha3", "beta3", "CA3"))
+    for N, a0x, b0x, ag, bg, _ in groups:
+        if N == 0:
+            continue                                   # f == 0 everywhere: no bracket, the `try` keeps the old value
+        s = mp.fsum(gammaELn(p[ag], b) for b in p[bg])
+        r = _root(lambda x: N * mp.log(p[b0x]) - N * mp.digamma(x) + s)
+        if r is not None:
+            p[a0x] = r
+    for N, a0x, b0x, _, _, cag in groups:
+        if N > 0:
+            p[b0x] = N * p[a0x] / mp.fsum(p[cag])
 
 
 def from_oracle(p, Y):

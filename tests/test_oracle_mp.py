@@ -102,3 +102,32 @@ def test_dual_grouped_ard_and_hyperprior_root():
         mr.dual_update_priors(d)
         _cmp(p, d, SPARSE_FIELDS + ("CA0", "CA1", "beta0", "beta1", "alpha0", "alpha1", "sigmaHat"))
         _cmp(p, d, ("alpha00", "alpha01", "beta00", "beta01"), tol=1e-10)
+
+
+@pytest.mark.parametrize("M0", [0, 2, 5])
+def test_trial_three_group_ard_and_priors(M0):
+    """src/vbmf_trial.jl: groups (columns < H0 | rows <= M0 | rows > M0) incl. the empty-group edges M0 = 0 and M0 = M."""
+    L, M, H, H0 = 4, 5, 3, 1
+    Y, rng = _problem(L, M, H, 23 + M0)
+    p = vo.vbmf_trial_init(Y, H, H0, M0, rng=rng, alpha0=1.0, beta0=1.0)
+    for it in range(3):
+        Ym, d = mr.from_oracle(copy.deepcopy(p), Y)
+        vo.trial_updateA(Y, p, full_cov=(it == 1))
+        vo.sparse_updateB(Y, p)
+        vo.trial_updateCA(p)
+        vo.sparse_updateCB(p)
+        vo.sparse_updateSigma(Y, p)
+        vo.trial_update_priors(p)
+        mr.updateA(Ym, d, full_cov=(it == 1), mask=False)
+        mr.trial_split(d)
+        mr.updateB(Ym, d)
+        mr.trial_updateCA(d)
+        mr.updateCB(d)
+        mr.updateSigma(Ym, d)
+        mr.trial_update_priors(d)
+        _cmp(p, d, ("AHat", "diagSigmaATVec", "SigmaA", "BHat", "SigmaB", "CA", "beta", "CA1", "beta1", "alpha1", "alpha2", "alpha3", "sigmaHat"))
+        for f in ("CA2", "beta2", "CA3", "beta3"):
+            if len(d[f]):
+                _cmp(p, d, (f,))
+        live = ["alpha01", "beta01"] + (["alpha02", "beta02"] if M0 > 0 else []) + (["alpha03", "beta03"] if M0 < M else [])
+        _cmp(p, d, live, tol=1e-10)
