@@ -375,7 +375,7 @@ int k_gram_w2(cudaStream_t st, const Dev& d, const double* X, int n, const doubl
 template <int HP2>   // H rounded up to a power of two (32, 64, 128); thread t owns column t % HP2, rows t / HP2 + q * (1024 / HP2)
 __global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_var) {
     ACTIVE_OR_RETURN(d);
-    __shared__ double cbuf[2 * 128], sbuf[128];
+    __shared__ double cbuf[2 * 128], sbuf[128], idb[2];
     constexpr int Q = HP2 * HP2 / 1024, RP = 1024 / HP2;
     const int H = d.H;
     Scalars* sc = d.sc;
@@ -409,28 +409,37 @@ __global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_
     const double sj = live ? sbuf[j] : 1.0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) { const int i = i0 + q * RP; if (live && i < H) a[q] *= sbuf[i] * sj; }
-    for (int k = 0; k < H; ++k) {
-        double* col = cbuf + (k & 1) * 128;
-        if (j == k) {
+    // One barrier per sweep: the owners of column k+1 publish it (and the owner of the next pivot its reciprocal, so the
+    // other 1023 threads do not each pay for a double-precision division) right after their own update of sweep k.
+    // Per element one FMA: a + col[i]*beta with beta = -col[j]/d, and beta = 1/d - 1 in the pivot column (a == col[i] there).
+    if (j == 0) {
 #pragma unroll
-            for (int q = 0; q < Q; ++q) { const int i = i0 + q * RP; if (i < H) col[i] = a[q]; }
-        }
-        __syncthreads();
+        for (int q = 0; q < Q; ++q) { const int i = i0 + q * RP; if (i < H) cbuf[i] = a[q]; }
+        if (i0 == 0) idb[0] = 1.0 / a[0];
+    }
+    __syncthreads();
+    for (int k = 0; k < H; ++k) {
+        const double* col = cbuf + (k & 1) * 128;
+        double* coln = cbuf + ((k + 1) & 1) * 128;
         const double dk = col[k];
         if (!(dk > 0.0) || !(dk < 1e300)) ok = false;
-        const double id = 1.0 / dk;
-        const double cj = live ? col[j] : 0.0;
+        const double id = idb[k & 1];
+        const double t = (live ? col[j] : 0.0) * id;
+        const bool pc = j == k;
+        const double beta = pc ? id - 1.0 : -t, rowv = pc ? -id : t;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int i = i0 + q * RP;
             if (live && i < H) {
-                double v;
-                if (i == k) v = (j == k) ? -id : cj * id;
-                else if (j == k) v = col[i] * id;
-                else v = a[q] - (col[i] * cj) * id;
+                const double v = (i == k) ? rowv : fma(col[i], beta, a[q]);
                 a[q] = v;
+                if (j == k + 1) {
+                    coln[i] = v;
+                    if (i == k + 1) idb[(k + 1) & 1] = 1.0 / v;
+                }
             }
         }
+        __syncthreads();
     }
     if (!ok && threadIdx.x == 0) sc->chol_fail = 1;
     double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_
 }
 static int hxh_launch(cudaStream_t st, const Dev& d, int mode, int dv) {
     const int hh = d.H * d.H;
-    // 1024 threads beat 256 (0.060 vs 0.099 ms at H = 64): the sweep is latency bound, more warps hide it
+    // 1024 threads beat 512 / 256 (46 vs 62 vs ~100 us at H = 64): the sweep is latency bound, more warps hide it
     if (hh <= 1024) hxh_kernel<32><<<1, 1024, 0, st>>>(d, mode, dv);
     else if (hh <= 4096) hxh_kernel<64><<<1, 1024, 0, st>>>(d, mode, dv);
     else hxh_kernel<128><<<1, 1024, 0, st>>>(d, mode, dv);
