@@ -631,3 +631,56 @@ def test_mil_train_dual_restarts(G, ctx):
     assert p0.M == 400 and p1.M == 50 and p0.H0 == 7
     for p in (p0, p1):
         assert np.linalg.norm(p.AHat, 2) + np.linalg.norm(p.BHat, 2) >= 1e-2 and np.all(np.isfinite(p.BHat))
+
+
+def _random_cases():
+    """Random (kind, shape, flags) cases; VBMF_FUZZ_N widens the sweep for a soak run (default keeps the suite fast)."""
+    import os
+    n = int(os.environ.get("VBMF_FUZZ_N", "8"))
+    rng = np.random.default_rng(int(os.environ.get("VBMF_FUZZ_SEED", "424242")))
+    out = []
+    for c in range(n):
+        kind = ["dense", "sparse", "dual", "trial"][int(rng.integers(0, 4))]
+        H = int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 31, 32, 33, 40, 48, 64, 65, 80, 96, 128]))
+        L = int(rng.integers(1, 400))
+        M = int(rng.integers(max(2, H // 4), 2500))
+        full_cov = bool(rng.integers(0, 2)) and (H <= 64 or M <= 600)
+        diag_var = bool(rng.integers(0, 2))
+        out.append((c, kind, L, M, H, full_cov, diag_var))
+    return out
+
+
+@pytest.mark.parametrize("case,kind,L,M,H,full_cov,diag_var", _random_cases())
+def test_random_fuzz(G, ctx, case, kind, L, M, H, full_cov, diag_var):
+    """Random kinds / shapes / flags, one teacher-forced iteration twice (the second from the GPU's own state) vs the oracle."""
+    rng = np.random.default_rng(1000 + case)
+    Y = synth(L, M, max(1, min(H, L, M) // 2), seed=31 * case + 7)
+    Yf = np.asfortranarray(Y)
+    if kind == "dense":
+        H1 = int(rng.integers(0, H + 1)) if case % 2 else 0
+        labels = sorted(set(int(x) for x in rng.integers(1, M + 1, size=min(M, 5)))) if H1 else []
+        p = vo.vbmf_init(Y, H, H1=H1, labels=labels, rng=rng)
+        run_o = lambda q_: vo.vbmf_run(Y, q_, 1, eps=0.0, est_covs=True, est_var=True)
+        run_g = lambda q_: G.vb.vbmf_(Yf, q_, 1, eps=0.0, est_covs=True, est_var=True, ctx=ctx, yhat=False)
+        fields = ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "sigma2"]
+    elif kind == "sparse":
+        H1 = int(rng.integers(0, H + 1)) if case % 2 else 0
+        labels = sorted(set(int(x) for x in rng.integers(1, M + 1, size=min(M, 5)))) if H1 else []
+        p = vo.vbmf_sparse_init(Y, H, H1=H1, labels=labels, rng=rng)
+        run_o = lambda q_: vo.vbmf_sparse_run(Y, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var)
+        run_g = lambda q_: G.vb.vbmf_sparse_(Yf, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var, ctx=ctx, yhat=False)
+        fields = ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "beta", "CB", "diagSigmaATVec", "sigmaHat", "sigmaVecHat"]
+    elif kind == "dual":
+        p = vo.vbmf_dual_init(Y, H, int(rng.integers(0, H + 1)), rng=rng)
+        run_o = lambda q_: vo.vbmf_dual_run(Y, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var)
+        run_g = lambda q_: G.vb.vbmf_dual_(Yf, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var, ctx=ctx, yhat=False)
+        fields = ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "beta", "CB", "sigmaHat", "sigmaVecHat", "alpha00", "alpha01", "beta00", "beta01"]
+    else:
+        p = vo.vbmf_trial_init(Y, H, int(rng.integers(0, H + 1)), int(rng.integers(0, M + 1)), rng=rng)
+        run_o = lambda q_: vo.vbmf_trial_run(Y, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var)
+        run_g = lambda q_: G.vb.vbmf_trial_(Yf, q_, 1, eps=0.0, full_cov=full_cov, diag_var=diag_var, ctx=ctx, yhat=False)
+        fields = ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "beta", "CB", "sigmaHat", "sigmaVecHat", "alpha01", "alpha02", "alpha03"]
+    q = G.to_gpu_params(p)
+    run_o(p)
+    run_g(q)
+    G.compare(q, p, 1e-9, fields)
