@@ -684,3 +684,46 @@ def test_random_fuzz(G, ctx, case, kind, L, M, H, full_cov, diag_var):
     run_o(p)
     run_g(q)
     G.compare(q, p, 1e-9, fields)
+
+
+def test_two_contexts_concurrently(G):
+    """Two host threads, each with its own context (own stream) on the same GPU, run different problems at the same time
+    (ctypes drops the GIL inside the library): no shared mutable state between contexts, results equal the oracle's."""
+    import threading
+    jobs = []
+    for k, (L, M, H, kind) in enumerate([(90, 1500, 12, "sparse"), (130, 900, 20, "dense")]):
+        Y = synth(L, M, H // 2, seed=900 + k)
+        if kind == "sparse":
+            p = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(k))
+        else:
+            p = vo.vbmf_init(Y, H, rng=np.random.default_rng(k))
+        jobs.append((kind, Y, p))
+    outs, errs = [None, None], []
+
+    def work(k):
+        try:
+            kind, Y, p = jobs[k]
+            c = G.vb.Context(device=0)
+            Yf = np.asfortranarray(Y)
+            for rep in range(6):                      # several calls so the two threads really overlap
+                q = G.to_gpu_params(p)
+                if kind == "sparse":
+                    G.vb.vbmf_sparse_(Yf, q, 8, eps=0.0, full_cov=True, ctx=c, yhat=False)
+                else:
+                    G.vb.vbmf_(Yf, q, 8, eps=0.0, est_covs=True, est_var=True, ctx=c, yhat=False)
+            outs[k] = q
+            c.close()
+        except Exception as e:                        # surfaced in the main thread
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k, (kind, Y, p) in enumerate(jobs):
+        po = copy.deepcopy(p)
+        if kind == "sparse":
+            vo.vbmf_sparse_run(Y, po, 8, eps=0.0, full_cov=True)
+            G.compare(outs[k], po, 1e-8, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "sigmaHat"])
+        else:
+            vo.vbmf_run(Y, po, 8, eps=0.0, est_covs=True, est_var=True)
+            G.compare(outs[k], po, 1e-8, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "sigma2"])
