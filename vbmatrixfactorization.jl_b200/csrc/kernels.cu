@@ -492,9 +492,18 @@ __global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(
     }
     const double s2 = d.sc->sigma2;
     const int hmask = H - d.H1;      // columns >= hmask are zeroed on labelled rows
-    double g[TPW][2];
+    constexpr int NTW = TPW == 2 ? 2 : (TPW == 8 ? 4 : 8);       // column tiles of the product per warp: ceil(nt8 / 2)
+    constexpr int GT = TPW == 2 ? 2 : (TPW == 8 ? 5 : 17);       // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
+    double g[GT][2];
+    int ga[GT], gb[GT];            // this warp's Gram tiles (at <= bt), -1 = none; idx = warp + 8*q enumerates the upper triangle
 #pragma unroll
-    for (int q = 0; q < TPW; ++q) { g[q][0] = 0.0; g[q][1] = 0.0; }
+    for (int q = 0; q < GT; ++q) {
+        g[q][0] = 0.0; g[q][1] = 0.0;
+        int idx = warp + 8 * q, at = 0;
+        while (at < nt8 && idx >= nt8 - at) { idx -= nt8 - at; ++at; }
+        ga[q] = at < nt8 ? at : -1;
+        gb[q] = at + idx;
+    }
     const int ntiles = (d.Mloc + 31) / 32;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
@@ -513,50 +522,61 @@ __global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(
             T[i * ld + c] = v;
         }
         __syncthreads();
-        // An = T * SigmaA / sigma2 : warp -> row tile (warp & 3), column tiles (warp >> 2), +2, ...
+        // An = T * SigmaA / sigma2 : warp -> row tile (warp & 3), column tiles (warp >> 2), +2, ... with one independent
+        // accumulator per column tile (a single accumulator makes the k loop one dependent chain of DMMAs, 26 clk each)
         {
             const int mt = warp & 3;
-            for (int nt = warp >> 2; nt < nt8; nt += 2) {
-                double c2[2] = {0.0, 0.0};
-#pragma unroll 8
-                for (int k0 = 0; k0 < HP8; k0 += 4)
-                    dmma_acc(c2, T[(8 * mt + r) * ld + k0 + j], Ss[(k0 + j) * ld + 8 * nt + r]);
-                const int row = 8 * mt + r, col = 8 * nt + 2 * j;
-                double v0 = c2[0] / s2, v1 = c2[1] / s2;
-                const bool lab = d.rowmask != nullptr && row < nr && d.rowmask[m0 + row];
-                if (lab && col >= hmask) v0 = 0.0;
-                if (lab && col + 1 >= hmask) v1 = 0.0;
-                An[row * ld + col] = v0;
-                An[row * ld + col + 1] = v1;
-                if (row < nr) {
-                    double* out = d.A + (size_t)(m0 + row) * H + col;
-                    if (col < H) out[0] = v0;
-                    if (col + 1 < H) out[1] = v1;
+            double c2[NTW][2];
+#pragma unroll
+            for (int u = 0; u < NTW; ++u) { c2[u][0] = 0.0; c2[u][1] = 0.0; }
+#pragma unroll 4
+            for (int k0 = 0; k0 < HP8; k0 += 4) {
+                const double af = T[(8 * mt + r) * ld + k0 + j];
+#pragma unroll
+                for (int u = 0; u < NTW; ++u) {
+                    const int nt = (warp >> 2) + 2 * u;
+                    if (nt < nt8) dmma_acc(c2[u], af, Ss[(k0 + j) * ld + 8 * nt + r]);
+                }
+            }
+            const int row = 8 * mt + r;
+            const bool lab = d.rowmask != nullptr && row < nr && d.rowmask[m0 + row];
+#pragma unroll
+            for (int u = 0; u < NTW; ++u) {
+                const int nt = (warp >> 2) + 2 * u;
+                if (nt < nt8) {
+                    const int col = 8 * nt + 2 * j;
+                    double v0 = c2[u][0] / s2, v1 = c2[u][1] / s2;
+                    if (lab && col >= hmask) v0 = 0.0;
+                    if (lab && col + 1 >= hmask) v1 = 0.0;
+                    An[row * ld + col] = v0;
+                    An[row * ld + col + 1] = v1;
+                    if (row < nr) {
+                        double* out = d.A + (size_t)(m0 + row) * H + col;
+                        if (col < H) out[0] = v0;
+                        if (col + 1 < H) out[1] = v1;
+                    }
                 }
             }
         }
         __syncthreads();
-        // G += An' * An over the 32 rows of the tile
+        // G += An' * An over the 32 rows of the tile; G is symmetric, so only the tiles on and above the diagonal are
+        // accumulated (tile (bt, at) is the transpose of (at, bt) bit for bit) and mirrored when the partial is written
 #pragma unroll
-        for (int q = 0; q < TPW; ++q) {
-            const int idx = warp + 8 * q;
-            if (idx < nt8 * nt8) {
-                const int at = idx / nt8, bt = idx - at * nt8;
+        for (int q = 0; q < GT; ++q) {
+            if (ga[q] >= 0) {
 #pragma unroll
                 for (int i0 = 0; i0 < 32; i0 += 4)
-                    dmma_acc(g[q], An[(i0 + j) * ld + 8 * at + r], An[(i0 + j) * ld + 8 * bt + r]);
+                    dmma_acc(g[q], An[(i0 + j) * ld + 8 * ga[q] + r], An[(i0 + j) * ld + 8 * gb[q] + r]);
             }
         }
     }
     double* out = d.part + (size_t)blockIdx.x * H * H;
 #pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-        const int idx = warp + 8 * q;
-        if (idx < nt8 * nt8) {
-            const int at = idx / nt8, bt = idx - at * nt8;
-            const int a = 8 * at + r, b = 8 * bt + 2 * j;
-            if (a < H && b < H) out[a * H + b] = g[q][0];
-            if (a < H && b + 1 < H) out[a * H + b + 1] = g[q][1];
+    for (int q = 0; q < GT; ++q) {
+        if (ga[q] >= 0) {
+            const int a = 8 * ga[q] + r, b = 8 * gb[q] + 2 * j;
+            if (a < H && b < H) { out[a * H + b] = g[q][0]; out[b * H + a] = g[q][0]; }
+            if (a < H && b + 1 < H) { out[a * H + b + 1] = g[q][1]; out[(b + 1) * H + a] = g[q][1]; }
         }
     }
 }
