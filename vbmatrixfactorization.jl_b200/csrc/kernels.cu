@@ -282,7 +282,7 @@ __device__ __forceinline__ void dmma_acc2(double (&c)[2], double a, double b) {
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 __host__ __device__ inline int pitch4g(int hp8) { return ((hp8 + 11) / 16) * 16 + 4; }
-template <int TPW, bool AMAT>
+template <int GT, bool AMAT>   // GT = upper-triangular 8x8 tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
 __global__ void __launch_bounds__(256) gram_dmma_kernel(const double* __restrict__ X, int n, int H, int ldx, double* __restrict__ part,
                                                         const Scalars* sc) {
     if (!sc->active) return;
@@ -290,9 +290,15 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(const double* __restrict
     const int HP8 = (H + 7) & ~7, ld = pitch4g(HP8), nt8 = HP8 / 8;
     double* T = sm;     // [32][ld]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
-    double g[TPW][2];
+    double g[GT][2];
+    int gt[GT];           // this warp's tiles at | bt << 8 (at <= bt; the lower triangle is the bit-exact mirror), -1 = none
 #pragma unroll
-    for (int q = 0; q < TPW; ++q) { g[q][0] = 0.0; g[q][1] = 0.0; }
+    for (int q = 0; q < GT; ++q) {
+        g[q][0] = 0.0; g[q][1] = 0.0;
+        int idx = warp + 8 * q, at = 0;
+        while (at < nt8 && idx >= nt8 - at) { idx -= nt8 - at; ++at; }
+        gt[q] = at < nt8 ? (at | ((at + idx) << 8)) : -1;
+    }
     const int ntiles = (n + 31) / 32;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = tile * 32, nr = min(32, n - r0);
@@ -312,24 +318,22 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(const double* __restrict
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < TPW; ++q) {
-            const int idx = warp + 8 * q;
-            if (idx < nt8 * nt8) {
-                const int at = idx / nt8, bt = idx - at * nt8;
+        for (int q = 0; q < GT; ++q) {
+            if (gt[q] >= 0) {
+                const double* pa = T + j * ld + 8 * (gt[q] & 255) + r;
+                const double* pb = T + j * ld + 8 * (gt[q] >> 8) + r;
 #pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += 4) dmma_acc2(g[q], T[(i0 + j) * ld + 8 * at + r], T[(i0 + j) * ld + 8 * bt + r]);
+                for (int i0 = 0; i0 < 32; i0 += 4) dmma_acc2(g[q], pa[i0 * ld], pb[i0 * ld]);
             }
         }
     }
     double* out = part + (size_t)blockIdx.x * H * H;
 #pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-        const int idx = warp + 8 * q;
-        if (idx < nt8 * nt8) {
-            const int at = idx / nt8, bt = idx - at * nt8;
-            const int a = 8 * at + r, b = 8 * bt + 2 * j;
-            if (a < H && b < H) out[a * H + b] = g[q][0];
-            if (a < H && b + 1 < H) out[a * H + b + 1] = g[q][1];
+    for (int q = 0; q < GT; ++q) {
+        if (gt[q] >= 0) {
+            const int a = 8 * (gt[q] & 255) + r, b = 8 * (gt[q] >> 8) + 2 * j;
+            if (a < H && b < H) { out[a * H + b] = g[q][0]; out[b * H + a] = g[q][0]; }
+            if (a < H && b + 1 < H) { out[a * H + b + 1] = g[q][1]; out[(b + 1) * H + a] = g[q][1]; }
         }
     }
 }
@@ -340,7 +344,7 @@ static int gram_dmma(cudaStream_t st, const Dev& d, const double* X, bool amat, 
 #define GD(TP)                                                                                                          \
     if (amat) gram_dmma_kernel<TP, true><<<grid, 256, smem, st>>>(X, n, H, d.ldB, d.part, d.sc);                       \
     else gram_dmma_kernel<TP, false><<<grid, 256, smem, st>>>(X, n, H, d.ldB, d.part, d.sc);
-    if (HP8 <= 32) { GD(2) } else if (HP8 <= 64) { GD(8) } else { GD(32) }
+    if (HP8 <= 32) { GD(2) } else if (HP8 <= 64) { GD(5) } else { GD(17) }
 #undef GD
     VB_LAUNCH_OK();
     return sum_partials(st, d.part, grid, (size_t)H * H, (size_t)H * H, out, d.sc);
