@@ -389,11 +389,19 @@ def main():
         except Exception:
             traffic = None
     achieved = flops_per_launch / (dom_ms * 1e-3) * 1e-12
+    hbm_peak = None
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs"))
+    except Exception:
+        hbm_peak = 6535.7          # B200_PROFILING.md fallback (measured copy bandwidth of this pool)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic, "frac_of_nominal_40_tflops": achieved / 40.0,
                 "peak_source": "measured FP64 DMMA issue-rate microbenchmark on this pool's B200 (tools/microbench, profiles/"
                                "r01_fp64_peak_microbench.jsonl); MEASURED_PEAKS.json carries no FP64 figure; cuBLAS DGEMM reaches 35.4",
                 "algorithmic_flops_per_launch": flops_per_launch,
+                # the other roof, for context: one pass over the Y shard per launch against the measured HBM copy bandwidth
+                "algorithmic_bytes_per_launch": 8.0 * L * Mloc, "hbm_gbs": 8.0 * L * Mloc / (dom_ms * 1e-3) * 1e-9,
+                "hbm_peak_gbs": hbm_peak, "hbm_frac": (8.0 * L * Mloc / (dom_ms * 1e-3) * 1e-9 / hbm_peak) if hbm_peak else None,
                 "k1_ms": k1, "k2_ms": k2, "k1_tflops": flops_per_launch / k1 * 1e-9 if k1 else None,
                 "k2_tflops": flops_per_launch / k2 * 1e-9 if k2 else None,
                 "iteration_frac_of_peak": 4.0 * L * M * H / (ms / args.steps * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
