@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
 //   Bn = (c .* Qtile) * SigmaB [/ sigma2]        32 x HP8 x HP8 product, 4 x HP8/8 mma tiles over 8 warps
 //   G_B += Bn' Bn,  G_D += Dn' Dn                 accumulators in registers across the CTA's tiles
 template <int TPW, bool GRAM>   // Gram tiles per warp: ceil((HP8/8)^2 / 8); GRAM = false (H > 64): the Grams come from gram_dmma
-__global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_var) {
+__global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(Dev d, int diag_var) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
     __shared__ double red[32];
@@ -1025,9 +1025,17 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
     }
     const bool dense = d.kind == KIND_DENSE;
     const double s2 = sc->sigma2, sh = sc->sigmaHat;
-    double gB[GRAM ? TPW : 1][2], gD[GRAM ? TPW : 1][2];
+    constexpr int NTW = TPW == 2 ? 2 : (TPW == 8 ? 4 : 8);      // product column tiles per warp: ceil(nt8 / 2)
+    constexpr int GT = GRAM ? (TPW == 2 ? 2 : 5) : 1;           // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
+    double gB[GT][2], gD[GT][2];
+    int gt[GT];                                                 // at | bt << 8, -1 = none
 #pragma unroll
-    for (int q = 0; q < (GRAM ? TPW : 1); ++q) { gB[q][0] = gB[q][1] = 0.0; gD[q][0] = gD[q][1] = 0.0; }
+    for (int q = 0; q < GT; ++q) {
+        gB[q][0] = gB[q][1] = 0.0; gD[q][0] = gD[q][1] = 0.0;
+        int idx = warp + 8 * q, at = 0;
+        while (at < nt8 && idx >= nt8 - at) { idx -= nt8 - at; ++at; }
+        gt[q] = at < nt8 ? (at | ((at + idx) << 8)) : -1;
+    }
     double tr = 0.0;
     const int ntiles = (d.L + 31) / 32;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1043,38 +1051,52 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
             T[i * ld + h] = q;
         }
         __syncthreads();
-        for (int idx = warp; idx < 4 * nt8; idx += 8) {
-            const int mt = idx & 3, nt = idx >> 2;
-            double c2[2] = {0.0, 0.0};
-#pragma unroll 8
-            for (int k0 = 0; k0 < HP8; k0 += 4) dmma_acc(c2, T[(8 * mt + r) * ld + k0 + j], Ss[(k0 + j) * ld + 8 * nt + r]);
-            const int row = 8 * mt + r;
+        {   // warp -> row tile (warp & 3), column tiles (warp >> 2) + 2u with one independent accumulator each
+            const int mt = warp & 3, row = 8 * mt + r;
+            double c2[NTW][2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int col = 8 * nt + 2 * j + i;
-                double bn = 0.0, dn = 0.0;
-                if (row < nr && col < H) {
-                    double v = c2[i];
-                    if (dense) v /= s2;
-                    const size_t g = (size_t)col * d.ldB + l0 + row;
-                    const double old = d.B[g];
-                    d.Bold[g] = old;
-                    dn = v - old;
-                    d.D[g] = dn;
-                    d.B[g] = v;
-                    tr = fma(v, Q[g], tr);
-                    bn = v;
+            for (int u = 0; u < NTW; ++u) { c2[u][0] = 0.0; c2[u][1] = 0.0; }
+#pragma unroll 4
+            for (int k0 = 0; k0 < HP8; k0 += 4) {
+                const double af = T[row * ld + k0 + j];
+#pragma unroll
+                for (int u = 0; u < NTW; ++u) {
+                    const int nt = (warp >> 2) + 2 * u;
+                    if (nt < nt8) dmma_acc(c2[u], af, Ss[(k0 + j) * ld + 8 * nt + r]);
                 }
-                if (GRAM) { Bn[row * ld + col] = bn; Dn[row * ld + col] = dn; }
+            }
+#pragma unroll
+            for (int u = 0; u < NTW; ++u) {
+                const int nt = (warp >> 2) + 2 * u;
+                if (nt < nt8) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int col = 8 * nt + 2 * j + i;
+                        double bn = 0.0, dn = 0.0;
+                        if (row < nr && col < H) {
+                            double v = c2[u][i];
+                            if (dense) v /= s2;
+                            const size_t g = (size_t)col * d.ldB + l0 + row;
+                            const double old = d.B[g];
+                            d.Bold[g] = old;
+                            dn = v - old;
+                            d.D[g] = dn;
+                            d.B[g] = v;
+                            tr = fma(v, Q[g], tr);
+                            bn = v;
+                        }
+                        if (GRAM) { Bn[row * ld + col] = bn; Dn[row * ld + col] = dn; }
+                    }
+                }
             }
         }
         if (GRAM) {
             __syncthreads();
+            // symmetric Grams: tiles on and above the diagonal only, mirrored when the partial is written
 #pragma unroll
-            for (int q = 0; q < TPW; ++q) {
-                const int idx = warp + 8 * q;
-                if (idx < nt8 * nt8) {
-                    const int at = idx / nt8, bt = idx - at * nt8;
+            for (int q = 0; q < GT; ++q) {
+                if (gt[q] >= 0) {
+                    const int at = gt[q] & 255, bt = gt[q] >> 8;
 #pragma unroll
                     for (int i0 = 0; i0 < 32; i0 += 4) {
                         dmma_acc(gB[q], Bn[(i0 + j) * ld + 8 * at + r], Bn[(i0 + j) * ld + 8 * bt + r]);
@@ -1087,13 +1109,17 @@ __global__ void __launch_bounds__(256) B_epilogue_dmma_kernel(Dev d, int diag_va
     if (GRAM) {
         double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
 #pragma unroll
-        for (int q = 0; q < TPW; ++q) {
-            const int idx = warp + 8 * q;
-            if (idx < nt8 * nt8) {
-                const int at = idx / nt8, bt = idx - at * nt8;
-                const int a = 8 * at + r, b = 8 * bt + 2 * j;
-                if (a < H && b < H) { out[a * H + b] = gB[q][0]; out[H * H + a * H + b] = gD[q][0]; }
-                if (a < H && b + 1 < H) { out[a * H + b + 1] = gB[q][1]; out[H * H + a * H + b + 1] = gD[q][1]; }
+        for (int q = 0; q < GT; ++q) {
+            if (gt[q] >= 0) {
+                const int a = 8 * (gt[q] & 255) + r, b = 8 * (gt[q] >> 8) + 2 * j;
+                if (a < H && b < H) {
+                    out[a * H + b] = gB[q][0]; out[b * H + a] = gB[q][0];
+                    out[H * H + a * H + b] = gD[q][0]; out[H * H + b * H + a] = gD[q][0];
+                }
+                if (a < H && b + 1 < H) {
+                    out[a * H + b + 1] = gB[q][1]; out[(b + 1) * H + a] = gB[q][1];
+                    out[H * H + a * H + b + 1] = gD[q][1]; out[H * H + (b + 1) * H + a] = gD[q][1];
+                }
             }
         }
         tr = block_sum(tr, red);
