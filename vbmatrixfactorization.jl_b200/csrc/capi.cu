@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 namespace vb {
 
@@ -1195,6 +1196,18 @@ struct BatchDenseDesc {
 int k_batched_vbls_dense(cudaStream_t st, const BatchDenseDesc& bd);
 }
 
+// host-side packing / unpacking of many small problems: a few threads over disjoint problem ranges (plain memcpy work)
+template <class F> static void parallel_for(int64_t n, F&& fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), n / 64);
+    if (T <= 1) { for (int64_t p = 0; p < n; ++p) fn(p); return; }
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&fn, n, t, T] { for (int64_t p = n * t / T; p < n * (t + 1) / T; ++p) fn(p); });
+    for (auto& x : th) x.join();
+}
+
 // grow-only staging of the batched path: device arena + pinned host mirror with identical offsets
 static int batch_reserve(vbmf_b200_ctx* c, size_t total) {
     if (total <= c->batch_bytes) return 0;
@@ -1263,7 +1276,7 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     memcpy(hb + o_moff, moff.data(), (size_t)(nprob + 1) * 4);
     double *hY = (double*)(hb + o_Y), *hB = (double*)(hb + o_B), *hSB = (double*)(hb + o_SB), *hCA = (double*)(hb + o_CA), *hsc = (double*)(hb + o_sc);
     memset(hsc, 0, (size_t)nprob * 16 * 8);
-    for (int64_t p = 0; p < nprob; ++p) {
+    parallel_for(nprob, [&](int64_t p) {
         const ST* s = (const ST*)states[p];
         memcpy(&hY[(size_t)moff[p] * L], Y[p], (size_t)s->M * L * 8);
         memcpy(&hB[p * LH], s->BHat, LH * 8);
@@ -1276,7 +1289,7 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
             sc[5] = (double)std::min<int64_t>(std::max<int64_t>(s->M0, 0), s->M);
             sc[7] = s->alpha01; sc[8] = s->beta01; sc[9] = s->alpha02; sc[10] = s->beta02; sc[14] = s->alpha03; sc[15] = s->beta03;
         } else { sc[5] = s->alpha; sc[6] = s->beta0; }
-    }
+    });
     int rc = 0;
     cudaStream_t st = c->st;
     if (cudaMemcpyAsync(db, hb, up_end, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); set_error("batched vbls: upload failed"); return -1; }
@@ -1298,12 +1311,12 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     if (rc || bd.niter == 0) return rc;
     const double *hA = (const double*)(hb + o_A), *hbeta = (const double*)(hb + o_beta), *hs = (const double*)(hb + o_s), *hSA = (const double*)(hb + o_SA),
                  *hYH = (const double*)(hb + o_YH), *hblk = (const double*)(hb + o_blk);
-    bool failed = false;
-    for (int64_t p = 0; p < nprob; ++p) {
+    std::atomic<bool> failed(false);
+    parallel_for(nprob, [&](int64_t p) {
         ST* s = (ST*)states[p];
         const size_t M = (size_t)s->M, o = (size_t)moff[p] * H;
         const double* sc = &hsc[(size_t)p * 16];
-        failed = failed || sc[13] != 0.0;
+        if (sc[13] != 0.0) failed.store(true);
         if (s->ATVecHat) memcpy(s->ATVecHat, &hA[o], M * H * 8);
         if (s->AHat) for (size_t m = 0; m < M; ++m) for (size_t h = 0; h < (size_t)H; ++h) s->AHat[h * M + m] = hA[o + m * H + h];
         if (s->diagSigmaATVec) memcpy(s->diagSigmaATVec, &hs[o], M * H * 8);
@@ -1350,8 +1363,8 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
                 else { if (s->A0Hat) s->A0Hat[h * M + m] = hA[o + m * H + h]; }
             }
         }
-    }
-    if (failed) { set_error("batched vbls: a per-column precision matrix was not positive definite (NaN written)"); return -2; }
+    });
+    if (failed.load()) { set_error("batched vbls: a per-column precision matrix was not positive definite (NaN written)"); return -2; }
     return 0;
 }
 
