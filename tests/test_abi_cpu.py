@@ -79,3 +79,119 @@ def test_init_mirrors_reference(vb):
     with pytest.raises(vb.VBMFError, match="H must be at least H0"):
         vb.vbmf_dual_init(Y, 1, 2)
     assert vb.shard_columns(10, 4, 0) == (0, 3) and vb.shard_columns(10, 4, 3) == (8, 2)
+
+
+def _c_struct_fields(header, name):
+    import re
+    m = re.search(r"typedef struct \{([^}]*)\} " + name + ";", header)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        mm = re.match(r"(const\s+)?(int64_t|double)\s*(\*?)\s*(.*)", decl)
+        base, ptr, names = mm.group(2), mm.group(3), mm.group(4)
+        for n in names.split(","):
+            n = n.strip()
+            p = ptr
+            if n.startswith("*"):
+                p, n = "*", n[1:].strip()
+            out.append((n, ("Ptr" if p else "") + ("Int64" if base == "int64_t" else "Float64")))
+    return out
+
+
+def _julia_struct_fields(src, name):
+    import re
+    m = re.search(r"immutable " + name + r"\b[^\n]*\n(.*?)\nend", src, flags=re.S)
+    out = []
+    for line in m.group(1).split("\n"):
+        for decl in line.split("#")[0].split(";"):
+            decl = decl.strip()
+            if decl:
+                n, t = decl.split("::")
+                out.append((n.strip(), t.strip().replace("Ptr{Int64}", "PtrInt64").replace("Ptr{Float64}", "PtrFloat64")))
+    return out
+
+
+def _call_arity(src, callee):
+    """Number of top-level arguments of every `callee(` call in src."""
+    out, i = [], 0
+    while True:
+        i = src.find(callee + "(", i)
+        if i < 0:
+            return out
+        j, depth, n, seen = i + len(callee) + 1, 1, 0, False
+        while depth:
+            ch = src[j]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                n += 1
+            if not ch.isspace() and depth:
+                seen = True
+            j += 1
+        out.append(n + 1 if seen else 0)
+        i = j
+
+
+def test_julia_shim_mirrors_the_header():
+    """julia/VBMatrixFactorizationB200.jl cannot be executed here (no Julia): at least its four `immutable` struct mirrors must
+    match include/vbmf_b200.h field for field (name, order, pointer-ness, integer/float), and every constructor call must pass
+    exactly one value per field."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "vbmf_b200.h")).read()
+    shim = open(os.path.join(root, "julia", "VBMatrixFactorizationB200.jl")).read()
+    for cname, jname in (("vbmf_b200_dense_state", "DenseState"), ("vbmf_b200_sparse_state", "SparseState"),
+                         ("vbmf_b200_dual_state", "DualState"), ("vbmf_b200_trial_state", "TrialState")):
+        c, j = _c_struct_fields(header, cname), _julia_struct_fields(shim, jname)
+        assert c == j, (cname, [(a, b) for a, b in zip(c, j) if a != b])
+        body = shim.split("immutable " + jname, 1)[1].split("\nend", 1)[1]       # everything after the type definition
+        calls = [n for n in _call_arity(body, jname) if n > 1]                      # skip Ref{T}-style mentions
+        assert calls and all(n == len(c) for n in calls), (jname, calls, len(c))
+    # every C symbol the shim ccalls is declared in the header
+    import re
+    for sym in set(re.findall(r"ccall\(\(:(\w+), LIB\)", shim)):
+        assert re.search(r"\b" + sym + r"\s*\(", header), sym
+
+
+def test_julia_shim_ccall_arities_match_prototypes():
+    """Every `ccall((:sym, LIB), Cint, (types...), args...)` in the shim passes as many types and as many arguments as the C
+    prototype of `sym` in include/vbmf_b200.h has parameters."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "vbmf_b200.h")).read(), flags=re.S)
+    shim = open(os.path.join(root, "julia", "VBMatrixFactorizationB200.jl")).read()
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*|void)\s+(vbmf_b200_\w+)\s*\(([^)]*)\)\s*;", hdr):
+        a = m.group(2).strip()
+        protos[m.group(1)] = 0 if a in ("", "void") else len(a.split(","))
+
+    def split_top(s):
+        out, depth, cur = [], 0, ""
+        for ch in s:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 0:
+                out.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        return out + ([cur] if cur.strip() else [])
+    i, n = 0, 0
+    while True:
+        i = shim.find("ccall((:", i)
+        if i < 0:
+            break
+        j, depth = i + 6, 1
+        while depth:
+            depth += shim[j] in "([{"
+            depth -= shim[j] in ")]}"
+            j += 1
+        parts = split_top(shim[i + 6:j - 1])
+        sym = re.search(r":(\w+)", parts[0]).group(1)
+        types = [t for t in split_top(parts[2].strip()[1:-1]) if t.strip()]
+        assert protos.get(sym) == len(types) == len(parts) - 3, (sym, protos.get(sym), len(types), len(parts) - 3)
+        i, n = j, n + 1
+    assert n >= 15
