@@ -26,6 +26,11 @@ def test_header_symbols_exported(vb):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(vb._lib.SYMBOLS), declared ^ set(vb._lib.SYMBOLS)
+    # the ctypes prototypes carry one argtype per C parameter
+    plain = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*|void)\s+(vbmf_b200_\w+)\s*\(([^)]*)\)\s*;", plain):
+        a = m.group(2).strip()
+        assert len(vb._lib.SYMBOLS[m.group(1)][1]) == (0 if a in ("", "void") else len(a.split(","))), m.group(1)
 
 
 def test_struct_sizes_match_header(vb):
