@@ -727,3 +727,32 @@ def test_two_contexts_concurrently(G):
         else:
             vo.vbmf_run(Y, po, 8, eps=0.0, est_covs=True, est_var=True)
             G.compare(outs[k], po, 1e-8, ["AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB", "sigma2"])
+
+
+def test_checkpoint_resume(G, ctx, tmp_path):
+    """SURVEY section 5, checkpoint / resume: the parameter struct IS the state.  (a) 4 + 6 iterations in two calls give what 10
+    iterations in one call give (every field round-trips through the ABI; not bit for bit: on re-entry B'B is recomputed by the
+    stand-alone Gram kernel, whose fixed summation order differs from the B epilogue's); (b) a state rebuilt from iteration 37 of a
+    saved log (load_log + extract_params!, src/data_manip.jl:74-118) and continued for 63 iterations lands on the log's last entry."""
+    Y = synth(60, 700, 4, seed=3)
+    Yf = np.asfortranarray(Y)
+    p = vo.vbmf_dual_init(Y, 8, 5, rng=np.random.default_rng(4))
+    one, two = G.to_gpu_params(p), G.to_gpu_params(p)
+    G.vb.vbmf_dual_(Yf, one, 10, eps=0.0, full_cov=True, ctx=ctx, yhat=False)
+    G.vb.vbmf_dual_(Yf, two, 4, eps=0.0, full_cov=True, ctx=ctx, yhat=False)
+    G.vb.vbmf_dual_(Yf, two, 6, eps=0.0, full_cov=True, ctx=ctx, yhat=False)
+    for f in ("AHat", "BHat", "SigmaA", "SigmaB", "CA", "beta", "CB", "delta", "diagSigmaATVec"):
+        assert G.rel(getattr(two, f), getattr(one, f)) < TOL, f
+    for f in ("sigmaHat", "zeta", "alpha00", "alpha01", "beta00", "beta01"):
+        assert abs(getattr(one, f) - getattr(two, f)) <= TOL * abs(getattr(one, f)), f
+    g = load_golden("vbmf_test")
+    Yg, pg = dense_state_from_golden(g)
+    q = G.to_gpu_params(pg)
+    G.vb.vbmf_(np.asfortranarray(Yg), q, 100, eps=0.0, est_covs=True, est_var=True, ctx=ctx, logdir=str(tmp_path), desc="ck")
+    log, _ = G.vb.load_log(str(tmp_path / "ck"))
+    r = G.to_gpu_params(pg)
+    G.vb.extract_params_(log, r, 37)
+    G.vb.vbmf_(np.asfortranarray(Yg), r, 63, eps=0.0, est_covs=True, est_var=True, ctx=ctx, yhat=False)
+    for f in ("AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB"):
+        assert G.rel(getattr(r, f), log[f][..., 100]) < TOL, f
+    assert abs(r.sigma2 - log["sigma2"][100]) <= TOL * abs(log["sigma2"][100])
