@@ -279,6 +279,44 @@ def dual_updateCA(p):
     p["alpha"] = [p["alpha0"], p["alpha1"]]
 
 
+def dual_lowerBound(Y, p):
+    """src/vbmf_dual.jl:556-599, term by term (two CA groups), with the literal (LH)x(LH) Kronecker determinant."""
+    L, M, H, H0, MH = p["L"], p["M"], p["H"], p["H0"], p["MH"]
+    H1 = H - H0
+    A, B = p["AHat"], p["BHat"]
+    GB = B.T * B + L * p["SigmaB"]
+    e0 = mp.fsum(gammaELn(p["alpha0"], b) for b in p["beta0"])
+    e1 = mp.fsum(gammaELn(p["alpha1"], b) for b in p["beta1"])
+    ed = mp.fsum(gammaELn(p["gamma"], d) for d in p["delta"])
+    Lb = mp.mpf(0)
+    Lb += -mp.mpf(L * M) / 2 * LN2PI + mp.mpf(L * M) / 2 * gammaELn(p["eta"], p["zeta"])
+    Lb += -p["sigmaHat"] / 2 * (p["trYTY"] - 2 * trace_xty(B, Y * A) + trace_xty(A.T * A + p["SigmaA"], GB))
+    Lb += -mp.mpf(MH) / 2 * LN2PI + e0 / 2
+    Lb += e1 / 2
+    Lb += -mp.fsum(p["CA"][i] * (p["ATVecHat"][i] ** 2 + p["diagSigmaATVec"][i]) for i in range(len(p["CA"]))) / 2
+    Lb += -mp.mpf(L * H) / 2 * LN2PI
+    Lb += mp.mpf(L) / 2 * ed
+    Lb += -trace_xty(diagm(p["CB"]), GB) / 2
+    Lb += p["eta0"] * mp.log(p["zeta0"]) - mp.loggamma(p["eta0"])
+    Lb += (p["eta0"] - 1) * gammaELn(p["eta"], p["zeta"]) - p["zeta0"] * p["sigmaHat"]
+    Lb += M * H0 * (p["alpha00"] * mp.log(p["beta00"]) - mp.loggamma(p["alpha00"]))
+    Lb += (p["alpha00"] - 1) * e0
+    Lb += -p["beta00"] * mp.fsum(p["CA0"])
+    Lb += M * H1 * (p["alpha01"] * mp.log(p["beta01"]) - mp.loggamma(p["alpha01"]))
+    Lb += (p["alpha01"] - 1) * e1
+    Lb += -p["beta01"] * mp.fsum(p["CA1"])
+    Lb += H * (p["gamma0"] * mp.log(p["delta0"]) - mp.loggamma(p["gamma0"]))
+    Lb += (p["gamma0"] - 1) * ed
+    Lb += -p["gamma0"] * mp.fsum(p["CB"])
+    Lb += normalEntropy_diag(p["diagSigmaATVec"])
+    Lb += normalEntropy_mat(kron(p["SigmaB"], eye(L)))
+    Lb += gammaEntropy(p["eta"], p["zeta"])
+    Lb += mp.fsum(gammaEntropy(p["alpha0"], b) for b in p["beta0"])
+    Lb += mp.fsum(gammaEntropy(p["alpha1"], b) for b in p["beta1"])
+    Lb += mp.fsum(gammaEntropy(p["gamma"], d) for d in p["delta"])
+    return Lb
+
+
 def _root(f, a=mp.mpf("1e-10"), b=mp.mpf("1e10")):
     """Exact root of a monotone f on [a, b] (what a bracketing solver run to floating-point resolution returns, to within
     one ulp); None when there is no sign change - the reference's `try ... end` then keeps the old value."""

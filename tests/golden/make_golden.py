@@ -110,6 +110,9 @@ def read_jld(path):
 
 
 def main():
+    global OUT
+    if "--out" in sys.argv:          # write somewhere else (tests/test_oracle_mp.py re-derives the fixtures and compares)
+        OUT = sys.argv[sys.argv.index("--out") + 1]
     for case in ("vbmf_test", "sparse_test"):
         inputs = read_jld(os.path.join(REF, case, "inputs.jld"))
         log = read_jld(os.path.join(REF, case, "log.jld"))
