@@ -199,6 +199,11 @@ int vbmf_b200_trYTY(vbmf_b200_ctx* ctx, double* out);          /* traceXTY(Y, Y)
 int vbmf_b200_ctx_sync(vbmf_b200_ctx* ctx);
 /* instrumentation for bench.py: kernel launches issued so far; CUDA-event time of the K1/K2 launches when profiling is on */
 int64_t vbmf_b200_launch_count(void);
+/* Host-side work decomposition of the two contractions for an L x M_local shard and rank H on a GPU with num_sms SMs (pure
+ * host logic, needs no device): out[0] = K1 split count over L, out[1] = 16-row k-blocks per K1 split, out[2] = K2 split
+ * count over M_local, out[3] = columns per K2 split (multiple of 16), out[4] = CTAs per SM, out[5] = tile width BN.
+ * (none in the reference: src/vbmf.jl:98,112 are single BLAS calls) */
+int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_sms, int64_t* out6);
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
 

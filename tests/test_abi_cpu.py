@@ -200,3 +200,31 @@ def test_julia_shim_ccall_arities_match_prototypes():
         assert protos.get(sym) == len(types) == len(parts) - 3, (sym, protos.get(sym), len(types), len(parts) - 3)
         i, n = j, n + 1
     assert n >= 15
+
+
+def test_contraction_planner_host_logic(vb):
+    """Split-K plans of K1 / K2 (host logic, no device needed): every slab is non-empty, the slabs cover L resp. M exactly once,
+    K2 chunks are multiples of the 16-row stage, and at the BASELINE shapes the static work list fills >= 95 % of its last wave."""
+    import ctypes as C
+    lib = vb._lib.load()
+    out = (C.c_int64 * 6)()
+
+    def plan(L, M, H, sms=148):
+        assert lib.vbmf_b200_plan_contractions(L, M, H, sms, C.cast(out, C.c_void_p)) == 0
+        return list(out)
+    rng = np.random.default_rng(0)
+    shapes = [(20000, 200000, 64), (20000, 25000, 64), (10000, 100000, 32), (50000, 125000, 128), (10, 20, 2), (1, 1, 1), (38, 40, 20)]
+    shapes += [(int(rng.integers(1, 60000)), int(rng.integers(1, 300000)), int(rng.integers(1, 129))) for _ in range(300)]
+    for L, M, H in shapes:
+        S1, kbs, S2, kchunk, cps, bn = plan(L, M, H)
+        nkb = -(-L // 16)
+        assert bn in (32, 64, 128) and bn >= H and (bn == 32 or bn // 2 < H)
+        assert S1 >= 1 and kbs >= 1 and S1 * kbs >= nkb and (S1 - 1) * kbs < nkb, (L, M, H, S1, kbs)
+        assert S2 >= 1 and kchunk % 16 == 0 and S2 * kchunk >= M and (S2 - 1) * kchunk < M, (L, M, H, S2, kchunk)
+        assert S2 * H * ((L + 1) & ~1) * 8 <= (1 << 30) or S2 == 1          # K2 slab workspace cap
+    for L, M, H in shapes[:4]:
+        S1, kbs, S2, kchunk, cps, bn = plan(L, M, H)
+        cap = 148 * cps
+        for work in (-(-M // 128) * S1, -(-L // 128) * S2):
+            assert work / (-(-work // cap) * cap) >= 0.95, (L, M, H, work, cap)
+    assert lib.vbmf_b200_plan_contractions(10, 10, 129, 148, C.cast(out, C.c_void_p)) != 0      # H > 128 is refused

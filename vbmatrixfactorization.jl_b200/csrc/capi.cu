@@ -109,6 +109,17 @@ static int ctx_allreduce(vbmf_b200_ctx* c, double* buf, size_t n) {
 extern "C" int vbmf_b200_version(void) { return 100; }
 extern "C" const char* vbmf_b200_last_error(void) { return g_err; }
 extern "C" int64_t vbmf_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_sms, int64_t* out6) {
+    if (!out6 || L < 1 || M_local < 0 || H < 1 || H > 128 || num_sms < 1 || L > 0x7fffff00LL || M_local > 0x7fffff00LL) {
+        set_error("plan_contractions: bad argument"); return -1;
+    }
+    int S1 = 1, kbs = 1, S2 = 1, kchunk = 16;
+    plan_splitk_ytb((int)L, (int)M_local, (int)H, num_sms, &S1, &kbs);
+    plan_splitk((int)L, (int)M_local, (int)H, num_sms, &S2, &kchunk);
+    const GemmGeometry g = gemm_geometry((int)H);
+    out6[0] = S1; out6[1] = kbs; out6[2] = S2; out6[3] = kchunk; out6[4] = g.ctas_per_sm; out6[5] = g.bn;
+    return 0;
+}
 extern "C" int vbmf_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
