@@ -161,7 +161,10 @@ def run_reference(args, L, M, H, kind, flags, desc):
             "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, kind),
             "value": cb["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "parallelism": "host cores only"},
+            "data": "synthetic", "extrapolated": True,
+            "config": {"workload": desc, "parallelism": "host cores only",
+                       "sample": "timed on L=%d x M_s columns (M_s << M=%d, see cpu_baseline.sample) and scaled by M_s/M: one iteration is "
+                                 "linear in M; the full-size CPU iteration would take ~%.0f s" % (L, M, 1.0 / cb["value"])},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -376,6 +379,25 @@ def main():
     ms = float(tms.item())
     value = args.steps / (ms * 1e-3)
 
+    # ---- state_check: shard-invariant scalars of the state after warm-up + K iterations.  Runs at N = 1/2/4/8 start from the
+    # same global initialisation, so these must agree across N to ~1e-10 (driver-visible sharded parity).
+    solver.download(p)
+    a2 = torch.tensor([float(np.sum(np.asarray(p.AHat) ** 2))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(a2, op=dist.ReduceOp.SUM)
+    state_check = {"iterations": args.warmup + args.steps, "norm_BHat_fro": float(np.linalg.norm(p.BHat)),
+                   "norm_AHat_fro": float(np.sqrt(a2.item())), "trace_SigmaB": float(np.trace(p.SigmaB)),
+                   "trace_SigmaA": float(np.trace(p.SigmaA)),
+                   "noise": float(p.sigma2) if kind == "dense" else float(p.sigmaHat), "delta": float(d)}
+    if kind != "dense":
+        ca = torch.tensor([float(np.sum(p.CA))], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ca, op=dist.ReduceOp.SUM)
+        state_check["sum_CA"] = float(ca.item())
+        state_check["sum_CB"] = float(np.sum(p.CB))
+    if kind == "dual":
+        state_check.update({"alpha00": float(p.alpha00), "beta00": float(p.beta00), "alpha01": float(p.alpha01), "beta01": float(p.beta01)})
+
     # ---- roofline of the dominant kernel (the slower of the two contractions), CUDA events on the launching stream
     k1 = prof["k1_ms"] / max(prof["k1_launches"], 1)
     k2 = prof["k2_ms"] / max(prof["k2_launches"], 1)
@@ -466,7 +488,7 @@ def main():
                    "NCCL all-reduce per iteration" % world if world > 1 else "single GPU", "l2": "inputs larger than L2 (Y shard %.1f GB), no flush"
                    % (L * Mloc * 8 / 1e9), "norm": "spectral", "eps": 0.0},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "final_delta": d,
+        "final_delta": d, "state_check": state_check,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

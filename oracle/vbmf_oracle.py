@@ -52,9 +52,15 @@ class ContractedY:
     sum(Y.^2)) are supplied as callables, every other line of the update loop still runs in this oracle.  Used by the
     full-size GPU tests, where the contractions themselves are validated through size-independent properties."""
 
+    __array_ufunc__ = None            # ndarray @ ContractedY defers to __rmatmul__ below
+
     def __init__(self, shape, ytb, ya, trYTY):
         self.shape = tuple(shape)
         self._ytb, self._ya, self._tr = ytb, ya, float(trYTY)
+
+    def __rmatmul__(self, Bt):
+        """B' * Y (H x M), the form src/vbmf_sparse.jl:195,232 uses: (Y' * B)'."""
+        return np.asarray(self._ytb(np.ascontiguousarray(np.asarray(Bt).T))).T
 
     class _T:
         def __init__(self, outer):
@@ -116,6 +122,8 @@ def preprocess(Y, lam):
 
 def traceXTY(X, Y):
     """src/util.jl:104-106."""
+    if X is Y and hasattr(X, "norm2"):      # traceXTY(Y, Y) of a ContractedY
+        return float(X.norm2())
     return float(np.sum(X * Y))
 
 
@@ -269,7 +277,7 @@ def dense_updateYHat(p):
     p.YHat = p.BHat @ p.AHat.T
 
 
-def vbmf_run(Y, p, niter, eps=1e-6, est_covs=False, est_var=False, norm="spectral", trace=None):
+def vbmf_run(Y, p, niter, eps=1e-6, est_covs=False, est_var=False, norm="spectral", trace=None, yhat=True):
     """`vbmf!` src/vbmf.jl:175-231.  Returns (params, iterations_done, d).  trace(p, i) is called once per iteration."""
     old = p.BHat
     d = eps + 1.0
@@ -287,7 +295,8 @@ def vbmf_run(Y, p, niter, eps=1e-6, est_covs=False, est_var=False, norm="spectra
         d = delta(p.BHat, old, norm)
         old = p.BHat
         i += 1
-    dense_updateYHat(p)
+    if yhat:        # the L x M product is skipped by the full-size tests
+        dense_updateYHat(p)
     return p, i - 1, d
 
 
@@ -449,7 +458,7 @@ def sparse_updateYHat(p):
     p.YHat = p.BHat @ p.AHat.T
 
 
-def vbmf_sparse_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_cb=True, norm="spectral", trace=None):
+def vbmf_sparse_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_cb=True, norm="spectral", trace=None, yhat=True):
     """`vbmf_sparse!` src/vbmf_sparse.jl:344-410.  Returns (d, iterations_done)."""
     old = p.BHat.copy()
     d = eps + 1.0
@@ -466,7 +475,8 @@ def vbmf_sparse_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_c
         d = delta(p.BHat, old, norm)
         old = p.BHat.copy()
         i += 1
-    sparse_updateYHat(p)
+    if yhat:        # the L x M product is skipped by the full-size tests
+        sparse_updateYHat(p)
     return d, i - 1
 
 
@@ -684,7 +694,7 @@ def dual_updateBeta01(p):
 
 
 def vbmf_dual_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_priors=True, est_cb=True,
-                  norm="spectral", trace=None):
+                  norm="spectral", trace=None, yhat=True):
     """`vbmf_dual!` src/vbmf_dual.jl:455-530.  Returns (d, iterations_done)."""
     old = p.BHat.copy()
     d = eps + 1.0
@@ -706,7 +716,8 @@ def vbmf_dual_run(Y, p, niter, eps=1e-6, diag_var=False, full_cov=False, est_pri
         d = delta(p.BHat, old, norm)
         old = p.BHat.copy()
         i += 1
-    dual_updateYHat(p)
+    if yhat:        # the L x M product is skipped by the full-size tests
+        dual_updateYHat(p)
     return d, i - 1
 
 

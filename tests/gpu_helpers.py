@@ -82,9 +82,22 @@ FIELDS = {
 }
 
 
+# measured worst relative error per test (filled by compare, written to gpurun_out/parity_worst.json by tests/conftest.py)
+WORST = {}
+CURRENT = [""]
+
+
+def record(name, err):
+    d = WORST.setdefault(CURRENT[0], {})
+    if not (d.get(name, -1.0) >= err):
+        d[name] = float(err)
+
+
 def compare(q, p, tol, fields=None):
     """max relative error per field between GPU params q and oracle params p; asserts all <= tol."""
     errs = {f: rel(getattr(q, f), getattr(p, f)) for f in (fields or FIELDS[p.kind])}
+    for f, e in errs.items():
+        record(f, e)
     bad = {f: e for f, e in errs.items() if not e <= tol}
     assert not bad, "fields above %.1e: %s (all: %s)" % (tol, bad, errs)
     return errs

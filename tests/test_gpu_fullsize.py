@@ -1,5 +1,6 @@
-"""Parity at BASELINE.json's full single-GPU size (configs[2]: 20000 x 200000, H = 64) where the CPU oracle cannot form the
-two contractions in reasonable time:
+"""Parity at BASELINE.json's full single-GPU sizes -- configs[2] dense 20000 x 200000 x 64, configs[3] vbmf_sparse
+10000 x 100000 x 32 (diagonal and full covariance) and the per-GPU slice of configs[4], vbmf_dual 50000 x 125000 x 128 with
+est_priors -- where the CPU oracle cannot form the two contractions in reasonable time:
 
   * the contractions are checked through size-independent properties (linearity in the small operand, the checksum of
     checksums sum(P .* A) == sum(Q .* B) == tr(A' Y' B), agreement of sum(Y.^2) with tr of a contraction against e_h);
@@ -58,9 +59,84 @@ def test_dense_loop_fullsize_per_iteration(G, ctx):
         s.download(q)
         s.close()
         old = po.BHat.copy()
-        vo.vbmf_run(Yc, po, 1, eps=0.0, est_covs=True, est_var=True)
+        vo.vbmf_run(Yc, po, 1, eps=0.0, est_covs=True, est_var=True, yhat=False)
         assert n == 1
         G.compare(q, po, 1e-10)
         d_o = vo.delta(po.BHat, old)
         # d = ||B - Bold|| / ||Bold||: a 1e-10 relative error on BHat is a 1e-10 ABSOLUTE error on d
         assert abs(d - d_o) <= 1e-9 + 1e-8 * d_o, (d, d_o)
+
+
+# ------------------------------------------------------------------------------------------------ configs[3] and configs[4]
+def _teacher_forced(G, c, Yc, po, run_oracle, flags, iters=3):
+    """One GPU iteration from the oracle's state of every iteration (north_star: <= 1e-10 per iteration on every field)."""
+    worst = 0.0
+    for it in range(iters):
+        q = G.to_gpu_params(po)
+        s = G.vb.Solver(c, q)
+        s.upload(q)
+        n, d = s.run(1, eps=0.0, flags=flags)
+        s.download(q)
+        s.close()
+        old = po.BHat.copy()
+        run_oracle(po)
+        assert n == 1 and not s.failed
+        errs = G.compare(q, po, 1e-10)
+        worst = max(worst, max(errs.values()))
+        d_o = vo.delta(po.BHat, old)
+        G.record("delta_abs", abs(d - d_o))
+        assert abs(d - d_o) <= 1e-9 + 1e-8 * d_o, (d, d_o)
+    return worst
+
+
+@pytest.fixture(scope="module")
+def ctx4(G):
+    c = G.vb.Context(device=0)
+    c.synth(10000, 100000, rank=16, noise=0.1, seed=20260101)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("full_cov", [False, True])
+def test_sparse_loop_config4_per_iteration(G, ctx4, full_cov):
+    """configs[3]: vbmf_sparse 10000 x 100000 x 32 (src/vbmf_sparse.jl:176-323): diagonal (Q2-Q4) and full covariance (1e5
+    32 x 32 inverses per iteration), est_cb, homoscedastic noise."""
+    Lc, Mc, Hc = 10000, 100000, 32
+    Yc = vo.ContractedY((Lc, Mc), ctx4.gemm_YtB, ctx4.gemm_YA, ctx4.trYTY())
+    po = vo.vbmf_sparse_init(Yc, Hc, rng=np.random.default_rng(2))
+    flags = G.vb._lib.EST_CB | (G.vb._lib.FULL_COV if full_cov else 0)
+    _teacher_forced(G, ctx4, Yc, po, lambda p: vo.vbmf_sparse_run(Yc, p, 1, eps=0.0, full_cov=full_cov, est_cb=True, yhat=False), flags)
+
+
+def test_contraction_properties_config4(G, ctx4):
+    rng = np.random.default_rng(4)
+    Lc, Mc, Hc = 10000, 100000, 32
+    B1, B2, A1 = rng.standard_normal((Lc, Hc)), rng.standard_normal((Lc, Hc)), rng.standard_normal((Mc, Hc))
+    P1, P2, P12 = ctx4.gemm_YtB(B1), ctx4.gemm_YtB(B2), ctx4.gemm_YtB(B1 - 3.0 * B2)
+    assert G.rel(P12, P1 - 3.0 * P2) < 1e-12
+    Q1 = ctx4.gemm_YA(A1)
+    assert abs(np.sum(P1 * A1) - np.sum(Q1 * B1)) <= 1e-11 * abs(np.sum(Q1 * B1))
+    assert np.array_equal(ctx4.gemm_YtB(B1), P1) and np.array_equal(ctx4.gemm_YA(A1), Q1)
+
+
+def test_dual_loop_config5_slice_per_iteration(G):
+    """The per-GPU slice of configs[4]: vbmf_dual 50000 x 125000 x 128, H0 = 64, diagonal covariance, est_priors, est_cb
+    (src/vbmf_dual.jl:216-434, 480-513): contraction properties + three teacher-forced iterations incl. the hyper-prior roots."""
+    import torch
+    if torch.cuda.mem_get_info(0)[0] < 70 * 2**30:
+        pytest.skip("needs ~60 GB of free device memory")
+    Lc, Mc, Hc = 50000, 125000, 128
+    c = G.vb.Context(device=0)
+    try:
+        c.synth(Lc, Mc, rank=64, noise=0.1, seed=20260101)
+        rng = np.random.default_rng(5)
+        B1, A1 = rng.standard_normal((Lc, Hc)), rng.standard_normal((Mc, Hc))
+        P1, Q1 = c.gemm_YtB(B1), c.gemm_YA(A1)
+        assert abs(np.sum(P1 * A1) - np.sum(Q1 * B1)) <= 1e-11 * abs(np.sum(Q1 * B1))
+        assert G.rel(c.gemm_YtB(2.0 * B1), 2.0 * P1) < 1e-13
+        Yc = vo.ContractedY((Lc, Mc), c.gemm_YtB, c.gemm_YA, c.trYTY())
+        po = vo.vbmf_dual_init(Yc, Hc, 64, rng=np.random.default_rng(3))
+        flags = G.vb._lib.EST_CB | G.vb._lib.EST_PRIORS
+        _teacher_forced(G, c, Yc, po, lambda p: vo.vbmf_dual_run(Yc, p, 1, eps=0.0, est_priors=True, est_cb=True, yhat=False), flags)
+    finally:
+        c.close()

@@ -1,0 +1,165 @@
+"""Lane-level emulation (NumPy) of the warp-resident blocked Gauss-Jordan inverse used by K4 / the H x H inverses:
+verifies the index algebra of the DMMA fragment layouts before any GPU time is spent.  Test infrastructure only.
+
+DMMA m8n8k4 (mma.sync.aligned.m8n8k4.row.col.f64): lane = 4*r + j
+  A fragment: lane holds A[r][j]            (8 x 4)
+  B fragment: lane holds B[j][r]            (4 x 8)
+  C fragment: lane holds C[r][2j], C[r][2j+1]
+"""
+import numpy as np
+
+R = np.arange(32) >> 2
+J = np.arange(32) & 3
+
+
+def dmma(c, a, b):
+    """c: (32, 2) accumulator fragment, a: (32,) A fragment, b: (32,) B fragment -> c += A * B."""
+    A = np.zeros((8, 4)); B = np.zeros((4, 8))
+    A[R, J] = a
+    B[J, R] = b
+    C = A @ B
+    out = c.copy()
+    out[:, 0] += C[R, 2 * J]
+    out[:, 1] += C[R, 2 * J + 1]
+    return out
+
+
+def warp_block_gj(S, NT):
+    """S: (8NT, 8NT) SPD (already equilibrated).  Returns -inv(S) computed with the per-warp algorithm (NT <= 4)."""
+    N = 8 * NT
+    lane = np.arange(32)
+    # tiles in C layout
+    c = np.zeros((NT, NT, 32, 2))
+    for ti in range(NT):
+        for tj in range(NT):
+            c[ti, tj, :, 0] = S[8 * ti + R, 8 * tj + 2 * J]
+            c[ti, tj, :, 1] = S[8 * ti + R, 8 * tj + 2 * J + 1]
+    Ps = np.zeros(N * 4); Ws = np.zeros(N * 4)
+    for s in range(2 * NT):
+        tk, half = s >> 1, s & 1
+        # (1) publish the column panel from C layout
+        for t in range(NT):
+            for l in range(32):
+                if (J[l] >> 1) == half:
+                    Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 0] = c[t, tk, l, 0]
+                    Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 1] = c[t, tk, l, 1]
+        # (2) lane = row
+        X = np.zeros((32, 4))
+        for l in range(min(N, 32)):
+            X[l] = Ps[l * 4:l * 4 + 4]
+        # (3) four sweeps restricted to the panel
+        for cc in range(4):
+            kc = 4 * s + cc
+            pr = X[kc].copy()              # shuffle broadcast from lane kc
+            idv = 1.0 / pr[cc]
+            for l in range(min(N, 32)):
+                f = (1.0 - idv) if l == kc else X[l, cc] * idv
+                for q in range(4):
+                    if q != cc:
+                        X[l, q] = X[l, q] - f * pr[q]
+                X[l, cc] = -idv if l == kc else f
+        # (4)/(5) publish -W' (W' = X + I on the pivot entries) and P' = P - I on the pivot entries
+        for l in range(min(N, 32)):
+            w = X[l].copy()
+            if (l >> 2) == s:
+                w[l & 3] += 1.0
+                Ps[l * 4 + (l & 3)] -= 1.0
+            Ws[l * 4:l * 4 + 4] = -w
+        # (6) fragments
+        pf = np.zeros((NT, 32)); wf = np.zeros((NT, 32))
+        for t in range(NT):
+            pf[t] = Ps[(8 * t + R) * 4 + J]
+            wf[t] = Ws[(8 * t + R) * 4 + J]
+        # (7) rank-4 update of every tile
+        for ti in range(NT):
+            for tj in range(NT):
+                c[ti, tj] = dmma(c[ti, tj], wf[ti], pf[tj])
+        # (8) -2 on the diagonal of the pivot block
+        for l in range(32):
+            r = R[l]
+            if (r >> 2) == half and J[l] == (r >> 1) & 3 and ((r >> 1) == J[l]):
+                c[tk, tk, l, r & 1] -= 2.0
+    out = np.zeros((N, N))
+    for ti in range(NT):
+        for tj in range(NT):
+            out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
+            out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
+    return out
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(0)
+    for NT in (1, 2, 3, 4):
+        N = 8 * NT
+        Bm = rng.standard_normal((N + 5, N))
+        S = Bm.T @ Bm + np.diag(rng.uniform(0.1, 1e4, N))
+        sc = 1.0 / np.sqrt(np.diag(S))
+        Se = S * sc[:, None] * sc[None, :]
+        Minv = -warp_block_gj(Se, NT) * sc[:, None] * sc[None, :]
+        ref = np.linalg.inv(S)
+        print(NT, np.max(np.abs(Minv - ref)) / np.max(np.abs(ref)), np.linalg.cond(Se))
+
+
+def warp_block_gj_sym(S, v, NT):
+    """Symmetric storage (tiles ti <= tj only) + the right-hand side v riding along in lane = row layout.
+    Returns (-inv(S) assembled from the upper tiles, inv(S) @ v)."""
+    N = 8 * NT
+    c = np.zeros((NT, NT, 32, 2))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            c[ti, tj, :, 0] = S[8 * ti + R, 8 * tj + 2 * J]
+            c[ti, tj, :, 1] = S[8 * ti + R, 8 * tj + 2 * J + 1]
+    Ps = np.zeros(N * 4); Ws = np.zeros(N * 4)
+    vv = np.zeros(32); vv[:N] = v
+    for s in range(2 * NT):
+        tk, half = s >> 1, s & 1
+        for t in range(NT):
+            for l in range(32):
+                if t <= tk:
+                    if (J[l] >> 1) == half:          # column access into T[t][tk]
+                        Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 0] = c[t, tk, l, 0]
+                        Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 1] = c[t, tk, l, 1]
+                else:
+                    if (R[l] >> 2) == half:          # row access into T[tk][t] (symmetry)
+                        Ps[(8 * t + 2 * J[l] + 0) * 4 + (R[l] & 3)] = c[tk, t, l, 0]
+                        Ps[(8 * t + 2 * J[l] + 1) * 4 + (R[l] & 3)] = c[tk, t, l, 1]
+        X = np.zeros((32, 4))
+        for l in range(N):
+            X[l] = Ps[l * 4:l * 4 + 4]
+        for cc in range(4):
+            kc = 4 * s + cc
+            pr = X[kc].copy(); prv = vv[kc]
+            idv = 1.0 / pr[cc]
+            for l in range(N):
+                f = (1.0 - idv) if l == kc else X[l, cc] * idv
+                for q in range(4):
+                    if q != cc:
+                        X[l, q] = X[l, q] - f * pr[q]
+                vv[l] = vv[l] - f * prv
+                X[l, cc] = -idv if l == kc else f
+        for l in range(N):
+            w = X[l].copy()
+            if (l >> 2) == s:
+                w[l & 3] += 1.0
+                Ps[l * 4 + (l & 3)] -= 1.0
+            Ws[l * 4:l * 4 + 4] = -w
+        pf = np.zeros((NT, 32)); wf = np.zeros((NT, 32))
+        for t in range(NT):
+            pf[t] = Ps[(8 * t + R) * 4 + J]
+            wf[t] = Ws[(8 * t + R) * 4 + J]
+        for ti in range(NT):
+            for tj in range(ti, NT):
+                c[ti, tj] = dmma(c[ti, tj], wf[ti], pf[tj])
+        for l in range(32):
+            r = R[l]
+            if (r >> 2) == half and J[l] == (r >> 1):
+                c[tk, tk, l, r & 1] -= 2.0
+    out = np.zeros((N, N))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
+            out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
+            if tj > ti:
+                out[8 * tj + 2 * J, 8 * ti + R] = c[ti, tj, :, 0]
+                out[8 * tj + 2 * J + 1, 8 * ti + R] = c[ti, tj, :, 1]
+    return out, vv[:N]

@@ -27,7 +27,7 @@ __all__ = [
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
     "updateAlpha00_", "updateAlpha01_", "updateBeta00_", "updateBeta01_", "lowerBound", "lowerBoundTrimmed", "copy",
-    "vbls_", "vbls_batched_", "BatchedVbls", "preprocess", "create_log", "update_log_", "save_log", "load_log", "extract_params_", "VBMFError",
+    "vbls_", "vbls_batched_", "BatchedVbls", "preprocess", "VBMFWarning", "create_log", "update_log_", "save_log", "load_log", "extract_params_", "VBMFError",
 ]
 
 VBMFError = L_.VBMFError
@@ -85,24 +85,18 @@ class Context:
         except Exception:
             pass
 
-    @staticmethod
-    def _fingerprint(Y):
-        flat = Y.ravel(order="K")
-        step = max(1, flat.size // 4096)
-        return (Y.ctypes.data, Y.shape, float(flat[::step].sum()), float(flat[-1]) if flat.size else 0.0)
-
-    def attach(self, Y, M_global=None, col_offset=0, force=False):
-        """Upload this rank's L x M_local slice of Y (cached on pointer + shape + a strided checksum)."""
+    def attach(self, Y, M_global=None, col_offset=0, force=True):
+        """Upload this rank's L x M_local slice of Y.  Every call uploads: the library never guesses that a host array is
+        unchanged (an in-place edit is invisible to any cheap fingerprint).  Residency is explicit instead: attach once, then
+        pass Y=None to the drivers / step functions to run on the matrix already on the device (tests/mgpu_worker.py).
+        `force` is accepted for backward compatibility and ignored."""
         Y = _f(Y)
         if Y.ndim != 2:
             raise ValueError("Y must be a matrix")
-        key = self._fingerprint(Y) + (M_global, col_offset)
-        if not force and key == self._key:
-            return
         Lr, M = Y.shape
         Mg = M if M_global is None else M_global
         L_.check(self.lib.vbmf_b200_attach_Y(self.h, _ptr(Y), Lr, M, max(Lr, 1), Mg, col_offset))
-        self._key = key
+        self._key = ("host", Lr, M, Mg, col_offset)
         self.L, self.M, self.M_global, self.col_offset = Lr, M, Mg, col_offset
 
     def set_shape(self, Lr, M_local, M_global=None, col_offset=0):
@@ -172,9 +166,18 @@ def default_context(device=0):
 
 
 def _ctx_for(Y, ctx):
+    """Context for a call that takes Y.  Y=None: run on the matrix already resident in ctx.  On a sharded context
+    (world > 1) a host Y must be this rank's shard: it is re-attached with the geometry (M_global, col_offset) the context
+    already holds; a shard of a different shape cannot be placed and is refused instead of silently running with M_global = M_local."""
     ctx = ctx or default_context()
     if Y is not None:
-        ctx.attach(Y)
+        if ctx.world > 1:
+            if ctx.M_global <= 0 or tuple(np.shape(Y)) != (ctx.L, ctx.M):
+                raise VBMFError("sharded context (world=%d): pass Y=None after ctx.attach(Y_shard, M_global=..., col_offset=...), or a shard "
+                                "of the attached shape %s (got %s)" % (ctx.world, (ctx.L, ctx.M), tuple(np.shape(Y))))
+            ctx.attach(Y, M_global=ctx.M_global, col_offset=ctx.col_offset)
+        else:
+            ctx.attach(Y)
     return ctx
 
 
@@ -501,7 +504,8 @@ class Solver:
 
     def run(self, niter, eps=1e-6, flags=0, norm="spectral"):
         it, d = C.c_int64(), C.c_double()
-        L_.check(self.lib.vbmf_b200_solver_run(self.h, int(niter), float(eps), flags, _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
+        self.failed = _not_pd(L_.check(self.lib.vbmf_b200_solver_run(self.h, int(niter), float(eps), flags, _NORMS[norm], C.byref(it), C.byref(d)),
+                                       allow=(-2,))) == -2
         return it.value, d.value
 
     def lower_bound(self, trim=0.0, trimmed=False):
@@ -519,6 +523,22 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+class VBMFWarning(RuntimeWarning):
+    """A posterior precision matrix was not positive definite: NaN was written and the loop ended (ABI return code -2)."""
+
+
+def _not_pd(rc, params=None):
+    """Return code -2: the reference's LU `inv` would return garbage (or throw SingularException); here the state carries NaN,
+    `params.failed` is set and a VBMFWarning names the cause.  Nothing is swallowed silently."""
+    if params is not None:
+        params.failed = rc == -2
+    if rc == -2:
+        import warnings
+        msg = (L_.load().vbmf_b200_last_error() or b"").decode("utf-8", "replace")
+        warnings.warn(VBMFWarning(msg or "a posterior precision matrix was not positive definite"), stacklevel=3)
+    return rc
 
 
 def _flags(diag_var=False, full_cov=False, est_cb=False, est_priors=False, est_covs=False, est_var=False):
@@ -544,8 +564,8 @@ def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False,
     ctx = _ctx_for(Y, ctx)
     st = _dense_struct(params, yhat)
     it, d = C.c_int64(), C.c_double()
-    L_.check(ctx.lib.vbmf_b200_dense_run(ctx.h, C.byref(st), int(niter), float(eps), int(est_covs), int(est_var), _NORMS[norm],
-                                         C.byref(it), C.byref(d)), allow=(-2,))
+    _not_pd(L_.check(ctx.lib.vbmf_b200_dense_run(ctx.h, C.byref(st), int(niter), float(eps), int(est_covs), int(est_var), _NORMS[norm],
+                                         C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations, params.d = it.value, d.value
     _verb(verb, it.value, d.value)
@@ -569,8 +589,8 @@ def vbmf_sparse_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, ver
     ctx = _ctx_for(Y, ctx)
     st = _sparse_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
-    L_.check(ctx.lib.vbmf_b200_sparse_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_cb),
-                                          _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
+    _not_pd(L_.check(ctx.lib.vbmf_b200_sparse_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_cb),
+                                          _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.AHat = _f(params.AHat)
     params.iterations = it.value
@@ -597,8 +617,8 @@ def vbmf_dual_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=
     ctx = _ctx_for(Y, ctx)
     st = _dual_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
-    L_.check(ctx.lib.vbmf_b200_dual_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
-                                        int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
+    _not_pd(L_.check(ctx.lib.vbmf_b200_dual_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
+                                        int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations = it.value
     _verb(verb, it.value, d.value)
@@ -618,8 +638,8 @@ def vbmf_trial_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb
     ctx = _ctx_for(Y, ctx)
     st = _trial_struct(params, yhat, keep_blocks, getattr(params, "_m2_local", None))
     it, d = C.c_int64(), C.c_double()
-    L_.check(ctx.lib.vbmf_b200_trial_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
-                                         int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,))
+    _not_pd(L_.check(ctx.lib.vbmf_b200_trial_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
+                                         int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations = it.value
     _verb(verb, it.value, d.value)
@@ -642,8 +662,26 @@ def _shape_for(params, ctx):
     return ctx
 
 
+def _a_mismatch(params):
+    """True when AHat and ATVecHat (= vec(AHat')) of a sparse / dual / trial params object disagree, e.g. after
+    `params.AHat = X` (examples/toy_data.jl:54).  The reference keeps two host copies: updateB!/updateSigma!/lowerBound read
+    AHat, updateCA!/lowerBound read ATVecHat.  The device holds ONE factor, so the step functions pick the copy their
+    reference counterpart reads and leave the other host copy untouched."""
+    if params.kind == L_.DENSE or getattr(params, "ATVecHat", None) is None:
+        return False
+    return not np.array_equal(np.ascontiguousarray(params.AHat).reshape(-1), np.asarray(params.ATVecHat).reshape(-1))
+
+
 def _one_step(Y, params, step, flags=0, ctx=None, want_yhat=False):
     ctx = _ctx_for(Y, ctx) if Y is not None else _shape_for(params, ctx)
+    keep = None
+    if _a_mismatch(params):
+        if step == L_.STEP_UPDATE_CA:            # updateCA! reads ATVecHat and leaves AHat alone (src/vbmf_sparse.jl:284-288)
+            keep = ("AHat", params.AHat.copy())
+            params.AHat = _f(np.asarray(params.ATVecHat).reshape(params.M, params.H))
+        elif step != L_.STEP_UPDATE_A:           # updateB! / updateSigma! / updateYHat! read AHat and leave ATVecHat alone
+            keep = ("ATVecHat", np.array(params.ATVecHat))
+            params.ATVecHat = np.ascontiguousarray(params.AHat).reshape(-1).copy()
     s = Solver(ctx, params, keep_blocks=bool(flags & L_.FULL_COV) and getattr(params, "SigmaATVec_blocks", None) is not None)
     try:
         s.upload(params)
@@ -652,6 +690,8 @@ def _one_step(Y, params, step, flags=0, ctx=None, want_yhat=False):
         s.download(params, want_yhat=want_yhat)
     finally:
         s.close()
+        if keep is not None:
+            setattr(params, keep[0], keep[1])
 
 
 def updateA_(Y, params, full_cov=False, diag_var=False, ctx=None):
@@ -718,6 +758,8 @@ def updateBeta01_(params, ctx=None):
 
 def lowerBound(Y, params, ctx=None):
     """lowerBound src/vbmf_sparse.jl:435, src/vbmf_dual.jl:556"""
+    if _a_mismatch(params):
+        raise VBMFError("lowerBound: params.AHat and params.ATVecHat disagree (the reference would mix the two copies); set both")
     ctx = _ctx_for(Y, ctx)
     s = Solver(ctx, params)
     try:
@@ -729,6 +771,8 @@ def lowerBound(Y, params, ctx=None):
 
 def lowerBoundTrimmed(Y, params, trim=1e-1, ctx=None):
     """lowerBoundTrimmed src/vbmf_sparse.jl:478, src/vbmf_dual.jl:606"""
+    if _a_mismatch(params):
+        raise VBMFError("lowerBoundTrimmed: params.AHat and params.ATVecHat disagree (the reference would mix the two copies); set both")
     ctx = _ctx_for(Y, ctx)
     s = Solver(ctx, params)
     try:
@@ -778,8 +822,10 @@ class BatchedVbls:
     def run(self, niter, full_cov=False):
         if self.n == 0:
             return 0
-        return L_.check(self.ctx.lib.vbmf_b200_batched_vbls(self.ctx.h, self.kind, self.n, self.yp, self.sp, int(niter),
-                                                           L_.FULL_COV if full_cov else 0), allow=(-2,))
+        rc = _not_pd(L_.check(self.ctx.lib.vbmf_b200_batched_vbls(self.ctx.h, self.kind, self.n, self.yp, self.sp, int(niter),
+                                                                  L_.FULL_COV if full_cov else 0), allow=(-2,)))
+        self.failed = rc == -2
+        return rc
 
     def readback(self):
         for p, st in zip(self.params, self.structs):
@@ -799,21 +845,19 @@ def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, k
 
 def preprocess(Y, lam, verb=False, ctx=None):
     """`preprocess(Y, lambda; verb)` src/util.jl:73-87: returns the scaled matrix with near-constant rows removed, times lambda.
-    The result also stays resident on the device (ctx), ready for the solvers."""
+    The result also stays resident on the device (ctx): solvers called with Y=None run on it."""
     ctx = ctx or default_context()
     Y = _f(Y)
-    ctx.attach(Y, force=True)
+    ctx.attach(Y)
     L0 = ctx.L
     rows = ctx.preprocess(lam)
     if verb:
         print("Original problem size: %d rows, %d rows not relevant and are not used." % (L0, L0 - rows.size))
-    out = ctx.download_Y()
-    ctx._key = Context._fingerprint(out) + (None, 0)     # the resident matrix IS `out`: the next solver call need not upload it
-    return out
+    return ctx.download_Y()       # the processed matrix also stays resident: pass Y=None to run on it without another upload
 
 
 # ----------------------------------------------------------------------------------------------------------- trajectory logging (N4)
-_LOG_SKIP = ("YHat", "SigmaATVec_blocks", "iterations", "d", "kind")
+_LOG_SKIP = ("YHat", "SigmaATVec_blocks", "iterations", "d", "kind", "log", "failed")
 
 
 def _log_fields(params):
@@ -826,6 +870,8 @@ def create_log(params):
     log = {}
     for k in _log_fields(params):
         v = getattr(params, k)
+        if isinstance(v, (dict, list, tuple, str)) or not np.issubdtype(np.asarray(v).dtype, np.number):
+            continue                      # only numeric fields are logged (src/data_manip.jl:10-22 handles Array / Number)
         log[k] = [np.array(v, dtype=np.float64 if not isinstance(v, (int, np.integer)) else np.int64)]
     return log
 

@@ -152,6 +152,7 @@ extern "C" int vbmf_b200_ctx_create(int device, int rank, int world, const void*
         set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
         return -1;
     }
+    if (gemm_init_device() || kernels_init_device()) return -1;      // per-device dynamic shared memory opt-ins
     vbmf_b200_ctx* c = new vbmf_b200_ctx();
     c->device = device; c->rank = rank; c->world = world < 1 ? 1 : world;
     c->num_sms = prop.multiProcessorCount;

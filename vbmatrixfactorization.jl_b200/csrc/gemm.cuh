@@ -14,6 +14,8 @@ struct GemmGeometry {
     int stages;
 };
 GemmGeometry gemm_geometry(int H);
+// opt the contraction kernels into their dynamic shared memory on the CURRENT device (once per context)
+int gemm_init_device();
 
 // K1: P[m][h] = sum_l Y[l, m] * B[l, h]      (Y' * BHat, src/vbmf.jl:98, src/vbmf_sparse.jl:195,232)
 // tmY : dims {L, M}, box {16, 128};  tmB : dims {L, H} (column h contiguous in l), box {16, bn}

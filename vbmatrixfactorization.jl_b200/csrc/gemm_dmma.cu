@@ -399,16 +399,22 @@ void plan_splitk_ytb(int L, int M, int H, int num_sms, int* S_out, int* kb_per_s
 template <int BN>
 static int launch_ytb_t(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* tmB, double* P, int M, int L, int H,
                         int ldP, int S, int kbs, size_t slab_stride, const Scalars* sc, int num_sms) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CUDA_OK(cudaFuncSetAttribute(gemm_ytb_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<BN>::SMEM));
-        attr_set = true;
-    }
     const int nwork = ((M + BM - 1) / BM) * S;
     const int grid = std::max(1, std::min(nwork, num_sms * CfgK1<BN>::CPS));
     const int threads = (CfgK1<BN>::WM * CfgK1<BN>::WN + 1) * 32;
     gemm_ytb_kernel<BN><<<grid, threads, Sizes<BN>::SMEM, st>>>(*tmY, *tmB, P, M, L, H, ldP, S, kbs, slab_stride, sc);
     VB_LAUNCH_OK();
+    return 0;
+}
+
+// cudaFuncSetAttribute is per device: called once per context for the context's device (no process-wide flags)
+int gemm_init_device() {
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ytb_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<32>::SMEM));
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ytb_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<64>::SMEM));
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ytb_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<128>::SMEM));
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ya_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<32>::SMEM));
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ya_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<64>::SMEM));
+    VB_CUDA_OK(cudaFuncSetAttribute(gemm_ya_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<128>::SMEM));
     return 0;
 }
 
@@ -424,11 +430,6 @@ int launch_gemm_ytb(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* 
 template <int BN>
 static int launch_ya_t(cudaStream_t st, const CUtensorMap* tmY, const CUtensorMap* tmA, double* Qpart, int L, int M, int H,
                        int ldQ, int kchunk, int S, const Scalars* sc, int num_sms) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CUDA_OK(cudaFuncSetAttribute(gemm_ya_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sizes<BN>::SMEM));
-        attr_set = true;
-    }
     const int ntl = (L + BM - 1) / BM;
     const int grid = std::max(1, std::min(ntl * S, num_sms * Cfg<BN>::CPS));
     const int threads = (Cfg<BN>::WM * Cfg<BN>::WN + 1) * 32;

@@ -6,6 +6,7 @@
 #include "linalg.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace vb {
 
@@ -591,14 +592,6 @@ int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, s
     const size_t smem = (size_t)((HP8 + 64) * ld) * sizeof(double);
     const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));     // latency hiding across CTAs
     const int grid = std::max(1, std::min(cdiv(d.Mloc, 32), 148 * per_sm));
-    static bool done = false;
-    if (!done) {
-        const int mx = (int)((128 + 64) * pitch4(128) * 8);
-        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        VB_CUDA_OK(cudaFuncSetAttribute(dense_A_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        done = true;
-    }
     if (HP8 <= 32) dense_A_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
     else if (HP8 <= 64) dense_A_fused_kernel<8><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
     else dense_A_fused_kernel<32><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
@@ -822,29 +815,146 @@ __global__ void __launch_bounds__(256, 2) sparse_A_full_warp_kernel(Dev d, int d
         out[e] = t;
     }
 }
+// H <= 32, tensor-core version: one warp per matrix, upper-triangular 8 x 8 tiles in DMMA accumulator registers, blocked
+// rank-4 Gauss-Jordan (linalg.cuh::warp_block_gj_sym).  The right-hand side p_m rides through the sweeps, the running sum of
+// Sigma_m stays in registers (tiles on and above the diagonal only).  Shared memory: G as accumulator-layout tiles (read once
+// per matrix with conflict-free 128-bit loads), 2.5 KB of scratch per warp.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, int diag_var, int nwarps_total) {
+    ACTIVE_OR_RETURN(d);
+    constexpr int NTRI = NT * (NT + 1) / 2, N = 8 * NT, WPC = 4;
+    extern __shared__ __align__(16) double wsm[];
+    double* s_G = wsm;                                  // [NTRI][32][2]
+    double* s_scr = s_G + NTRI * 64;                    // [WPC][4N + 4N + 32 + 32]
+    double* s_red = s_scr + WPC * (8 * N + 64);         // [WPC][NTRI][64] end-of-kernel reduction
+    const int H = d.H;
+    const Scalars* sc = d.sc;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, r = lane >> 2, j = lane & 3;
+    const int gw = blockIdx.x * WPC + wic;
+    double* Ps = s_scr + wic * (8 * N + 64);
+    double* Ws = Ps + 4 * N;
+    double* sv = Ws + 4 * N;                            // [32] equilibration scale 1/sqrt(diag)
+    double* cav = sv + 32;                              // [32] CA_m
+    const double sh = sc->sigmaHat;
+    const bool live = lane < H;
+    // G in accumulator layout, zero padded
+    for (int e = threadIdx.x; e < NTRI * 64; e += blockDim.x) {
+        const int t = e >> 6, l = (e >> 1) & 31, k = e & 1;
+        int ti = 0, rem = t;
+        while (rem >= NT - ti) { rem -= NT - ti; ++ti; }
+        const int row = 8 * ti + (l >> 2), col = 8 * (ti + rem) + 2 * (l & 3) + k;
+        s_G[e] = (row < H && col < H) ? d.Gm[row * H + col] : 0.0;
+    }
+    const double gll = live ? d.Gm[lane * H + lane] : 0.0;
+    double acc[NTRI][2];
+#pragma unroll
+    for (int t = 0; t < NTRI; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    __syncthreads();
+    bool all_ok = true;
+    for (int m = gw; m < d.Mloc; m += nwarps_total) {
+        const double ca = live ? d.CAv[(size_t)m * H + lane] : 1.0;       // padded rows / columns: identity
+        const double p = live ? d.P[(size_t)m * H + lane] : 0.0;
+        const double sl = rsqrt(gll + ca);
+        sv[lane] = sl;
+        cav[lane] = ca;
+        __syncwarp();
+        double c[NTRI][2];
+        {
+            double srow[NT];
+            double2 scol[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { srow[t] = sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
+#pragma unroll
+            for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < NT; ++tj) {
+                    const int t = tri_idx(ti, tj, NT);
+                    const double2 g = *reinterpret_cast<const double2*>(s_G + t * 64 + lane * 2);
+                    double g0 = g.x, g1 = g.y;
+                    if (ti == tj && j == (r >> 1)) { const double cr = cav[8 * ti + r]; if (r & 1) g1 += cr; else g0 += cr; }
+                    c[t][0] = g0 * (srow[ti] * scol[tj].x);
+                    c[t][1] = g1 * (srow[ti] * scol[tj].y);
+                }
+        }
+        double v = p * sl;
+        const bool ok = warp_block_gj_sym<NT>(c, v, lane, Ps, Ws);
+        all_ok = all_ok && ok;
+        if (live) d.A[(size_t)m * H + lane] = ok ? (diag_var ? sl * v : (sh * sl) * v) : nan("");
+        // Sigma_m = -D*c*D: un-equilibrate (the scale vector is re-read: holding it across the sweeps costs 24 registers), emit
+        // the diagonal (and the blocks on request), add to the running sum
+        double srow[NT];
+        double2 scol[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { srow[t] = -sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < NT; ++tj) {
+                const int t = tri_idx(ti, tj, NT);
+                const double s0 = c[t][0] * (srow[ti] * scol[tj].x), s1 = c[t][1] * (srow[ti] * scol[tj].y);
+                acc[t][0] += s0;
+                acc[t][1] += s1;
+                const int row = 8 * ti + r, col = 8 * tj + 2 * j;
+                if (ti == tj && j == (r >> 1) && row < H) d.sdiag[(size_t)m * H + row] = ok ? ((r & 1) ? s1 : s0) : nan("");
+                if (d.blocks != nullptr && row < H) {
+                    double* blk = d.blocks + (size_t)m * H * H;
+                    if (col < H) { blk[row * H + col] = s0; if (ti != tj) blk[col * H + row] = s0; }
+                    if (col + 1 < H) { blk[row * H + col + 1] = s1; if (ti != tj) blk[(col + 1) * H + row] = s1; }
+                }
+            }
+        __syncwarp();
+    }
+    if (!all_ok && lane == 0) d.sc->chol_fail = 1;
+    // per-CTA sum of the warps' running sums in fixed warp order; the lower tiles are the mirror image
+    double* myred = s_red + wic * NTRI * 64;
+#pragma unroll
+    for (int t = 0; t < NTRI; ++t) *reinterpret_cast<double2*>(myred + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+    __syncthreads();
+    double* out = d.part + (size_t)blockIdx.x * H * H;
+    for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+        int a = e / H, b = e - a * H;
+        if ((a >> 3) > (b >> 3)) { const int tmp = a; a = b; b = tmp; }
+        const int t = tri_idx(a >> 3, b >> 3, NT);
+        const int idx = t * 64 + (4 * (a & 7) + ((b & 7) >> 1)) * 2 + (b & 1);
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPC; ++w) sum += s_red[w * NTRI * 64 + idx];
+        out[e] = sum;
+    }
+}
+template <int NT> static size_t k4_dmma_smem() { return (size_t)(NT * (NT + 1) / 2 * 64 + 4 * (64 * NT + 64) + 4 * (NT * (NT + 1) / 2) * 64) * sizeof(double); }
+
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
     build_G_kernel<<<1, 256, 0, st>>>(d, dv);
     VB_LAUNCH_OK();
     int ngroups;
-    if (H <= 32) {
+    static const bool use_reg = getenv("VBMF_B200_K4") != nullptr && strcmp(getenv("VBMF_B200_K4"), "reg") == 0;
+    if (H <= 32 && !use_reg) {
+        static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 3;     // tuning probe
+        const int wpc = 4;
+        const int per_sm = (H <= 16) ? 4 : (minb == 2 ? 2 : 3);
+        const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * per_sm));
+        ngroups = grid;                                   // one partial per CTA
+        if (H <= 8) sparse_A_full_dmma_kernel<1, 4><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc);
+        else if (H <= 16) sparse_A_full_dmma_kernel<2, 4><<<grid, 128, k4_dmma_smem<2>(), st>>>(d, dv, grid * wpc);
+        else if (H <= 24) sparse_A_full_dmma_kernel<3, 3><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc);
+        else if (minb == 2) sparse_A_full_dmma_kernel<4, 2><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        else sparse_A_full_dmma_kernel<4, 3><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+    } else if (H <= 32) {
         const int wpc = 8;
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
         ngroups = grid;                                   // one partial per CTA
 #define WK(HPV)                                                                                                          \
     {                                                                                                                    \
         const size_t smem = (size_t)(HPV * 32 + 8 * 64 + 8 * 32 + 8 * HPV * 32) * sizeof(double);                        \
-        static bool done = false;                                                                                        \
-        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_warp_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; } \
         sparse_A_full_warp_kernel<HPV><<<grid, 256, smem, st>>>(d, dv, grid * wpc);                                      \
     }
         if (H <= 8) WK(8) else if (H <= 16) WK(16) else if (H <= 24) WK(24) else WK(32)
 #undef WK
     } else {
         const size_t smem = (size_t)(H * (H + 1) + 3 * H) * sizeof(double);
-        static bool done = false;
-        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sparse_A_full_kernel<BlockGroup, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * 129 + 384) * 8))); done = true; }
         const int grid = std::max(1, std::min(std::max(d.Mloc, 1), 148));
         ngroups = grid;
         sparse_A_full_kernel<BlockGroup, 64><<<grid, 256, smem, st>>>(d, dv, ngroups);
@@ -1158,13 +1268,6 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     if (H <= 64 && getenv("VBMF_B200_BEPI_SIMT") == nullptr) {
         const int HP8 = (H + 7) & ~7;
         const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
-        static bool done = false;
-        if (!done) {
-            const int mx = (int)((64 + 96) * pitch4(64) * 8);
-            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-            VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-            done = true;
-        }
         const int grid2 = std::max(1, std::min(cdiv(d.L, 32), 296));      // two CTAs per SM: the tile chain is latency bound
         if (HP8 <= 32) B_epilogue_dmma_kernel<2, true><<<grid2, 256, smem, st>>>(d, dv);
         else B_epilogue_dmma_kernel<8, true><<<grid2, 256, smem, st>>>(d, dv);
@@ -1177,8 +1280,6 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
         // H > 64: product-only DMMA epilogue (the Gram accumulators would not fit in registers), Grams by gram_dmma
         const int HP8 = (H + 7) & ~7;
         const size_t smem = (size_t)((HP8 + 32) * pitch4(HP8)) * sizeof(double);
-        static bool done2 = false;
-        if (!done2) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_dmma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 32) * pitch4(128) * 8))); done2 = true; }
         const int grid3 = std::max(1, std::min(cdiv(d.L, 32), 148));
         B_epilogue_dmma_kernel<1, false><<<grid3, 256, smem, st>>>(d, dv);
         VB_LAUNCH_OK();
@@ -1189,10 +1290,7 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     }
 #define BEPI(RR, TDD, TRR)                                                                                                   \
     {                                                                                                                        \
-        static bool done = false;                                                                                            \
         const size_t smem = (size_t)((H + 3 * TRR) * (H + 1)) * sizeof(double);                                              \
-        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(B_epilogue_kernel<RR, TDD, TRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                     (int)((TDD * RR + 3 * TRR) * (TDD * RR + 1) * 8))); done = true; }      \
         B_epilogue_kernel<RR, TDD, TRR><<<grid, TDD * TDD, smem, st>>>(d, dv);                                               \
     }
     if (H <= 16) BEPI(1, 16, 32) else if (H <= 32) BEPI(2, 16, 32) else if (H <= 64) BEPI(4, 16, 32) else BEPI(4, 32, 16)
@@ -1284,8 +1382,6 @@ __global__ void mean_sigma_kernel(Dev d, int nparts) {
     if (threadIdx.x == 0) d.sc->meanSigmaVec = s / (double)d.L;
 }
 int k_sigma_rows(cudaStream_t st, const Dev& d) {
-    static bool done = false;
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(sigma_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8)); done = true; }
     const int grid = std::max(1, std::min(cdiv(d.L, 128), MAX_PARTS));
     sigma_rows_kernel<<<grid, 128, (size_t)d.H * d.H * 8, st>>>(d);
     VB_LAUNCH_OK();
@@ -1494,12 +1590,6 @@ __global__ void __launch_bounds__(512) norms_kernel(Dev d, int first) {
 }
 static size_t post_smem(int H) { return (size_t)((H + 2) * (H + 2) + 4 * (H + 2) + 8) * sizeof(double); }
 static int post_launch(cudaStream_t st, const Dev& d, int what, int flags) {
-    static bool done = false;
-    if (!done) {
-        VB_CUDA_OK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128)));
-        VB_CUDA_OK(cudaFuncSetAttribute(norms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(128)));
-        done = true;
-    }
     if (what & (POST_DELTA | POST_NORM_INIT)) {
         const int first = (what & POST_DELTA) ? 0 : 1;
         norms_kernel<<<2 - first, 512, post_smem(d.H), st>>>(d, first);
@@ -1556,8 +1646,6 @@ __global__ void __launch_bounds__(256) yhat_kernel(Dev d, double* __restrict__ o
     }
 }
 int k_yhat(cudaStream_t st, const Dev& d, double* out, int ldo) {
-    static bool done = false;
-    if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(yhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 129 + 16 * 128) * 8)); done = true; }
     if (d.L <= 0 || d.Mloc <= 0) return 0;
     dim3 grid(cdiv(d.L, 64), cdiv(d.Mloc, 16));
     yhat_kernel<<<grid, 256, (size_t)(64 * (d.H + 1) + 16 * d.H) * 8, st>>>(d, out, ldo);
@@ -1724,8 +1812,6 @@ int k_lower_bound(cudaStream_t st, const Dev& d, double trim, int trimmed, int p
         lb_reduce_kernel<<<1, 32, 0, st>>>(d, grid);
         VB_LAUNCH_OK();
     } else {
-        static bool done = false;
-        if (!done) { VB_CUDA_OK(cudaFuncSetAttribute(lb_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8)); done = true; }
         lb_final_kernel<<<1, 32, (size_t)d.H * d.H * 8, st>>>(d, trimmed);
         VB_LAUNCH_OK();
     }
@@ -1792,6 +1878,41 @@ int k_synth(cudaStream_t st, double* Y, int ldY, int L, int Mloc, int moff, int 
     dim3 grid(cdiv(L, 64), cdiv(Mloc, 16));
     synth_kernel<<<grid, 256, (size_t)80 * rank * 8, st>>>(Y, ldY, L, Mloc, moff, rank, noise, seed);
     VB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- per-device kernel attributes
+// cudaFuncSetAttribute applies to the CURRENT device only, so every context opts the kernels of this file into their dynamic
+// shared memory once for its own device (a process may hold contexts on several GPUs).
+#define VB_SMEM_ATTR(kernel, bytes) VB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+int kernels_init_device() {
+    const int mxA = (int)((128 + 64) * pitch4(128) * 8);
+    VB_SMEM_ATTR(dense_A_fused_kernel<2>, mxA);
+    VB_SMEM_ATTR(dense_A_fused_kernel<8>, mxA);
+    VB_SMEM_ATTR(dense_A_fused_kernel<32>, mxA);
+    VB_SMEM_ATTR((sparse_A_full_kernel<BlockGroup, 64>), (128 * 129 + 384) * 8);
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<1, 4>), k4_dmma_smem<1>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<2, 4>), k4_dmma_smem<2>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<3, 3>), k4_dmma_smem<3>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 3>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 2>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR(sparse_A_full_warp_kernel<8>, (8 * 32 + 8 * 64 + 8 * 32 + 8 * 8 * 32) * 8);
+    VB_SMEM_ATTR(sparse_A_full_warp_kernel<16>, (16 * 32 + 8 * 64 + 8 * 32 + 8 * 16 * 32) * 8);
+    VB_SMEM_ATTR(sparse_A_full_warp_kernel<24>, (24 * 32 + 8 * 64 + 8 * 32 + 8 * 24 * 32) * 8);
+    VB_SMEM_ATTR(sparse_A_full_warp_kernel<32>, (32 * 32 + 8 * 64 + 8 * 32 + 8 * 32 * 32) * 8);
+    const int mxB = (int)((64 + 96) * pitch4(64) * 8);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<2, true>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<8, true>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<1, false>), (128 + 32) * pitch4(128) * 8);
+    VB_SMEM_ATTR((B_epilogue_kernel<1, 16, 32>), (16 + 96) * 17 * 8);
+    VB_SMEM_ATTR((B_epilogue_kernel<2, 16, 32>), (32 + 96) * 33 * 8);
+    VB_SMEM_ATTR((B_epilogue_kernel<4, 16, 32>), (64 + 96) * 65 * 8);
+    VB_SMEM_ATTR((B_epilogue_kernel<4, 32, 16>), (128 + 48) * 129 * 8);
+    VB_SMEM_ATTR(sigma_rows_kernel, 128 * 128 * 8);
+    VB_SMEM_ATTR(post_kernel, post_smem(128));
+    VB_SMEM_ATTR(norms_kernel, post_smem(128));
+    VB_SMEM_ATTR(yhat_kernel, (64 * 129 + 16 * 128) * 8);
+    VB_SMEM_ATTR(lb_final_kernel, 128 * 128 * 8);
     return 0;
 }
 

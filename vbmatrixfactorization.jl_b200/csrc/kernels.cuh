@@ -54,6 +54,9 @@ enum {
     F_FORCE = 64   // ignore sc->active (step-level API)
 };
 
+// opt the kernels of kernels.cu / batched.cu into their dynamic shared memory on the CURRENT device (once per context)
+int kernels_init_device();
+
 int k_set_control(cudaStream_t st, const Dev& d, int niter, double eps, int norm_mode, int force_active);
 int k_y_stats(cudaStream_t st, const Dev& d, double* out_tr /*device, 1*/);
 int k_transpose(cudaStream_t st, const double* src, double* dst, int rows, int cols);  // src col-major rows x cols -> dst row-major

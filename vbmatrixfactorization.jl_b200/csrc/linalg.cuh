@@ -128,6 +128,112 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
     return ok;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked (rank-4) symmetric Gauss-Jordan on FP64 tensor-core fragments: the inverse the per-column full-covariance update
+// needs 1e5 times per iteration (src/vbmf_sparse.jl:188, src/vbmf_dual.jl:228).
+//
+// One warp holds an equilibrated SPD matrix of order N = 8*NT (NT <= 4) as the upper-triangular 8 x 8 tiles (ti <= tj) of the
+// DMMA accumulator layout: lane = 4*r + j holds S[8ti + r][8tj + 2j], S[8ti + r][8tj + 2j + 1].  A block step sweeps the four
+// pivots K = 4s .. 4s+3 at once:
+//   1. the column panel P = S[:, K] (N x 4) goes to shared memory (tiles below the diagonal are read through symmetry);
+//   2. with lane = row, four ordinary sweeps restricted to the panel turn it into X = [P*inv(D) ; -inv(D)], D = P[K, :]
+//      (pivot rows travel by shuffle; the right-hand side v rides along as a fifth column, so inv(S)*v needs no mat-vec);
+//   3. -X and P are read back as A / B fragments (lane (r, j) <- row 8t + r, column j) and every stored tile takes ONE
+//      DMMA.8x8x4:  T[ti][tj] -= W'[ti] * P'[tj]^T  with  W' = X + E, P' = P - E (E = identity on the pivot rows), which
+//      writes the swept values of the pivot rows / columns as well (up to the constant 2 on the block's diagonal).
+// After the 2*NT steps the tiles hold -inv(S) and v holds inv(S)*v.  Operand traffic per lane: 8 doubles per FOUR pivots
+// (the rank-1 register sweep above needs 32 per ONE pivot, which made it shared-memory bound), and symmetry halves the
+// FP64 work.  Accuracy equals LAPACK's LU inverse on the equilibrated matrices (tools/k4bench/acc_compare.py).
+// Ps, Ws: 4*N doubles each of per-warp shared scratch (16-byte aligned).  `ok` is uniform across the warp.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// 1/x for a positive, finite, normal x: hardware seed + two Newton steps (<= 1 ulp; no special-case slow path, the callers
+// have already rejected non-positive / non-finite pivots)
+__device__ __forceinline__ double rcp_pos(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// positive, finite and not denormal / huge, tested on the exponent word (integer pipe, keeps the FP64 pipe for the math)
+__device__ __forceinline__ bool pivot_ok(double x) {
+    return (unsigned)(__double2hiint(x) - 0x00100000) < (unsigned)(0x7e300000 - 0x00100000);
+}
+__host__ __device__ constexpr int tri_idx(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
+
+template <int NT>
+__device__ __forceinline__ bool warp_block_gj_sym(double (&c)[NT * (NT + 1) / 2][2], double& v, const int lane,
+                                                  double* __restrict__ Ps, double* __restrict__ Ws) {
+    constexpr int N = 8 * NT;
+    const int r = lane >> 2, j = lane & 3;
+    const bool rowlane = lane < N;
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < 2 * NT; ++s) {
+        const int tk = s >> 1, half = s & 1;
+        // 1. publish the column panel
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (t <= tk) {
+                if ((j >> 1) == half)
+                    *reinterpret_cast<double2*>(Ps + (8 * t + r) * 4 + 2 * (j & 1)) = make_double2(c[tri_idx(t, tk, NT)][0], c[tri_idx(t, tk, NT)][1]);
+            } else {
+                if ((r >> 2) == half) {
+                    Ps[(8 * t + 2 * j) * 4 + (r & 3)] = c[tri_idx(tk, t, NT)][0];
+                    Ps[(8 * t + 2 * j + 1) * 4 + (r & 3)] = c[tri_idx(tk, t, NT)][1];
+                }
+            }
+        }
+        __syncwarp();
+        // 2. lane = row: four sweeps on the panel (+ the right-hand side)
+        double x[4] = {0.0, 0.0, 0.0, 0.0};
+        if (rowlane) {
+            const double2 a0 = *reinterpret_cast<const double2*>(Ps + lane * 4), a1 = *reinterpret_cast<const double2*>(Ps + lane * 4 + 2);
+            x[0] = a0.x; x[1] = a0.y; x[2] = a1.x; x[3] = a1.y;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int kc = 4 * s + cc;
+            double pr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pr[q] = __shfl_sync(0xffffffffu, x[q], kc);
+            const double prv = __shfl_sync(0xffffffffu, v, kc);
+            const double dpiv = pr[cc];
+            ok = ok && pivot_ok(dpiv);
+            const double id = rcp_pos(dpiv);
+            const bool piv = lane == kc;
+            const double f = piv ? 1.0 - id : x[cc] * id;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q != cc) x[q] = fma(-f, pr[q], x[q]);
+            v = fma(-f, prv, v);
+            x[cc] = piv ? -id : f;
+        }
+        if (rowlane) {
+            *reinterpret_cast<double2*>(Ws + lane * 4) = make_double2(-x[0], -x[1]);
+            *reinterpret_cast<double2*>(Ws + lane * 4 + 2) = make_double2(-x[2], -x[3]);
+        }
+        __syncwarp();
+        // 3. fragments and the rank-4 update of every stored tile
+        double pf[NT], wf[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { pf[t] = Ps[(8 * t + r) * 4 + j]; wf[t] = Ws[(8 * t + r) * 4 + j]; }
+        if (r == 4 * half + j) { pf[tk] -= 1.0; wf[tk] -= 1.0; }
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < NT; ++tj) dmma884(c[tri_idx(ti, tj, NT)], wf[ti], pf[tj]);
+        if ((r >> 2) == half && j == (r >> 1)) {
+            if (r & 1) c[tri_idx(tk, tk, NT)][1] -= 2.0; else c[tri_idx(tk, tk, NT)][0] -= 2.0;
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
 // CTA version: thread t owns elements e = t + q*blockDim.x (q < Q) of the row-major H x H matrix; column k travels
 // through a double-buffered shared vector, one __syncthreads per sweep.  cbuf = 2*H doubles, sbuf = H doubles.
 // Result stays in a[]; `ok` is uniform across the CTA.
