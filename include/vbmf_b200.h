@@ -234,6 +234,14 @@ int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags);
 /* the while-loop of vbmf! (src/vbmf.jl:193-214), vbmf_sparse! (src/vbmf_sparse.jl:368-393), vbmf_dual!
  * (src/vbmf_dual.jl:480-513) with the convergence test on the device.  iters = iterations done, d = last delta. */
 int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode, int64_t* iters, double* d);
+/* The same loop with the reference's per-iteration logging hook (`update_log!(log, params)` after every iteration when
+ * logdir != "", src/vbmf.jl:206-208, src/vbmf_sparse.jl:385-387, src/vbmf_dual.jl:505-507; log format src/data_manip.jl:6-66):
+ * after each iteration the device is synchronised and cb(user, s, iterations_done, d) runs on the calling thread; it may call
+ * the *_download function of the solver's kind to fetch the fields it logs (small fields only at scale: pass NULL for YHat
+ * and the blocks).  A non-zero return stops the loop early.  cb == NULL behaves like vbmf_b200_solver_run one iteration at a time. */
+typedef int (*vbmf_b200_iter_callback)(void* user, vbmf_b200_solver* s, int64_t iterations_done, double d);
+int vbmf_b200_solver_run_logged(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode,
+                                vbmf_b200_iter_callback cb, void* user, int64_t* iters, double* d);
 /* lowerBound (trimmed = 0) / lowerBoundTrimmed (trimmed = 1), src/vbmf_sparse.jl:435-489, src/vbmf_dual.jl:556-617 */
 int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, int trimmed, double* out);
 /* updateYHat!: YHat (L x M_local, leading dimension ld) = BHat*AHat', src/vbmf.jl:120 */
@@ -264,6 +272,38 @@ int vbmf_b200_dual_run(vbmf_b200_ctx* ctx, vbmf_b200_dual_state* st, int64_t nit
 /* vbmf_trial!(Y, params, niter; eps, diag_var, full_cov, est_priors, est_cb)   src/vbmf_trial.jl:528 */
 int vbmf_b200_trial_run(vbmf_b200_ctx* ctx, vbmf_b200_trial_state* st, int64_t niter, double eps, int diag_var, int full_cov,
                         int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
+
+/* ---- several GPUs from ONE host process ---- */
+/* The reference is a single Julia process making plain calls (src/vbmf.jl:175,238; src/vbmf_sparse.jl:344; src/vbmf_dual.jl:455),
+ * so the drop-in must reach the column-sharded path without one process per GPU.  A multi-device context owns one ordinary
+ * context per device (communicators from ncclCommInitAll) and drives them with one host thread per device inside the library.
+ * Y and the state structs are the caller's FULL-SIZE host arrays (M = all columns, global 1-based labels); the library splits
+ * the columns contiguously (device i gets [offset_i, offset_i + n_i), near-equal) and scatters / gathers AHat and the
+ * per-element vectors itself.  Results equal the single-device ones up to the summation order of the all-reduce.
+ * devices == NULL: devices 0 .. ndev-1; ndev <= 0: all visible devices. */
+typedef struct vbmf_b200_mctx vbmf_b200_mctx;
+int vbmf_b200_mctx_create(int ndev, const int* devices, vbmf_b200_mctx** out);
+int vbmf_b200_mctx_destroy(vbmf_b200_mctx* mctx);
+int vbmf_b200_mctx_ndev(vbmf_b200_mctx* mctx);
+/* borrow the context of device i (valid until mctx_destroy), e.g. for vbmf_b200_ctx_profile */
+int vbmf_b200_mctx_ctx(vbmf_b200_mctx* mctx, int i, vbmf_b200_ctx** out);
+/* column range of device i after attach / synth */
+int vbmf_b200_mctx_shard(vbmf_b200_mctx* mctx, int i, int64_t* col_offset, int64_t* n_cols);
+/* Y: L x M column-major host matrix (all columns); every device uploads its own column range in parallel */
+int vbmf_b200_mctx_attach_Y(vbmf_b200_mctx* mctx, const double* Y, int64_t L, int64_t M, int64_t ldY);
+int vbmf_b200_mctx_synth_Y(vbmf_b200_mctx* mctx, int64_t L, int64_t M, int rank, double noise, uint64_t seed);
+int vbmf_b200_mctx_trYTY(vbmf_b200_mctx* mctx, double* out);
+/* vbmf!, vbmf_sparse!, vbmf_dual!, vbmf_trial! on the attached Y: same arguments as the one-call drop-ins above */
+int vbmf_b200_mctx_dense_run(vbmf_b200_mctx* mctx, vbmf_b200_dense_state* st, int64_t niter, double eps, int est_covs, int est_var,
+                             int norm_mode, int64_t* iters, double* d);
+int vbmf_b200_mctx_sparse_run(vbmf_b200_mctx* mctx, vbmf_b200_sparse_state* st, int64_t niter, double eps, int diag_var,
+                              int full_cov, int est_cb, int norm_mode, int64_t* iters, double* d);
+int vbmf_b200_mctx_dual_run(vbmf_b200_mctx* mctx, vbmf_b200_dual_state* st, int64_t niter, double eps, int diag_var, int full_cov,
+                            int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
+int vbmf_b200_mctx_trial_run(vbmf_b200_mctx* mctx, vbmf_b200_trial_state* st, int64_t niter, double eps, int diag_var, int full_cov,
+                             int est_priors, int est_cb, int norm_mode, int64_t* iters, double* d);
+/* lowerBound / lowerBoundTrimmed of a full-size sparse / dual / trial state (kind = VBMF_B200_SPARSE / _DUAL / _TRIAL) */
+int vbmf_b200_mctx_lower_bound(vbmf_b200_mctx* mctx, int kind, void* state, double trim, int trimmed, double* out);
 
 #ifdef __cplusplus
 }

@@ -228,3 +228,47 @@ def test_contraction_planner_host_logic(vb):
         for work in (-(-M // 128) * S1, -(-L // 128) * S2):
             assert work / (-(-work // cap) * cap) >= 0.95, (L, M, H, work, cap)
     assert lib.vbmf_b200_plan_contractions(10, 10, 129, 148, C.cast(out, C.c_void_p)) != 0      # H > 128 is refused
+
+
+def test_logging_mirror_ignores_non_numeric_fields(vb):
+    """A second logdir run on the same params must not trip over the trajectory stored by the first one (params.log) or over
+    other non-numeric attributes; `failed` is not logged either."""
+    p = vb.vbmf_init(np.zeros((4, 6)), 2, rng=np.random.default_rng(0))
+    log = vb.create_log(p)
+    p.log, p.failed, p.note = {"x": [1]}, False, "text"
+    log2 = vb.create_log(p)
+    assert set(log2) == set(log) and "log" not in log2 and "failed" not in log2 and "note" not in log2
+    vb.update_log_(log2, p)
+    assert all(len(v) == 2 for v in log2.values())
+
+
+def test_a_copies_mismatch_detection(vb):
+    """params.AHat = X without touching ATVecHat (examples/toy_data.jl:54): the step functions pick the copy their reference
+    counterpart reads; lowerBound refuses the mixed state (needs no device: raised before any library call)."""
+    from vbmf_b200 import api
+    Y = np.random.default_rng(0).standard_normal((5, 7))
+    p = vb.vbmf_sparse_init(Y, 3, rng=np.random.default_rng(1))
+    assert not api._a_mismatch(p)
+    p.AHat = np.asfortranarray(p.AHat + 1.0)
+    assert api._a_mismatch(p)
+    with pytest.raises(vb.VBMFError, match="disagree"):
+        vb.lowerBound(Y, p)
+    assert not api._a_mismatch(vb.vbmf_init(Y, 3))
+
+
+def test_sharded_context_refuses_ambiguous_y(vb):
+    """_ctx_for on a world > 1 context: a host Y of another shape than the attached shard cannot be placed."""
+    from vbmf_b200 import api
+
+    class FakeCtx:
+        world, L, M, M_global, col_offset = 2, 5, 4, 8, 4
+        attached = None
+
+        def attach(self, Y, M_global=None, col_offset=0):
+            self.attached = (Y.shape, M_global, col_offset)
+    c = FakeCtx()
+    with pytest.raises(vb.VBMFError, match="sharded context"):
+        api._ctx_for(np.zeros((5, 8)), c)
+    api._ctx_for(np.zeros((5, 4)), c)
+    assert c.attached == ((5, 4), 8, 4)          # the shard keeps its global geometry
+    assert api._ctx_for(None, c) is c

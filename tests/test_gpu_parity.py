@@ -138,7 +138,9 @@ def test_dense_convergence_iteration(G, ctx):
         assert it_o < 500
         assert q.iterations == it_o
         assert abs(q.d - d_o) <= 1e-7 * d_o
-        G.compare(q, po, max(TOL, 100 * G.sensitivity(lambda s_: vo.vbmf_run(Y, s_, 500, eps=eps, est_covs=True, est_var=True, norm=norm), p, ["AHat", "BHat"])))
+        # free-running for tens of iterations: bounded by the trajectory's own sensitivity over the compared fields
+        G.compare(q, po, max(TOL, 100 * G.sensitivity(lambda s_: vo.vbmf_run(Y, s_, 500, eps=eps, est_covs=True, est_var=True, norm=norm), p,
+                                                      G.FIELDS["dense"])))
 
 
 SPARSE_CASES = [

@@ -163,3 +163,129 @@ def warp_block_gj_sym(S, v, NT):
                 out[8 * tj + 2 * J, 8 * ti + R] = c[ti, tj, :, 0]
                 out[8 * tj + 2 * J + 1, 8 * ti + R] = c[ti, tj, :, 1]
     return out, vv[:N]
+
+
+def warp_block_gj_neg(S, v, NT):
+    """Same as warp_block_gj_sym in the sign convention the CUDA code uses: tiles hold T = -S, the panel sweeps run on
+    y = -x, the update is T += (Y - E)(Y0 + E)' and +2 on the pivot block's diagonal.  Returns (inv(S), inv(S) @ v)."""
+    N = 8 * NT
+    c = np.zeros((NT, NT, 32, 2))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            c[ti, tj, :, 0] = -S[8 * ti + R, 8 * tj + 2 * J]
+            c[ti, tj, :, 1] = -S[8 * ti + R, 8 * tj + 2 * J + 1]
+    Ps = np.zeros(N * 4); Ws = np.zeros(N * 4)
+    vv = np.zeros(32); vv[:N] = v
+    for s in range(2 * NT):
+        tk, half = s >> 1, s & 1
+        for t in range(NT):
+            for l in range(32):
+                if t <= tk:
+                    if (J[l] >> 1) == half:
+                        Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 0] = c[t, tk, l, 0]
+                        Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 1] = c[t, tk, l, 1]
+                else:
+                    if (R[l] >> 2) == half:
+                        Ps[(8 * t + 2 * J[l] + 0) * 4 + (R[l] & 3)] = c[tk, t, l, 0]
+                        Ps[(8 * t + 2 * J[l] + 1) * 4 + (R[l] & 3)] = c[tk, t, l, 1]
+        Yv = np.zeros((32, 4))
+        for l in range(N):
+            Yv[l] = Ps[l * 4:l * 4 + 4]
+        for cc in range(4):
+            kc = 4 * s + cc
+            pr = Yv[kc].copy(); prv = vv[kc]
+            idv = 1.0 / (-pr[cc])
+            for l in range(N):
+                g = (idv - 1.0) if l == kc else Yv[l, cc] * idv
+                for q in range(4):
+                    if q != cc:
+                        Yv[l, q] = Yv[l, q] + g * pr[q]
+                vv[l] = vv[l] + g * prv
+                Yv[l, cc] = idv if l == kc else g
+        for l in range(N):
+            Ws[l * 4:l * 4 + 4] = Yv[l]
+        pf = np.zeros((NT, 32)); wf = np.zeros((NT, 32))
+        for t in range(NT):
+            pf[t] = Ps[(8 * t + R) * 4 + J]
+            wf[t] = Ws[(8 * t + R) * 4 + J]
+        sel = R == 4 * half + J
+        pf[tk][sel] += 1.0
+        wf[tk][sel] -= 1.0
+        for ti in range(NT):
+            for tj in range(ti, NT):
+                c[ti, tj] = dmma(c[ti, tj], wf[ti], pf[tj])
+        for l in range(32):
+            r = R[l]
+            if (r >> 2) == half and J[l] == (r >> 1):
+                c[tk, tk, l, r & 1] += 2.0
+    out = np.zeros((N, N))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
+            out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
+            if tj > ti:
+                out[8 * tj + 2 * J, 8 * ti + R] = c[ti, tj, :, 0]
+                out[8 * tj + 2 * J + 1, 8 * ti + R] = c[ti, tj, :, 1]
+    return out, vv[:N]
+
+
+def cta_block_gj(S, NTD, nsteps=None):
+    """CTA-level variant for the single H x H inverses (H up to 128): full tile grid NTD x NTD of T = -S, every warp forms
+    inv(D) of the 4 x 4 pivot block itself and builds its A fragment as Y0[row, :] @ inv(D)[:, j] (+ inv(D)[c][j] on pivot rows);
+    B fragment = Y0 + E.  Returns inv(S)."""
+    N = 8 * NTD
+    c = np.zeros((NTD, NTD, 32, 2))
+    for ti in range(NTD):
+        for tj in range(NTD):
+            c[ti, tj, :, 0] = -S[8 * ti + R, 8 * tj + 2 * J]
+            c[ti, tj, :, 1] = -S[8 * ti + R, 8 * tj + 2 * J + 1]
+    nsteps = 2 * NTD if nsteps is None else nsteps
+    for s in range(nsteps):
+        tk, half = s >> 1, s & 1
+        Ps = np.zeros(N * 4)
+        for t in range(NTD):                    # owners of tile (t, tk) publish their rows of the panel
+            for l in range(32):
+                if (J[l] >> 1) == half:
+                    Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 0] = c[t, tk, l, 0]
+                    Ps[(8 * t + R[l]) * 4 + 2 * (J[l] & 1) + 1] = c[t, tk, l, 1]
+        D = -Ps[4 * (4 * s):4 * (4 * s) + 16].reshape(4, 4)
+        a = D.copy()
+        for cc in range(4):                     # 4 x 4 in-register sweep: a -> -inv(D)
+            idv = 1.0 / a[cc, cc]
+            rowc = a[cc].copy()
+            for i in range(4):
+                if i != cc:
+                    f = a[i, cc] * idv
+                    for q in range(4):
+                        if q != cc:
+                            a[i, q] -= f * rowc[q]
+                    a[i, cc] = f
+            for q in range(4):
+                if q != cc:
+                    a[cc, q] = rowc[q] * idv
+            a[cc, cc] = -idv
+        Dinv = -a
+        for ti in range(NTD):
+            wf = np.zeros(32)
+            for l in range(32):
+                row = 8 * ti + R[l]
+                y0 = Ps[row * 4:row * 4 + 4]
+                val = float(y0 @ Dinv[:, J[l]])
+                if (row >> 2) == s:
+                    val += Dinv[row & 3, J[l]]
+                wf[l] = val
+            for tj in range(NTD):
+                pf = Ps[(8 * tj + R) * 4 + J].copy()
+                rows = 8 * tj + R
+                pf[rows == 4 * s + J] += 1.0
+                c[ti, tj] = dmma(c[ti, tj], wf, pf)
+        for l in range(32):
+            r = R[l]
+            if (r >> 2) == half and J[l] == (r >> 1):
+                c[tk, tk, l, r & 1] += 2.0
+    out = np.zeros((N, N))
+    for ti in range(NTD):
+        for tj in range(NTD):
+            out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
+            out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
+    return out

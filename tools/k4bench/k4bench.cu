@@ -36,7 +36,50 @@ static void inv_ld(const std::vector<double>& S, int H, std::vector<double>& out
     for (int e = 0; e < H * H; ++e) out[e] = (double)(-A[e]);
 }
 
+// k4bench hxh <H> [reps]: the single H x H inverse of the dense A update (SigmaA = sigma2*inv(B'B + L*SigmaB + sigma2*invCA))
+static int bench_hxh(int H, int reps) {
+    CK(cudaSetDevice(0));
+    if (kernels_init_device()) return 1;
+    const int L = 1000;
+    std::mt19937_64 rng(777);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::uniform_real_distribution<double> ud(0.0, 1.0);
+    const size_t HH = (size_t)H * H;
+    std::vector<double> B((size_t)(H + 7) * H), BtB(HH, 0.0), SB(HH, 0.0), iCA(HH, 0.0), S(HH), Si;
+    for (auto& x : B) x = nd(rng);
+    for (int a = 0; a < H; ++a) for (int b = 0; b < H; ++b) { double t = 0; for (int l = 0; l < H + 7; ++l) t += B[l * H + a] * B[l * H + b]; BtB[a * H + b] = t; }
+    for (int a = 0; a < H; ++a) { SB[a * H + a] = 1e-3 * ud(rng); iCA[a * H + a] = pow(10.0, -2.0 + 10.0 * ud(rng)); }
+    const double s2 = 0.37;
+    for (size_t e = 0; e < HH; ++e) S[e] = BtB[e] + (double)L * SB[e] + s2 * iCA[e];
+    inv_ld(S, H, Si);
+    Dev d; memset(&d, 0, sizeof(d));
+    d.kind = KIND_DENSE; d.L = L; d.ldB = L; d.Mloc = 10; d.Mglob = 10; d.H = H;
+    Scalars hs; memset(&hs, 0, sizeof(hs)); hs.active = 1; hs.sigma2 = s2;
+    double *dBtB, *dSB, *diCA, *dSA; Scalars* dsc;
+    CK(cudaMalloc(&dBtB, HH * 8)); CK(cudaMalloc(&dSB, HH * 8)); CK(cudaMalloc(&diCA, HH * 8)); CK(cudaMalloc(&dSA, HH * 8)); CK(cudaMalloc(&dsc, sizeof(Scalars)));
+    CK(cudaMemcpy(dBtB, BtB.data(), HH * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dSB, SB.data(), HH * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(diCA, iCA.data(), HH * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsc, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+    d.sc = dsc; d.BtB = dBtB; d.SigmaB = dSB; d.invCA = diCA; d.SigmaA = dSA;
+    cudaStream_t st; CK(cudaStreamCreate(&st));
+    for (int w = 0; w < 3; ++w) if (k_dense_sigmaA(st, d)) return 1;
+    CK(cudaStreamSynchronize(st));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+    for (int w = 0; w < reps; ++w) if (k_dense_sigmaA(st, d)) return 1;
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<double> hSA(HH);
+    CK(cudaMemcpy(hSA.data(), dSA, HH * 8, cudaMemcpyDeviceToHost));
+    double err = 0, mx = 0;
+    for (size_t e = 0; e < HH; ++e) { err = std::max(err, fabs(hSA[e] - s2 * Si[e])); mx = std::max(mx, fabs(s2 * Si[e])); }
+    printf("{\"kernel\": \"hxh (k_dense_sigmaA)\", \"mode\": \"%s\", \"H\": %d, \"us_per_launch\": %.2f, \"rel_err\": %.3g}\n",
+           getenv("VBMF_B200_HXH") ? getenv("VBMF_B200_HXH") : "dmma", H, ms / reps * 1e3, err / mx);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 2 && strcmp(argv[1], "hxh") == 0) return bench_hxh(atoi(argv[2]), argc > 3 ? atoi(argv[3]) : 50);
     const char* mode = argc > 1 ? argv[1] : "dmma";
     const int H = argc > 2 ? atoi(argv[2]) : 32, M = argc > 3 ? atoi(argv[3]) : 100000, reps = argc > 4 ? atoi(argv[4]) : 20;
     if (strcmp(mode, "reg") == 0) setenv("VBMF_B200_K4", "reg", 1);

@@ -60,6 +60,8 @@ class TrialState(C.Structure):
                 ("sigmaVecHat", p_f64), ("etaVec", p_f64), ("zetaVec", p_f64), ("YHat", p_f64), ("trYTY", c_f64)]
 
 
+ITER_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, c_i64, c_f64)     # vbmf_b200_iter_callback
+
 # every symbol include/vbmf_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vbmf_b200_version": (C.c_int, []),
@@ -94,6 +96,7 @@ SYMBOLS = {
     "vbmf_b200_trial_download": (C.c_int, [C.c_void_p, C.POINTER(TrialState)]),
     "vbmf_b200_solver_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vbmf_b200_solver_run": (C.c_int, [C.c_void_p, c_i64, c_f64, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_solver_run_logged": (C.c_int, [C.c_void_p, c_i64, c_f64, C.c_int, C.c_int, ITER_CALLBACK, C.c_void_p, p_i64, p_f64]),
     "vbmf_b200_solver_lower_bound": (C.c_int, [C.c_void_p, c_f64, C.c_int, p_f64]),
     "vbmf_b200_solver_yhat": (C.c_int, [C.c_void_p, p_f64, c_i64]),
     "vbmf_b200_batched_vbls": (C.c_int, [C.c_void_p, C.c_int, c_i64, C.POINTER(p_f64), C.POINTER(C.c_void_p), c_i64, C.c_int]),
@@ -101,6 +104,20 @@ SYMBOLS = {
     "vbmf_b200_sparse_run": (C.c_int, [C.c_void_p, C.POINTER(SparseState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
     "vbmf_b200_dual_run": (C.c_int, [C.c_void_p, C.POINTER(DualState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
     "vbmf_b200_trial_run": (C.c_int, [C.c_void_p, C.POINTER(TrialState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    # several GPUs from one host process (csrc/multi.cu)
+    "vbmf_b200_mctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vbmf_b200_mctx_destroy": (C.c_int, [C.c_void_p]),
+    "vbmf_b200_mctx_ndev": (C.c_int, [C.c_void_p]),
+    "vbmf_b200_mctx_ctx": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "vbmf_b200_mctx_shard": (C.c_int, [C.c_void_p, C.c_int, p_i64, p_i64]),
+    "vbmf_b200_mctx_attach_Y": (C.c_int, [C.c_void_p, p_f64, c_i64, c_i64, c_i64]),
+    "vbmf_b200_mctx_synth_Y": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_int, c_f64, C.c_uint64]),
+    "vbmf_b200_mctx_trYTY": (C.c_int, [C.c_void_p, p_f64]),
+    "vbmf_b200_mctx_dense_run": (C.c_int, [C.c_void_p, C.POINTER(DenseState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_mctx_sparse_run": (C.c_int, [C.c_void_p, C.POINTER(SparseState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_mctx_dual_run": (C.c_int, [C.c_void_p, C.POINTER(DualState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_mctx_trial_run": (C.c_int, [C.c_void_p, C.POINTER(TrialState), c_i64, c_f64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p_i64, p_f64]),
+    "vbmf_b200_mctx_lower_bound": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_f64, C.c_int, p_f64]),
 }
 
 _lib = None

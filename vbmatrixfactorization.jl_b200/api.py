@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib as L_
 
 __all__ = [
-    "Context", "default_context", "shard_columns",
+    "Context", "MultiContext", "default_context", "shard_columns",
     "vbmf_parameters", "vbmf_sparse_parameters", "vbmf_dual_parameters", "vbmf_trial_parameters", "vbmf_trial_init", "vbmf_trial_", "vbmf_trial",
     "vbmf_init", "vbmf_", "vbmf", "vbmf_sparse_init", "vbmf_sparse_", "vbmf_sparse", "vbmf_dual_init", "vbmf_dual_",
     "vbmf_dual", "updateA_", "updateB_", "updateCA_", "updateCB_", "updateSigma2_", "updateSigma_", "updateYHat_",
@@ -154,6 +154,65 @@ class Context:
         na, nb = C.c_int64(), C.c_int64()
         L_.check(self.lib.vbmf_b200_ctx_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return {"k1_ms": a.value, "k1_launches": na.value, "k2_ms": b.value, "k2_launches": nb.value}
+
+
+class MultiContext:
+    """Several GPUs driven from THIS process (vbmf_b200_mctx): the reference is one Julia process making plain calls, so the
+    column-sharded path must be reachable without one process per GPU.  Y and the parameter objects are the full-size host
+    arrays; the library splits the columns over the devices, runs one host thread per device and gathers the results.
+    Pass it as `ctx=` to vbmf_ / vbmf_sparse_ / vbmf_dual_ / vbmf_trial_ / lowerBound*."""
+
+    def __init__(self, devices=None):
+        self.lib = L_.load()
+        h = C.c_void_p()
+        if devices is None:
+            L_.check(self.lib.vbmf_b200_mctx_create(0, None, C.byref(h)))
+        else:
+            devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+            L_.check(self.lib.vbmf_b200_mctx_create(len(devices), devs, C.byref(h)))
+        self.h = h
+        self.ndev = self.lib.vbmf_b200_mctx_ndev(h)
+        self.world = 1          # one process: the sharding is internal
+        self.L = self.M = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vbmf_b200_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def attach(self, Y, **_):
+        Y = _f(Y)
+        if Y.ndim != 2:
+            raise ValueError("Y must be a matrix")
+        Lr, M = Y.shape
+        L_.check(self.lib.vbmf_b200_mctx_attach_Y(self.h, _ptr(Y), Lr, M, max(Lr, 1)))
+        self.L, self.M = Lr, M
+
+    def synth(self, Lr, M, rank=8, noise=0.1, seed=20260101):
+        L_.check(self.lib.vbmf_b200_mctx_synth_Y(self.h, Lr, M, rank, noise, seed))
+        self.L, self.M = Lr, M
+
+    def trYTY(self):
+        v = C.c_double()
+        L_.check(self.lib.vbmf_b200_mctx_trYTY(self.h, C.byref(v)))
+        return v.value
+
+    def shard(self, i):
+        off, n = C.c_int64(), C.c_int64()
+        L_.check(self.lib.vbmf_b200_mctx_shard(self.h, i, C.byref(off), C.byref(n)))
+        return off.value, n.value
+
+    def device_context(self, i):
+        """Borrowed handle of device i's context (profiling)."""
+        h = C.c_void_p()
+        L_.check(self.lib.vbmf_b200_mctx_ctx(self.h, i, C.byref(h)))
+        return h
 
 
 _default_ctx = {}
@@ -475,6 +534,9 @@ class Solver:
     """Device-resident state of one problem (vbmf_b200_solver): upload once, step / run many times, download."""
 
     def __init__(self, ctx, params, keep_blocks=False):
+        if isinstance(ctx, MultiContext):
+            raise VBMFError("step-level calls, logging and vbls_ hold device-resident state of ONE context: use a single-device Context "
+                            "(the multi-device context offers the whole-loop drivers and lowerBound)")
         self.ctx, self.lib = ctx, ctx.lib
         p = params
         if (p.L, p.M) != (ctx.L, ctx.M):
@@ -546,6 +608,11 @@ def _flags(diag_var=False, full_cov=False, est_cb=False, est_priors=False, est_c
             (L_.EST_PRIORS if est_priors else 0) | (L_.EST_COVS if est_covs else 0) | (L_.EST_VAR if est_var else 0))
 
 
+def _run_call(ctx, name):
+    """The one-call drop-in of the single-device context or its multi-device twin."""
+    return getattr(ctx.lib, ("vbmf_b200_mctx_" if isinstance(ctx, MultiContext) else "vbmf_b200_") + name)
+
+
 def _verb(verb, it, d):
     if verb:
         print("Factorization finished after ", it, " iterations, eps = ", d)
@@ -564,7 +631,7 @@ def vbmf_(Y, params, niter, eps=1e-6, est_covs=False, est_var=False, verb=False,
     ctx = _ctx_for(Y, ctx)
     st = _dense_struct(params, yhat)
     it, d = C.c_int64(), C.c_double()
-    _not_pd(L_.check(ctx.lib.vbmf_b200_dense_run(ctx.h, C.byref(st), int(niter), float(eps), int(est_covs), int(est_var), _NORMS[norm],
+    _not_pd(L_.check(_run_call(ctx, "dense_run")(ctx.h, C.byref(st), int(niter), float(eps), int(est_covs), int(est_var), _NORMS[norm],
                                          C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations, params.d = it.value, d.value
@@ -589,7 +656,7 @@ def vbmf_sparse_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, ver
     ctx = _ctx_for(Y, ctx)
     st = _sparse_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
-    _not_pd(L_.check(ctx.lib.vbmf_b200_sparse_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_cb),
+    _not_pd(L_.check(_run_call(ctx, "sparse_run")(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_cb),
                                           _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.AHat = _f(params.AHat)
@@ -617,7 +684,7 @@ def vbmf_dual_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=
     ctx = _ctx_for(Y, ctx)
     st = _dual_struct(params, yhat, keep_blocks)
     it, d = C.c_int64(), C.c_double()
-    _not_pd(L_.check(ctx.lib.vbmf_b200_dual_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
+    _not_pd(L_.check(_run_call(ctx, "dual_run")(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
                                         int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations = it.value
@@ -633,12 +700,18 @@ def vbmf_dual(Y, params_in, niter, **kw):
 
 
 def vbmf_trial_(Y, params, niter, eps=1e-6, diag_var=False, full_cov=False, verb=False, est_priors=True, est_cb=True,
-                norm="spectral", ctx=None, keep_blocks=False, yhat=True):
+                norm="spectral", ctx=None, keep_blocks=False, yhat=True, logdir="", desc=""):
     """`vbmf_trial!` src/vbmf_trial.jl:528-604: mutates params, returns d."""
+    if logdir:
+        it, d, params.log = _run_logged(Y, params, niter, eps, _flags(diag_var=diag_var, full_cov=full_cov, est_cb=est_cb,
+                                                                      est_priors=est_priors), norm, ctx, logdir, desc, keep_blocks)
+        params.iterations = it
+        _verb(verb, it, d)
+        return d
     ctx = _ctx_for(Y, ctx)
     st = _trial_struct(params, yhat, keep_blocks, getattr(params, "_m2_local", None))
     it, d = C.c_int64(), C.c_double()
-    _not_pd(L_.check(ctx.lib.vbmf_b200_trial_run(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
+    _not_pd(L_.check(_run_call(ctx, "trial_run")(ctx.h, C.byref(st), int(niter), float(eps), int(diag_var), int(full_cov), int(est_priors),
                                          int(est_cb), _NORMS[norm], C.byref(it), C.byref(d)), allow=(-2,)), params)
     _readback(params, st)
     params.iterations = it.value
@@ -761,6 +834,8 @@ def lowerBound(Y, params, ctx=None):
     if _a_mismatch(params):
         raise VBMFError("lowerBound: params.AHat and params.ATVecHat disagree (the reference would mix the two copies); set both")
     ctx = _ctx_for(Y, ctx)
+    if isinstance(ctx, MultiContext):
+        return _multi_lower_bound(ctx, params, 0.0, False)
     s = Solver(ctx, params)
     try:
         s.upload(params)
@@ -774,12 +849,23 @@ def lowerBoundTrimmed(Y, params, trim=1e-1, ctx=None):
     if _a_mismatch(params):
         raise VBMFError("lowerBoundTrimmed: params.AHat and params.ATVecHat disagree (the reference would mix the two copies); set both")
     ctx = _ctx_for(Y, ctx)
+    if isinstance(ctx, MultiContext):
+        return _multi_lower_bound(ctx, params, trim, True)
     s = Solver(ctx, params)
     try:
         s.upload(params)
         return s.lower_bound(trim, True)
     finally:
         s.close()
+
+
+def _multi_lower_bound(ctx, params, trim, trimmed):
+    if params.kind == L_.DENSE:
+        raise VBMFError("the dense solver has no lowerBound (the reference defines none)")
+    st = _struct(params, False, False)
+    v = C.c_double()
+    L_.check(ctx.lib.vbmf_b200_mctx_lower_bound(ctx.h, params.kind, C.byref(st), float(trim), 1 if trimmed else 0, C.byref(v)))
+    return v.value
 
 
 def vbls_(Y, params, niter, diag_var=False, full_cov=False, ctx=None):
@@ -923,18 +1009,28 @@ def _run_logged(Y, params, niter, eps, flags, norm, ctx, logdir, desc, keep_bloc
     ctx = _ctx_for(Y, ctx)
     s = Solver(ctx, params, keep_blocks=keep_blocks)
     log = create_log(params)
-    it_total, d = 0, eps + 1.0
-    try:
-        s.upload(params)
-        while it_total < niter and d > eps:
-            n, d = s.run(1, eps=eps, flags=flags, norm=norm)
-            if n == 0:
-                break
-            it_total += n
+    err = []
+
+    def on_iter(_user, _solver, _done, _d):          # vbmf_b200_iter_callback: runs on this thread after every iteration
+        try:
             s.download(params)
             update_log_(log, params)
+            return 0
+        except Exception as e:                       # never raise across the C ABI
+            err.append(e)
+            return 1
+    cb = L_.ITER_CALLBACK(on_iter)
+    it, d = C.c_int64(), C.c_double()
+    try:
+        s.upload(params)
+        rc = L_.check(ctx.lib.vbmf_b200_solver_run_logged(s.h, int(niter), float(eps), flags, _NORMS[norm], cb, None, C.byref(it), C.byref(d)),
+                      allow=(-2,))
+        if err:
+            raise err[0]
+        _not_pd(rc, params)
         s.download(params, want_yhat=True)
     finally:
         s.close()
+    it_total, d = it.value, d.value
     save_log(log, Y if Y is not None else np.zeros((0, 0)), {}, logdir, desc)
     return it_total, d, log

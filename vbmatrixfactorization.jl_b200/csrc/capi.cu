@@ -33,6 +33,7 @@ struct NcclApi {
     void* handle = nullptr;
     int (*GetUniqueId)(NcclUniqueId*) = nullptr;
     int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -50,6 +51,7 @@ static int load_nccl() {
     if (!h) { set_error("NCCL not found (set VBMF_B200_NCCL_LIB): %s", dlerror()); return -1; }
     g_nccl.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommInitAll = (int (*)(void**, int, const int*))dlsym(h, "ncclCommInitAll");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
@@ -134,8 +136,9 @@ extern "C" int vbmf_b200_nccl_unique_id(void* id128) {
     return 0;
 }
 
-extern "C" int vbmf_b200_ctx_create(int device, int rank, int world, const void* nccl_id128, void* cuda_stream,
-                                    vbmf_b200_ctx** out) {
+// comm_in: an already initialised communicator for this rank (single-process multi-device contexts, ncclCommInitAll) or NULL
+static int ctx_create_impl(int device, int rank, int world, const void* nccl_id128, void* comm_in, void* cuda_stream,
+                           vbmf_b200_ctx** out) {
     if (out == nullptr) { set_error("ctx_create: out is NULL"); return -1; }
     *out = nullptr;
     int ndev = 0;
@@ -164,16 +167,35 @@ extern "C" int vbmf_b200_ctx_create(int device, int rank, int world, const void*
     const char* g = getenv("VBMF_B200_GEMM");
     c->simt = (g != nullptr && strcmp(g, "simt") == 0);
     if (c->world > 1) {
-        if (nccl_id128 == nullptr) { set_error("world > 1 needs the NCCL unique id of rank 0"); delete c; return -1; }
-        if (load_nccl()) { delete c; return -1; }
-        NcclUniqueId id;
-        memcpy(&id, nccl_id128, 128);
-        int r = g_nccl.CommInitRank(&c->comm, c->world, id, rank);
-        if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); delete c; return -1; }
+        if (comm_in != nullptr) c->comm = comm_in;
+        else {
+            if (nccl_id128 == nullptr) { set_error("world > 1 needs the NCCL unique id of rank 0"); delete c; return -1; }
+            if (load_nccl()) { delete c; return -1; }
+            NcclUniqueId id;
+            memcpy(&id, nccl_id128, 128);
+            int r = g_nccl.CommInitRank(&c->comm, c->world, id, rank);
+            if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); delete c; return -1; }
+        }
     }
     if (cudaMalloc(&c->d_tr, 64) != cudaSuccess) { set_error("cudaMalloc failed"); delete c; return -1; }
     *out = c;
     return 0;
+}
+extern "C" int vbmf_b200_ctx_create(int device, int rank, int world, const void* nccl_id128, void* cuda_stream,
+                                    vbmf_b200_ctx** out) {
+    return ctx_create_impl(device, rank, world, nccl_id128, nullptr, cuda_stream, out);
+}
+// used by the single-process multi-device contexts (csrc/multi.cu)
+namespace vb {
+int ctx_create_with_comm(int device, int rank, int world, void* comm, vbmf_b200_ctx** out) {
+    return ctx_create_impl(device, rank, world, nullptr, comm, nullptr, out);
+}
+int nccl_comm_init_all(void** comms, int ndev, const int* devs) {
+    if (load_nccl()) return -1;
+    if (!g_nccl.CommInitAll) { set_error("the NCCL library has no ncclCommInitAll"); return -1; }
+    VB_NCCL_OK(g_nccl.CommInitAll(comms, ndev, devs));
+    return 0;
+}
 }
 
 static void ctx_free_Y(vbmf_b200_ctx* c) {
@@ -1033,6 +1055,28 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
     if (dout) *dout = s->h_sc.d;
     if (s->h_sc.chol_fail) { set_error("a posterior precision matrix was not positive definite (NaN written, loop ended)"); return -2; }
     return 0;
+}
+
+// The reference's loop with `update_log!(log, params)` after every iteration (src/vbmf.jl:206-208, src/vbmf_sparse.jl:385-387,
+// src/vbmf_dual.jl:505-507): one device iteration at a time, the state stays resident, the callback downloads what it logs.
+extern "C" int vbmf_b200_solver_run_logged(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode,
+                                           vbmf_b200_iter_callback cb, void* user, int64_t* iters, double* dout) {
+    if (!s) { set_error("NULL solver"); return -1; }
+    int64_t done = 0;
+    double d = eps + 1.0;                                   // src/vbmf.jl:189
+    int rc = 0;
+    while (done < niter && d > eps) {                       // while (i <= niter) && (d > eps)
+        int64_t n = 0;
+        rc = vbmf_b200_solver_run(s, 1, eps, flags, norm_mode, &n, &d);
+        if (rc != 0 && rc != -2) return rc;
+        if (n == 0) break;
+        done += n;
+        if (cb != nullptr && cb(user, s, done, d) != 0) break;   // non-zero return: stop early (the state stays valid)
+        if (rc == -2) break;
+    }
+    if (iters) *iters = done;
+    if (dout) *dout = d;
+    return rc;
 }
 
 extern "C" int vbmf_b200_solver_lower_bound(vbmf_b200_solver* s, double trim, int trimmed, double* out) {

@@ -455,7 +455,171 @@ __global__ void __launch_bounds__(1024, 1) hxh_kernel(Dev d, int mode, int diag_
         if (live && i < H) out[i * H + j] = ok ? scale * (-a[q] * sbuf[i] * sj) : nan("");
     }
 }
+// Tensor-core versions of the same three inverses (blocked rank-4 Gauss-Jordan, see linalg.cuh::warp_block_gj_sym): the
+// register sweep above pays one CTA barrier per pivot (58 us at H = 64, 400 us at H = 128, all of it on the critical path of
+// every iteration and replicated on every GPU); here a step handles four pivots with one barrier and one DMMA per tile.
+__device__ __forceinline__ double hxh_elem(const Dev& d, int mode, int diag_var, int i, int j) {
+    const Scalars* sc = d.sc;
+    const int e = i * d.H + j;
+    if (mode == 0) return d.BtB[e] + (double)d.L * d.SigmaB[e] + sc->sigma2 * d.invCA[e];
+    if (mode == 1) return (d.packed + packed_ata(d))[e] + (double)d.Mglob * d.SigmaA[e] + sc->sigma2 * d.invCB[e];
+    const double c = diag_var ? sc->meanSigmaVec : sc->sigmaHat;
+    return ((i == j) ? d.CBv[i] : 0.0) + c * ((d.packed + packed_ata(d))[e] + (d.packed + packed_sa(d))[e]);
+}
+// H <= 32: one warp, upper-triangular tiles
+template <int NT>
+__global__ void __launch_bounds__(32, 1) hxh_warp_kernel(Dev d, int mode, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    constexpr int N = 8 * NT, NTRI = NT * (NT + 1) / 2;
+    __shared__ __align__(16) double Ps[4 * N], Ws[4 * N], sv[32];
+    const int H = d.H, lane = threadIdx.x, r = lane >> 2, j = lane & 3;
+    if (mode == 2) for (int e = lane; e < H * H; e += 32) d.SigmaA[e] = (d.packed + packed_sa(d))[e];
+    sv[lane] = lane < H ? rsqrt(hxh_elem(d, mode, diag_var, lane, lane)) : 1.0;
+    __syncwarp();
+    double c[NTRI][2];
+#pragma unroll
+    for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < NT; ++tj)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int row = 8 * ti + r, col = 8 * tj + 2 * j + k;
+                const double v = (row < H && col < H) ? hxh_elem(d, mode, diag_var, row, col) : (row == col ? 1.0 : 0.0);
+                c[tri_idx(ti, tj, NT)][k] = -v * (sv[row] * sv[col]);
+            }
+    double dummy = 0.0;
+    const bool ok = warp_block_gj_sym<NT>(c, dummy, lane, Ps, Ws);
+    if (!ok && lane == 0) d.sc->chol_fail = 1;
+    double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
+    const double scale = (mode == 2) ? 1.0 : d.sc->sigma2;
+    __syncwarp();
+#pragma unroll
+    for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < NT; ++tj)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int row = 8 * ti + r, col = 8 * tj + 2 * j + k;
+                if (row < H && col < H) {
+                    const double v = ok ? scale * (c[tri_idx(ti, tj, NT)][k] * (sv[row] * sv[col])) : nan("");
+                    out[row * H + col] = v;
+                    if (ti != tj) out[col * H + row] = v;
+                }
+            }
+}
+// 32 < H <= 128: 16 warps, the full NTD x NTD tile grid spread over the warps (warp w: tile row w / WPR, TPW tile columns).
+// Per block step: the owners of the pivot column block publish the panel (double buffered -> ONE barrier per step), every
+// warp inverts the 4 x 4 pivot block D itself (registers; identical in all warps, so `ok` needs no communication), forms
+// its A fragment as Y0[row, :]*inv(D)[:, j] (+ inv(D)[c][j] on the pivot rows) and issues TPW DMMAs.
+template <int NTD, int TPW>
+__global__ void __launch_bounds__(512, 1) hxh_dmma_kernel(Dev d, int mode, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    constexpr int N = 8 * NTD, WPR = NTD / TPW;
+    static_assert(NTD * WPR == 16, "16 warps cover the tile grid");
+    __shared__ __align__(16) double Ps[2][4 * N];
+    __shared__ double sv[N];
+    const int H = d.H, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+    const int ti = warp / WPR, tj0 = (warp % WPR) * TPW;
+    if (mode == 2) for (int e = threadIdx.x; e < H * H; e += 512) d.SigmaA[e] = (d.packed + packed_sa(d))[e];
+    for (int t = threadIdx.x; t < N; t += 512) sv[t] = t < H ? rsqrt(hxh_elem(d, mode, diag_var, t, t)) : 1.0;
+    __syncthreads();
+    const int row = 8 * ti + r;
+    double c[TPW][2];
+#pragma unroll
+    for (int u = 0; u < TPW; ++u)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int col = 8 * (tj0 + u) + 2 * j + k;
+            const double v = (row < H && col < H) ? hxh_elem(d, mode, diag_var, row, col) : (row == col ? 1.0 : 0.0);
+            c[u][k] = -v * (sv[row] * sv[col]);
+        }
+    const int nsteps = (H + 3) >> 2;
+    bool ok = true;
+    // panel of step 0
+#pragma unroll
+    for (int u = 0; u < TPW; ++u)
+        if (tj0 + u == 0 && (j >> 1) == 0) *reinterpret_cast<double2*>(&Ps[0][row * 4 + 2 * (j & 1)]) = make_double2(c[u][0], c[u][1]);
+    for (int s = 0; s < nsteps; ++s) {
+        __syncthreads();
+        const double* P = Ps[s & 1];
+        const int tk = s >> 1, half = s & 1;
+        // -D (4 x 4 pivot block of T = -S), swept in registers: a -> -inv(D)
+        double a[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 x0 = *reinterpret_cast<const double2*>(P + (4 * s + i) * 4), x1 = *reinterpret_cast<const double2*>(P + (4 * s + i) * 4 + 2);
+            a[i][0] = -x0.x; a[i][1] = -x0.y; a[i][2] = -x1.x; a[i][3] = -x1.y;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            ok = ok && pivot_ok(a[cc][cc]);
+            const double id = rcp_pos(a[cc][cc]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i != cc) {
+                    const double f = a[i][cc] * id;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q != cc) a[i][q] = fma(-f, a[cc][q], a[i][q]);
+                    a[i][cc] = f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q != cc) a[cc][q] *= id;
+            a[cc][cc] = -id;
+        }
+        // column j of -inv(D) for this lane
+        double aj[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aj[q] = j == 0 ? a[q][0] : j == 1 ? a[q][1] : j == 2 ? a[q][2] : a[q][3];
+        // A fragment: (Y - E)[row][j] = Y0[row, :]*inv(D)[:, j] (+ inv(D)[row - 4s][j] on a pivot row)
+        const double2 y0 = *reinterpret_cast<const double2*>(P + row * 4), y1 = *reinterpret_cast<const double2*>(P + row * 4 + 2);
+        double wsum = y0.x * aj[0];
+        wsum = fma(y0.y, aj[1], wsum); wsum = fma(y1.x, aj[2], wsum); wsum = fma(y1.y, aj[3], wsum);
+        if ((row >> 2) == s) { const int cr = row & 3; wsum += cr == 0 ? aj[0] : cr == 1 ? aj[1] : cr == 2 ? aj[2] : aj[3]; }
+        const double wf = -wsum;
+#pragma unroll
+        for (int u = 0; u < TPW; ++u) {
+            const int brow = 8 * (tj0 + u) + r;
+            double pf = P[brow * 4 + j];
+            if (brow == 4 * s + j) pf += 1.0;
+            dmma884(c[u], wf, pf);
+        }
+        if (ti == tk && (r >> 2) == half && j == (r >> 1)) {
+#pragma unroll
+            for (int u = 0; u < TPW; ++u) if (tj0 + u == tk) { if (r & 1) c[u][1] += 2.0; else c[u][0] += 2.0; }
+        }
+        // panel of the next step into the other buffer
+        if (s + 1 < nsteps) {
+            const int tkn = (s + 1) >> 1, halfn = (s + 1) & 1;
+#pragma unroll
+            for (int u = 0; u < TPW; ++u)
+                if (tj0 + u == tkn && (j >> 1) == halfn) *reinterpret_cast<double2*>(&Ps[(s + 1) & 1][row * 4 + 2 * (j & 1)]) = make_double2(c[u][0], c[u][1]);
+        }
+    }
+    if (!ok && threadIdx.x == 0) d.sc->chol_fail = 1;
+    double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
+    const double scale = (mode == 2) ? 1.0 : d.sc->sigma2;
+#pragma unroll
+    for (int u = 0; u < TPW; ++u)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int col = 8 * (tj0 + u) + 2 * j + k;
+            if (row < H && col < H) out[row * H + col] = ok ? scale * (c[u][k] * (sv[row] * sv[col])) : nan("");
+        }
+}
 static int hxh_launch(cudaStream_t st, const Dev& d, int mode, int dv) {
+    static const bool use_reg = getenv("VBMF_B200_HXH") != nullptr && strcmp(getenv("VBMF_B200_HXH"), "reg") == 0;
+    if (!use_reg) {
+        const int H = d.H;
+        if (H <= 8) hxh_warp_kernel<1><<<1, 32, 0, st>>>(d, mode, dv);
+        else if (H <= 16) hxh_warp_kernel<2><<<1, 32, 0, st>>>(d, mode, dv);
+        else if (H <= 24) hxh_warp_kernel<3><<<1, 32, 0, st>>>(d, mode, dv);
+        else if (H <= 32) hxh_warp_kernel<4><<<1, 32, 0, st>>>(d, mode, dv);
+        else if (H <= 64) hxh_dmma_kernel<8, 4><<<1, 512, 0, st>>>(d, mode, dv);
+        else hxh_dmma_kernel<16, 16><<<1, 512, 0, st>>>(d, mode, dv);
+        VB_LAUNCH_OK();
+        return 0;
+    }
     const int hh = d.H * d.H;
     // 1024 threads beat 512 / 256 (46 vs 62 vs ~100 us at H = 64): the sweep is latency bound, more warps hide it
     if (hh <= 1024) hxh_kernel<32><<<1, 1024, 0, st>>>(d, mode, dv);
@@ -816,17 +980,18 @@ __global__ void __launch_bounds__(256, 2) sparse_A_full_warp_kernel(Dev d, int d
     }
 }
 // H <= 32, tensor-core version: one warp per matrix, upper-triangular 8 x 8 tiles in DMMA accumulator registers, blocked
-// rank-4 Gauss-Jordan (linalg.cuh::warp_block_gj_sym).  The right-hand side p_m rides through the sweeps, the running sum of
-// Sigma_m stays in registers (tiles on and above the diagonal only).  Shared memory: G as accumulator-layout tiles (read once
-// per matrix with conflict-free 128-bit loads), 2.5 KB of scratch per warp.
-template <int NT, int MINB>
+// rank-4 Gauss-Jordan (linalg.cuh::warp_block_gj_sym).  The right-hand side p_m rides through the sweeps.  The running sum
+// of Sigma_m (tiles on and above the diagonal only) lives in registers (ACCS = false) or in per-warp shared memory
+// (ACCS = true: 40 registers less, one more CTA per SM).  Shared memory: G as accumulator-layout tiles (read once per matrix
+// with conflict-free 128-bit loads), 2.5 KB of scratch per warp.
+template <int NT, int MINB, bool ACCS>
 __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, int diag_var, int nwarps_total) {
     ACTIVE_OR_RETURN(d);
     constexpr int NTRI = NT * (NT + 1) / 2, N = 8 * NT, WPC = 4;
     extern __shared__ __align__(16) double wsm[];
     double* s_G = wsm;                                  // [NTRI][32][2]
     double* s_scr = s_G + NTRI * 64;                    // [WPC][4N + 4N + 32 + 32]
-    double* s_red = s_scr + WPC * (8 * N + 64);         // [WPC][NTRI][64] end-of-kernel reduction
+    double* s_red = s_scr + WPC * (8 * N + 64);         // [WPC][NTRI][64] running sums (ACCS) / end-of-kernel reduction
     const int H = d.H;
     const Scalars* sc = d.sc;
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, r = lane >> 2, j = lane & 3;
@@ -835,6 +1000,7 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
     double* Ws = Ps + 4 * N;
     double* sv = Ws + 4 * N;                            // [32] equilibration scale 1/sqrt(diag)
     double* cav = sv + 32;                              // [32] CA_m
+    double* myred = s_red + wic * NTRI * 64;
     const double sh = sc->sigmaHat;
     const bool live = lane < H;
     // G in accumulator layout, zero padded
@@ -846,9 +1012,14 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
         s_G[e] = (row < H && col < H) ? d.Gm[row * H + col] : 0.0;
     }
     const double gll = live ? d.Gm[lane * H + lane] : 0.0;
-    double acc[NTRI][2];
+    double acc[ACCS ? 1 : NTRI][2];
+    if (ACCS) {
 #pragma unroll
-    for (int t = 0; t < NTRI; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (int t = 0; t < NTRI; ++t) *reinterpret_cast<double2*>(myred + t * 64 + lane * 2) = make_double2(0.0, 0.0);
+    } else {
+#pragma unroll
+        for (int t = 0; t < (ACCS ? 1 : NTRI); ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    }
     __syncthreads();
     bool all_ok = true;
     for (int m = gw; m < d.Mloc; m += nwarps_total) {
@@ -858,12 +1029,12 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
         sv[lane] = sl;
         cav[lane] = ca;
         __syncwarp();
-        double c[NTRI][2];
+        double c[NTRI][2];                              // T = -(D*(G + diag(CA_m))*D), D = diag(sl)
         {
             double srow[NT];
             double2 scol[NT];
 #pragma unroll
-            for (int t = 0; t < NT; ++t) { srow[t] = sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
+            for (int t = 0; t < NT; ++t) { srow[t] = -sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
 #pragma unroll
             for (int ti = 0; ti < NT; ++ti)
 #pragma unroll
@@ -880,24 +1051,31 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
         const bool ok = warp_block_gj_sym<NT>(c, v, lane, Ps, Ws);
         all_ok = all_ok && ok;
         if (live) d.A[(size_t)m * H + lane] = ok ? (diag_var ? sl * v : (sh * sl) * v) : nan("");
-        // Sigma_m = -D*c*D: un-equilibrate (the scale vector is re-read: holding it across the sweeps costs 24 registers), emit
-        // the diagonal (and the blocks on request), add to the running sum
+        // Sigma_m = D*c*D: un-equilibrate (the scale vector is re-read: holding it across the sweeps costs 24 registers) fused
+        // with the running sum; the diagonal (and the blocks on request) are emitted separately
         double srow[NT];
         double2 scol[NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { srow[t] = -sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
+        for (int t = 0; t < NT; ++t) { srow[t] = sv[8 * t + r]; scol[t] = *reinterpret_cast<const double2*>(sv + 8 * t + 2 * j); }
 #pragma unroll
         for (int ti = 0; ti < NT; ++ti)
 #pragma unroll
             for (int tj = ti; tj < NT; ++tj) {
                 const int t = tri_idx(ti, tj, NT);
-                const double s0 = c[t][0] * (srow[ti] * scol[tj].x), s1 = c[t][1] * (srow[ti] * scol[tj].y);
-                acc[t][0] += s0;
-                acc[t][1] += s1;
+                const double w0 = srow[ti] * scol[tj].x, w1 = srow[ti] * scol[tj].y;
+                if (ACCS) {
+                    double2 a = *reinterpret_cast<const double2*>(myred + t * 64 + lane * 2);
+                    a.x = fma(c[t][0], w0, a.x); a.y = fma(c[t][1], w1, a.y);
+                    *reinterpret_cast<double2*>(myred + t * 64 + lane * 2) = a;
+                } else {
+                    acc[ACCS ? 0 : t][0] = fma(c[t][0], w0, acc[ACCS ? 0 : t][0]);
+                    acc[ACCS ? 0 : t][1] = fma(c[t][1], w1, acc[ACCS ? 0 : t][1]);
+                }
                 const int row = 8 * ti + r, col = 8 * tj + 2 * j;
-                if (ti == tj && j == (r >> 1) && row < H) d.sdiag[(size_t)m * H + row] = ok ? ((r & 1) ? s1 : s0) : nan("");
+                if (ti == tj && j == (r >> 1) && row < H) d.sdiag[(size_t)m * H + row] = ok ? ((r & 1) ? c[t][1] * w1 : c[t][0] * w0) : nan("");
                 if (d.blocks != nullptr && row < H) {
                     double* blk = d.blocks + (size_t)m * H * H;
+                    const double s0 = c[t][0] * w0, s1 = c[t][1] * w1;
                     if (col < H) { blk[row * H + col] = s0; if (ti != tj) blk[col * H + row] = s0; }
                     if (col + 1 < H) { blk[row * H + col + 1] = s1; if (ti != tj) blk[(col + 1) * H + row] = s1; }
                 }
@@ -906,9 +1084,10 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
     }
     if (!all_ok && lane == 0) d.sc->chol_fail = 1;
     // per-CTA sum of the warps' running sums in fixed warp order; the lower tiles are the mirror image
-    double* myred = s_red + wic * NTRI * 64;
+    if (!ACCS) {
 #pragma unroll
-    for (int t = 0; t < NTRI; ++t) *reinterpret_cast<double2*>(myred + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < (ACCS ? 1 : NTRI); ++t) *reinterpret_cast<double2*>(myred + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+    }
     __syncthreads();
     double* out = d.part + (size_t)blockIdx.x * H * H;
     for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
@@ -932,16 +1111,17 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     int ngroups;
     static const bool use_reg = getenv("VBMF_B200_K4") != nullptr && strcmp(getenv("VBMF_B200_K4"), "reg") == 0;
     if (H <= 32 && !use_reg) {
-        static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 3;     // tuning probe
+        static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 3;     // tuning probe: 2, 3 (registers), 4 (shared)
         const int wpc = 4;
-        const int per_sm = (H <= 16) ? 4 : (minb == 2 ? 2 : 3);
+        const int per_sm = (H <= 16) ? 4 : (H <= 24 ? 3 : minb);
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * per_sm));
         ngroups = grid;                                   // one partial per CTA
-        if (H <= 8) sparse_A_full_dmma_kernel<1, 4><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc);
-        else if (H <= 16) sparse_A_full_dmma_kernel<2, 4><<<grid, 128, k4_dmma_smem<2>(), st>>>(d, dv, grid * wpc);
-        else if (H <= 24) sparse_A_full_dmma_kernel<3, 3><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc);
-        else if (minb == 2) sparse_A_full_dmma_kernel<4, 2><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
-        else sparse_A_full_dmma_kernel<4, 3><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        if (H <= 8) sparse_A_full_dmma_kernel<1, 4, false><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc);
+        else if (H <= 16) sparse_A_full_dmma_kernel<2, 4, false><<<grid, 128, k4_dmma_smem<2>(), st>>>(d, dv, grid * wpc);
+        else if (H <= 24) sparse_A_full_dmma_kernel<3, 3, false><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc);
+        else if (minb == 2) sparse_A_full_dmma_kernel<4, 2, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        else if (minb == 4) sparse_A_full_dmma_kernel<4, 4, true><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        else sparse_A_full_dmma_kernel<4, 3, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
     } else if (H <= 32) {
         const int wpc = 8;
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
@@ -1891,11 +2071,12 @@ int kernels_init_device() {
     VB_SMEM_ATTR(dense_A_fused_kernel<8>, mxA);
     VB_SMEM_ATTR(dense_A_fused_kernel<32>, mxA);
     VB_SMEM_ATTR((sparse_A_full_kernel<BlockGroup, 64>), (128 * 129 + 384) * 8);
-    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<1, 4>), k4_dmma_smem<1>());
-    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<2, 4>), k4_dmma_smem<2>());
-    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<3, 3>), k4_dmma_smem<3>());
-    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 3>), k4_dmma_smem<4>());
-    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 2>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<1, 4, false>), k4_dmma_smem<1>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<2, 4, false>), k4_dmma_smem<2>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<3, 3, false>), k4_dmma_smem<3>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 3, false>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 2, false>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 4, true>), k4_dmma_smem<4>());
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<8>, (8 * 32 + 8 * 64 + 8 * 32 + 8 * 8 * 32) * 8);
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<16>, (16 * 32 + 8 * 64 + 8 * 32 + 8 * 16 * 32) * 8);
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<24>, (24 * 32 + 8 * 64 + 8 * 32 + 8 * 24 * 32) * 8);

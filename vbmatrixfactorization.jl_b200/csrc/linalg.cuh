@@ -132,16 +132,18 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
 // Blocked (rank-4) symmetric Gauss-Jordan on FP64 tensor-core fragments: the inverse the per-column full-covariance update
 // needs 1e5 times per iteration (src/vbmf_sparse.jl:188, src/vbmf_dual.jl:228).
 //
-// One warp holds an equilibrated SPD matrix of order N = 8*NT (NT <= 4) as the upper-triangular 8 x 8 tiles (ti <= tj) of the
-// DMMA accumulator layout: lane = 4*r + j holds S[8ti + r][8tj + 2j], S[8ti + r][8tj + 2j + 1].  A block step sweeps the four
-// pivots K = 4s .. 4s+3 at once:
-//   1. the column panel P = S[:, K] (N x 4) goes to shared memory (tiles below the diagonal are read through symmetry);
-//   2. with lane = row, four ordinary sweeps restricted to the panel turn it into X = [P*inv(D) ; -inv(D)], D = P[K, :]
-//      (pivot rows travel by shuffle; the right-hand side v rides along as a fifth column, so inv(S)*v needs no mat-vec);
-//   3. -X and P are read back as A / B fragments (lane (r, j) <- row 8t + r, column j) and every stored tile takes ONE
-//      DMMA.8x8x4:  T[ti][tj] -= W'[ti] * P'[tj]^T  with  W' = X + E, P' = P - E (E = identity on the pivot rows), which
-//      writes the swept values of the pivot rows / columns as well (up to the constant 2 on the block's diagonal).
-// After the 2*NT steps the tiles hold -inv(S) and v holds inv(S)*v.  Operand traffic per lane: 8 doubles per FOUR pivots
+// One warp holds T = -S, S an equilibrated SPD matrix of order N = 8*NT (NT <= 4), as the upper-triangular 8 x 8 tiles
+// (ti <= tj) of the DMMA accumulator layout: lane = 4*r + j holds T[8ti + r][8tj + 2j], T[8ti + r][8tj + 2j + 1].  A block step
+// sweeps the four pivots K = 4s .. 4s+3 at once:
+//   1. the column panel Y0 = T[:, K] (N x 4) goes to shared memory (tiles below the diagonal are read through symmetry);
+//   2. with lane = row, four ordinary sweeps restricted to the panel turn it into Y = -[P*inv(D) ; -inv(D)], P = S[:, K],
+//      D = P[K, :] (pivot rows travel by shuffle; the right-hand side v rides along as a fifth column, so inv(S)*v needs
+//      no mat-vec);
+//   3. Y and Y0 are read back as A / B fragments (lane (r, j) <- row 8t + r, column j) and every stored tile takes ONE
+//      DMMA.8x8x4:  T[ti][tj] += (Y - E)[ti] * (Y0 + E)[tj]^T  (E = identity on the pivot rows), which writes the swept
+//      values of the pivot rows / columns as well (up to the constant 2 on the block's diagonal).  Keeping -S instead of S
+//      makes every sign fall on an FMA operand (free) instead of costing negations.
+// After the 2*NT steps the tiles hold inv(S) and v holds inv(S)*v.  Operand traffic per lane: 8 doubles per FOUR pivots
 // (the rank-1 register sweep above needs 32 per ONE pivot, which made it shared-memory bound), and symmetry halves the
 // FP64 work.  Accuracy equals LAPACK's LU inverse on the equilibrated matrices (tools/k4bench/acc_compare.py).
 // Ps, Ws: 4*N doubles each of per-warp shared scratch (16-byte aligned).  `ok` is uniform across the warp.
@@ -149,20 +151,21 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-// 1/x for a positive, finite, normal x: hardware seed + two Newton steps (<= 1 ulp; no special-case slow path, the callers
-// have already rejected non-positive / non-finite pivots)
+// 1/x for a positive, finite, normal x: hardware seed (~2^-20) + one cubic Newton step, three dependent FMAs
+// (relative error ~2^-60; no special-case slow path, the callers have already rejected non-positive / non-finite pivots)
 __device__ __forceinline__ double rcp_pos(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 // positive, finite and not denormal / huge, tested on the exponent word (integer pipe, keeps the FP64 pipe for the math)
 __device__ __forceinline__ bool pivot_ok(double x) {
     return (unsigned)(__double2hiint(x) - 0x00100000) < (unsigned)(0x7e300000 - 0x00100000);
 }
+// -x through the integer pipe (sign-bit flip): keeps negations that must be materialised off the FP64 pipe
+__device__ __forceinline__ double neg_alu(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 __host__ __device__ constexpr int tri_idx(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
 
 template <int NT>
@@ -175,7 +178,7 @@ __device__ __forceinline__ bool warp_block_gj_sym(double (&c)[NT * (NT + 1) / 2]
 #pragma unroll
     for (int s = 0; s < 2 * NT; ++s) {
         const int tk = s >> 1, half = s & 1;
-        // 1. publish the column panel
+        // 1. publish the column panel of T = -S
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             if (t <= tk) {
@@ -189,45 +192,47 @@ __device__ __forceinline__ bool warp_block_gj_sym(double (&c)[NT * (NT + 1) / 2]
             }
         }
         __syncwarp();
-        // 2. lane = row: four sweeps on the panel (+ the right-hand side)
-        double x[4] = {0.0, 0.0, 0.0, 0.0};
+        // 2. lane = row: four sweeps on the (negated) panel y = -x and on the right-hand side
+        double y[4] = {0.0, 0.0, 0.0, 0.0};
         if (rowlane) {
             const double2 a0 = *reinterpret_cast<const double2*>(Ps + lane * 4), a1 = *reinterpret_cast<const double2*>(Ps + lane * 4 + 2);
-            x[0] = a0.x; x[1] = a0.y; x[2] = a1.x; x[3] = a1.y;
+            y[0] = a0.x; y[1] = a0.y; y[2] = a1.x; y[3] = a1.y;
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int kc = 4 * s + cc;
             double pr[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pr[q] = __shfl_sync(0xffffffffu, x[q], kc);
+            for (int q = 0; q < 4; ++q) pr[q] = __shfl_sync(0xffffffffu, y[q], kc);
             const double prv = __shfl_sync(0xffffffffu, v, kc);
-            const double dpiv = pr[cc];
+            const double dpiv = neg_alu(pr[cc]);                    // the pivot of S
             ok = ok && pivot_ok(dpiv);
             const double id = rcp_pos(dpiv);
             const bool piv = lane == kc;
-            const double f = piv ? 1.0 - id : x[cc] * id;
+            // x[q] -= f*x_piv[q] with f = x[cc]/d (f = 1 - 1/d on the pivot row itself, whose entries equal the pivot row's)
+            // in terms of y = -x:  y[q] += g*pr[q], g = -f = y[cc]/d (pivot row: 1/d - 1);  v -= f*v_piv = v + g*v_piv
+            const double g = piv ? id - 1.0 : y[cc] * id;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (q != cc) x[q] = fma(-f, pr[q], x[q]);
-            v = fma(-f, prv, v);
-            x[cc] = piv ? -id : f;
+            for (int q = 0; q < 4; ++q) if (q != cc) y[q] = fma(g, pr[q], y[q]);
+            v = fma(g, prv, v);
+            y[cc] = piv ? id : g;
         }
         if (rowlane) {
-            *reinterpret_cast<double2*>(Ws + lane * 4) = make_double2(-x[0], -x[1]);
-            *reinterpret_cast<double2*>(Ws + lane * 4 + 2) = make_double2(-x[2], -x[3]);
+            *reinterpret_cast<double2*>(Ws + lane * 4) = make_double2(y[0], y[1]);
+            *reinterpret_cast<double2*>(Ws + lane * 4 + 2) = make_double2(y[2], y[3]);
         }
         __syncwarp();
         // 3. fragments and the rank-4 update of every stored tile
         double pf[NT], wf[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) { pf[t] = Ps[(8 * t + r) * 4 + j]; wf[t] = Ws[(8 * t + r) * 4 + j]; }
-        if (r == 4 * half + j) { pf[tk] -= 1.0; wf[tk] -= 1.0; }
+        if (r == 4 * half + j) { pf[tk] += 1.0; wf[tk] -= 1.0; }
 #pragma unroll
         for (int ti = 0; ti < NT; ++ti)
 #pragma unroll
             for (int tj = ti; tj < NT; ++tj) dmma884(c[tri_idx(ti, tj, NT)], wf[ti], pf[tj]);
         if ((r >> 2) == half && j == (r >> 1)) {
-            if (r & 1) c[tri_idx(tk, tk, NT)][1] -= 2.0; else c[tri_idx(tk, tk, NT)][0] -= 2.0;
+            if (r & 1) c[tri_idx(tk, tk, NT)][1] += 2.0; else c[tri_idx(tk, tk, NT)][0] += 2.0;
         }
         __syncwarp();
     }
