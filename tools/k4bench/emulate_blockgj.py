@@ -289,3 +289,88 @@ def cta_block_gj(S, NTD, nsteps=None):
             out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
             out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
     return out
+
+
+def warp_block_gj_v3(S, v, NT):
+    """Third form (the one the CUDA code implements): as warp_block_gj_neg, but
+      * the rank-4 update is assembled from the SEQUENTIAL sweeps' own terms: A fragment = multipliers g_c of sweep c,
+        B fragment = column c of the panel right before its sweep (+1 on the pivot entry).  With X_final * P_original the
+        update loses accuracy like kappa(D) of the 4 x 4 pivot block (tools/k4bench/acc_variants.py);
+      * every lane evolves the 4 x 4 pivot block (and the pivot entries of v) itself from values read once from shared
+        memory instead of receiving the current pivot row by shuffle in every sweep;
+      * panel buffers are stored column-plane-wise, [col][row] with plane stride 36, so every access pattern is conflict free.
+    Returns (inv(S), inv(S) @ v)."""
+    N = 8 * NT
+    PS = 36
+    c = np.zeros((NT, NT, 32, 2))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            c[ti, tj, :, 0] = -S[8 * ti + R, 8 * tj + 2 * J]
+            c[ti, tj, :, 1] = -S[8 * ti + R, 8 * tj + 2 * J + 1]
+    Ps = np.zeros(4 * PS); Ws = np.zeros(4 * PS); vs = np.zeros(32)
+    vv = np.zeros(32); vv[:N] = v
+    for s in range(2 * NT):
+        tk, half = s >> 1, s & 1
+        for t in range(NT):
+            for l in range(32):
+                if t <= tk:
+                    if (J[l] >> 1) == half:
+                        Ps[(2 * (J[l] & 1) + 0) * PS + 8 * t + R[l]] = c[t, tk, l, 0]
+                        Ps[(2 * (J[l] & 1) + 1) * PS + 8 * t + R[l]] = c[t, tk, l, 1]
+                else:
+                    if (R[l] >> 2) == half:
+                        Ps[(R[l] & 3) * PS + 8 * t + 2 * J[l] + 0] = c[tk, t, l, 0]
+                        Ps[(R[l] & 3) * PS + 8 * t + 2 * J[l] + 1] = c[tk, t, l, 1]
+        vs[:] = vv
+        # every lane: the 4 x 4 pivot block (rows 4s..4s+3 of the panel) and the pivot entries of v
+        a0 = np.array([[Ps[q * PS + 4 * s + i] for q in range(4)] for i in range(4)])
+        vk0 = vs[4 * s:4 * s + 4].copy()
+        for l in range(N):
+            a = a0.copy(); vk = vk0.copy()
+            y = np.array([Ps[q * PS + l] for q in range(4)])
+            pq = np.zeros(4); gq = np.zeros(4)
+            vl = vv[l]
+            for cc in range(4):
+                kc = 4 * s + cc
+                pr = a[cc].copy(); prv = vk[cc]
+                idv = 1.0 / (-pr[cc])
+                piv = l == kc
+                g = (idv - 1.0) if piv else y[cc] * idv
+                pq[cc] = y[cc] + (1.0 if piv else 0.0)
+                gq[cc] = g
+                for q in range(4):
+                    if q != cc:
+                        y[q] = y[q] + g * pr[q]
+                vl = vl + g * prv
+                y[cc] = idv if piv else g
+                for i in range(cc + 1, 4):            # the later pivot rows, evolved redundantly
+                    gi = a[i, cc] * idv
+                    for q in range(4):
+                        if q != cc:
+                            a[i, q] = a[i, q] + gi * pr[q]
+                    vk[i] = vk[i] + gi * prv
+                    a[i, cc] = gi
+            vv[l] = vl
+            for q in range(4):
+                Ws[q * PS + l] = gq[q]
+                Ps[q * PS + l] = pq[q]
+        pf = np.zeros((NT, 32)); wf = np.zeros((NT, 32))
+        for t in range(NT):
+            pf[t] = Ps[J * PS + 8 * t + R]
+            wf[t] = Ws[J * PS + 8 * t + R]
+        for ti in range(NT):
+            for tj in range(ti, NT):
+                c[ti, tj] = dmma(c[ti, tj], wf[ti], pf[tj])
+        for l in range(32):
+            r = R[l]
+            if (r >> 2) == half and J[l] == (r >> 1):
+                c[tk, tk, l, r & 1] += 2.0
+    out = np.zeros((N, N))
+    for ti in range(NT):
+        for tj in range(ti, NT):
+            out[8 * ti + R, 8 * tj + 2 * J] = c[ti, tj, :, 0]
+            out[8 * ti + R, 8 * tj + 2 * J + 1] = c[ti, tj, :, 1]
+            if tj > ti:
+                out[8 * tj + 2 * J, 8 * ti + R] = c[ti, tj, :, 0]
+                out[8 * tj + 2 * J + 1, 8 * ti + R] = c[ti, tj, :, 1]
+    return out, vv[:N]

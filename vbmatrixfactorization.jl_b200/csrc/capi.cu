@@ -418,6 +418,7 @@ struct vbmf_b200_solver {
     // host-side validity of derived quantities (every enqueued kernel either runs or is skipped as a whole iteration)
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
+    bool ca_done = false;     // the fused diagonal A pass already did updateCA! of this iteration
     int* h_flag = nullptr;   // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // The single-CTA tail of an iteration (norms, hyper-parameter updates, convergence test) runs on a side stream so that
@@ -859,6 +860,15 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
         s->ata_local = true;
     } else {
         const bool dv = (flags & F_DIAG_VAR) != 0;
+        if (fused && !(flags & F_FULL_COV) && getenv("VBMF_B200_NO_DIAG_FUSION") == nullptr) {
+            // whole-loop diagonal path: slab sum, A, diag, mask, updateCA! and A'A in one pass over vec(A')
+            if (enq_k1(s, dv, false) || wait_post(s)) return -1;
+            const bool slabs = !s->c->simt && s->S1 > 1;
+            if (k_sparse_A_diag_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, flags)) return -1;
+            s->ata_valid = false; s->q_valid = false;
+            s->ata_local = true; s->ca_done = true;
+            return 0;
+        }
         if (enq_k1(s, dv) || wait_post(s)) return -1;
         if (flags & F_FULL_COV) { if (k_sparse_A_full(st, d, flags)) return -1; }
         else { if (k_sparse_A_diag(st, d, flags)) return -1; }
@@ -867,6 +877,7 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
     }
     s->ata_valid = false; s->q_valid = false;
     if (d.kind != KIND_DENSE) s->ata_local = false;
+    s->ca_done = false;
     return 0;
 }
 static int enq_gram_A(vbmf_b200_solver* s) {
@@ -968,7 +979,8 @@ static int enq_iteration(vbmf_b200_solver* s, int flags) {
     const Dev& d = s->d;
     cudaStream_t st = s->c->st;
     if (enq_updateA(s, flags, true)) return -1;                       // updateA!
-    if (d.kind != KIND_DENSE && enq_updateCA(s, flags, true)) return -1;   // updateCA! (local; hoisted before the all-reduce)
+    if (d.kind != KIND_DENSE && !s->ca_done && enq_updateCA(s, flags, true)) return -1;   // updateCA! (local; hoisted before the all-reduce)
+    s->ca_done = false;
     if (enq_updateB(s, flags, true)) return -1;                       // updateB! (+ Grams of BHat and of BHat - Bold)
     if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) {
         if (k_sigma_rows(st, d)) return -1;                           // updateSigma! (per-row)

@@ -470,8 +470,8 @@ __device__ __forceinline__ double hxh_elem(const Dev& d, int mode, int diag_var,
 template <int NT>
 __global__ void __launch_bounds__(32, 1) hxh_warp_kernel(Dev d, int mode, int diag_var) {
     ACTIVE_OR_RETURN(d);
-    constexpr int N = 8 * NT, NTRI = NT * (NT + 1) / 2;
-    __shared__ __align__(16) double Ps[4 * N], Ws[4 * N], sv[32];
+    constexpr int NTRI = NT * (NT + 1) / 2;
+    __shared__ __align__(16) double scr[GJ_SCRATCH], sv[32];
     const int H = d.H, lane = threadIdx.x, r = lane >> 2, j = lane & 3;
     if (mode == 2) for (int e = lane; e < H * H; e += 32) d.SigmaA[e] = (d.packed + packed_sa(d))[e];
     sv[lane] = lane < H ? rsqrt(hxh_elem(d, mode, diag_var, lane, lane)) : 1.0;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(32, 1) hxh_warp_kernel(Dev d, int mode, int di
                 c[tri_idx(ti, tj, NT)][k] = -v * (sv[row] * sv[col]);
             }
     double dummy = 0.0;
-    const bool ok = warp_block_gj_sym<NT>(c, dummy, lane, Ps, Ws);
+    const bool ok = warp_block_gj_sym<NT>(c, dummy, lane, scr);
     if (!ok && lane == 0) d.sc->chol_fail = 1;
     double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
     const double scale = (mode == 2) ? 1.0 : d.sc->sigma2;
@@ -508,23 +508,27 @@ __global__ void __launch_bounds__(32, 1) hxh_warp_kernel(Dev d, int mode, int di
             }
 }
 // 32 < H <= 128: 16 warps, the full NTD x NTD tile grid spread over the warps (warp w: tile row w / WPR, TPW tile columns).
-// Per block step: the owners of the pivot column block publish the panel (double buffered -> ONE barrier per step), every
-// warp inverts the 4 x 4 pivot block D itself (registers; identical in all warps, so `ok` needs no communication), forms
-// its A fragment as Y0[row, :]*inv(D)[:, j] (+ inv(D)[c][j] on the pivot rows) and issues TPW DMMAs.
+// Per block step: the owners of the pivot column block publish the panel (double buffered); the first N/32 warps run the
+// four sweeps with lane = row (linalg.cuh::gj_panel_sweeps, the 4 x 4 pivot block evolved in every lane) and leave the
+// multipliers G and the pre-sweep columns Q in shared memory; every warp then reads its A / B fragments and issues TPW DMMAs.
+// Two barriers per FOUR pivots (the register sweep: one per pivot, with 1024 threads).
 template <int NTD, int TPW>
 __global__ void __launch_bounds__(512, 1) hxh_dmma_kernel(Dev d, int mode, int diag_var) {
     ACTIVE_OR_RETURN(d);
-    constexpr int N = 8 * NTD, WPR = NTD / TPW;
+    constexpr int N = 8 * NTD, WPR = NTD / TPW, PL = N + 4, NRW = N / 32;
     static_assert(NTD * WPR == 16, "16 warps cover the tile grid");
-    __shared__ __align__(16) double Ps[2][4 * N];
+    __shared__ __align__(16) double Ps[2][4 * PL];
+    __shared__ __align__(16) double Gs[4 * PL], Qs[4 * PL];
     __shared__ double sv[N];
+    __shared__ int s_fail;
     const int H = d.H, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
     const int ti = warp / WPR, tj0 = (warp % WPR) * TPW;
     if (mode == 2) for (int e = threadIdx.x; e < H * H; e += 512) d.SigmaA[e] = (d.packed + packed_sa(d))[e];
     for (int t = threadIdx.x; t < N; t += 512) sv[t] = t < H ? rsqrt(hxh_elem(d, mode, diag_var, t, t)) : 1.0;
+    if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
     const int row = 8 * ti + r;
-    double c[TPW][2];
+    double c[TPW][2];                       // T = -(equilibrated matrix), identity padded
 #pragma unroll
     for (int u = 0; u < TPW; ++u)
 #pragma unroll
@@ -534,68 +538,44 @@ __global__ void __launch_bounds__(512, 1) hxh_dmma_kernel(Dev d, int mode, int d
             c[u][k] = -v * (sv[row] * sv[col]);
         }
     const int nsteps = (H + 3) >> 2;
-    bool ok = true;
-    // panel of step 0
 #pragma unroll
     for (int u = 0; u < TPW; ++u)
-        if (tj0 + u == 0 && (j >> 1) == 0) *reinterpret_cast<double2*>(&Ps[0][row * 4 + 2 * (j & 1)]) = make_double2(c[u][0], c[u][1]);
+        if (tj0 + u == 0 && (j >> 1) == 0) { Ps[0][(2 * (j & 1)) * PL + row] = c[u][0]; Ps[0][(2 * (j & 1) + 1) * PL + row] = c[u][1]; }
     for (int s = 0; s < nsteps; ++s) {
         __syncthreads();
         const double* P = Ps[s & 1];
         const int tk = s >> 1, half = s & 1;
-        // -D (4 x 4 pivot block of T = -S), swept in registers: a -> -inv(D)
-        double a[4][4];
+        if (warp < NRW) {
+            const int rowi = warp * 32 + lane;
+            double a[4][4], vk[4] = {0.0, 0.0, 0.0, 0.0}, y[4], gq[4], pq[4], dummy = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double2 x0 = *reinterpret_cast<const double2*>(P + (4 * s + i) * 4), x1 = *reinterpret_cast<const double2*>(P + (4 * s + i) * 4 + 2);
-            a[i][0] = -x0.x; a[i][1] = -x0.y; a[i][2] = -x1.x; a[i][3] = -x1.y;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            ok = ok && pivot_ok(a[cc][cc]);
-            const double id = rcp_pos(a[cc][cc]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i != cc) {
-                    const double f = a[i][cc] * id;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (q != cc) a[i][q] = fma(-f, a[cc][q], a[i][q]);
-                    a[i][cc] = f;
-                }
+            for (int q = 0; q < 4; ++q) {
+                const double2 lo = *reinterpret_cast<const double2*>(P + q * PL + 4 * s), hi = *reinterpret_cast<const double2*>(P + q * PL + 4 * s + 2);
+                a[0][q] = lo.x; a[1][q] = lo.y; a[2][q] = hi.x; a[3][q] = hi.y;
+                y[q] = P[q * PL + rowi];
             }
+            if (!gj_panel_sweeps(a, vk, y, dummy, rowi - 4 * s, gq, pq)) s_fail = 1;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (q != cc) a[cc][q] *= id;
-            a[cc][cc] = -id;
+            for (int q = 0; q < 4; ++q) { Gs[q * PL + rowi] = gq[q]; Qs[q * PL + rowi] = pq[q]; }
         }
-        // column j of -inv(D) for this lane
-        double aj[4];
+        __syncthreads();
+        const double wf = Gs[j * PL + row];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) aj[q] = j == 0 ? a[q][0] : j == 1 ? a[q][1] : j == 2 ? a[q][2] : a[q][3];
-        // A fragment: (Y - E)[row][j] = Y0[row, :]*inv(D)[:, j] (+ inv(D)[row - 4s][j] on a pivot row)
-        const double2 y0 = *reinterpret_cast<const double2*>(P + row * 4), y1 = *reinterpret_cast<const double2*>(P + row * 4 + 2);
-        double wsum = y0.x * aj[0];
-        wsum = fma(y0.y, aj[1], wsum); wsum = fma(y1.x, aj[2], wsum); wsum = fma(y1.y, aj[3], wsum);
-        if ((row >> 2) == s) { const int cr = row & 3; wsum += cr == 0 ? aj[0] : cr == 1 ? aj[1] : cr == 2 ? aj[2] : aj[3]; }
-        const double wf = -wsum;
-#pragma unroll
-        for (int u = 0; u < TPW; ++u) {
-            const int brow = 8 * (tj0 + u) + r;
-            double pf = P[brow * 4 + j];
-            if (brow == 4 * s + j) pf += 1.0;
-            dmma884(c[u], wf, pf);
-        }
+        for (int u = 0; u < TPW; ++u) dmma884(c[u], wf, Qs[j * PL + 8 * (tj0 + u) + r]);
         if (ti == tk && (r >> 2) == half && j == (r >> 1)) {
 #pragma unroll
             for (int u = 0; u < TPW; ++u) if (tj0 + u == tk) { if (r & 1) c[u][1] += 2.0; else c[u][0] += 2.0; }
         }
-        // panel of the next step into the other buffer
-        if (s + 1 < nsteps) {
+        if (s + 1 < nsteps) {              // panel of the next step into the other buffer
             const int tkn = (s + 1) >> 1, halfn = (s + 1) & 1;
+            double* Pn = Ps[(s + 1) & 1];
 #pragma unroll
             for (int u = 0; u < TPW; ++u)
-                if (tj0 + u == tkn && (j >> 1) == halfn) *reinterpret_cast<double2*>(&Ps[(s + 1) & 1][row * 4 + 2 * (j & 1)]) = make_double2(c[u][0], c[u][1]);
+                if (tj0 + u == tkn && (j >> 1) == halfn) { Pn[(2 * (j & 1)) * PL + row] = c[u][0]; Pn[(2 * (j & 1) + 1) * PL + row] = c[u][1]; }
         }
     }
+    __syncthreads();
+    const bool ok = s_fail == 0;
     if (!ok && threadIdx.x == 0) d.sc->chol_fail = 1;
     double* out = (mode == 0) ? d.SigmaA : d.SigmaB;
     const double scale = (mode == 2) ? 1.0 : d.sc->sigma2;
@@ -844,6 +824,183 @@ int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags) {
     return 0;
 }
 
+// Whole-loop version of the diagonal path: ONE pass over vec(A') does what sparse_A_diag + diag_to_sa + mask + update_CA +
+// gram_dmma(A) do in five (src/vbmf_sparse.jl:204-246 updateA!, :284-288 updateCA!, src/vbmf_dual.jl:322-351, and the Gram
+// AHat'AHat of updateB! :259).  updateCA! only needs this column's a and s and replicated scalars, so hoisting it in front of
+// updateB! changes nothing.  Per 32-row tile: P = fixed-order sum of the K1 slabs, s = 1/(d[src] + CA), a = (sigmaHat*s)*P
+// (label mask), beta = beta0_g + (a^2 + s)/2, CA = alpha_g/beta; the a tile goes to shared memory for the DMMA Gram
+// (accumulators in registers across the CTA's tiles); column sums of s (-> diag SigmaA) and the group sums of the dual /
+// trial hyper-prior updates are carried per thread.  Partials per CTA: [H*H Gram | HP8 column sums | 8 group sums].
+template <int GT>   // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
+__global__ void __launch_bounds__(256, (GT <= 5 ? 3 : 1)) sparse_A_diag_fused_kernel(Dev d, const double* __restrict__ slabs, int S,
+                                                                                    size_t slab_stride, int diag_var) {
+    ACTIVE_OR_RETURN(d);
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ long long s_q0[32];
+    __shared__ int s_r0[32];
+    const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
+    constexpr int KMAX = GT == 2 ? 4 : (GT == 5 ? 8 : 16);     // elements of a 32 x HP8 tile per thread (HP8 <= 32 / 64 / 128)
+    double* An = sm;                         // [32][ld]  new AHat tile (zero padded)
+    double* dv = An + 32 * ld;               // [HP8]     likelihood part of the diagonal precision
+    double* stage = dv + HP8;                // [32*HP8]  end-of-kernel staging of the per-thread column sums
+    Scalars* sc = d.sc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+    for (int h = threadIdx.x; h < HP8; h += 256) {
+        double v = 0.0;
+        if (h < H) v = diag_var ? d.BtBw[h * H + h] + (double)d.L * sc->meanSigmaVec * d.SigmaB[h * H + h]
+                                : sc->sigmaHat * d.BtB[h * H + h] + (double)d.L * d.SigmaB[h * H + h];
+        dv[h] = v;
+    }
+    const bool grouped = d.kind == KIND_DUAL || d.kind == KIND_TRIAL;
+    const double al[3] = {grouped ? sc->alpha00 + 0.5 : sc->alpha, grouped ? sc->alpha01 + 0.5 : sc->alpha, sc->alpha02 + 0.5};
+    const double be[3] = {grouped ? sc->beta00 : sc->beta0p, grouped ? sc->beta01 : sc->beta0p, sc->beta02};
+    const double sh = sc->sigmaHat;
+    const int hmask = H - d.H1;
+    const long long Mg1 = (long long)d.Mglob - 1;
+    double g[GT][2];
+    int gt[GT];
+#pragma unroll
+    for (int q = 0; q < GT; ++q) {
+        g[q][0] = 0.0; g[q][1] = 0.0;
+        int idx = warp + 8 * q, at = 0;
+        while (at < nt8 && idx >= nt8 - at) { idx -= nt8 - at; ++at; }
+        gt[q] = at < nt8 ? (at | ((at + idx) << 8)) : -1;
+    }
+    double csum[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) csum[k] = 0.0;
+    double sca[3] = {0.0, 0.0, 0.0}, slb[3] = {0.0, 0.0, 0.0};
+    const int nel = 32 * HP8;
+    const int ntiles = (d.Mloc + 31) / 32;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
+        __syncthreads();
+        // Q2: element j of vec(A') (0-based, global) reads d[j] for j < H, else d[(j - H) / (M - 1)]: one division per row
+        if (threadIdx.x < 32) {
+            const long long mg = (long long)d.moff + m0 + threadIdx.x;
+            long long q0 = 0; int r0 = 0;
+            if (mg > 0 && Mg1 > 0) { const long long base = (mg - 1) * H; q0 = base / Mg1; r0 = (int)(base - q0 * Mg1); }
+            s_q0[threadIdx.x] = q0; s_r0[threadIdx.x] = r0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int e = threadIdx.x + 256 * k;
+            if (e < nel) {
+                const int i = e / HP8, c = e - i * HP8;
+                double a = 0.0;
+                if (i < nr && c < H) {
+                    const size_t idx = (size_t)(m0 + i) * H + c;
+                    double p = slabs[idx];
+                    for (int s2 = 1; s2 < S; ++s2) p += slabs[(size_t)s2 * slab_stride + idx];
+                    const long long mg = (long long)d.moff + m0 + i;
+                    int src = c;
+                    if (mg > 0) {
+                        const long long rr = (long long)s_r0[i] + c;
+                        src = (int)(s_q0[i] + (rr >= Mg1 ? (Mg1 >= H ? 1 : rr / Mg1) : 0));
+                    }
+                    const double sv = 1.0 / (dv[src] + d.CAv[idx]);
+                    a = diag_var ? sv * p : (sh * sv) * p;
+                    if (d.rowmask != nullptr && c >= hmask && d.rowmask[m0 + i]) a = 0.0;
+                    const int grp = (!grouped || c < d.H0) ? 0 : (mg < d.M0 ? 1 : 2);
+                    const double beta = (grp == 0 ? be[0] : grp == 1 ? be[1] : be[2]) + 0.5 * (a * a + sv);
+                    const double ca = (grp == 0 ? al[0] : grp == 1 ? al[1] : al[2]) / beta;
+                    d.sdiag[idx] = sv;
+                    d.A[idx] = a;
+                    d.beta[idx] = beta;
+                    d.CAv[idx] = ca;
+                    csum[k] += sv;
+                    if (grouped) {
+                        const double lb = log(beta);
+                        if (grp == 0) { sca[0] += ca; slb[0] += lb; } else if (grp == 1) { sca[1] += ca; slb[1] += lb; } else { sca[2] += ca; slb[2] += lb; }
+                    }
+                }
+                An[i * ld + c] = a;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < GT; ++q) {
+            if (gt[q] >= 0) {
+                const double* pa = An + j * ld + 8 * (gt[q] & 255) + r;
+                const double* pb = An + j * ld + 8 * (gt[q] >> 8) + r;
+#pragma unroll
+                for (int i0 = 0; i0 < 32; i0 += 4) dmma_acc2(g[q], pa[i0 * ld], pb[i0 * ld]);
+            }
+        }
+    }
+    const int PS = H * H + HP8 + 8;
+    double* out = d.part + (size_t)blockIdx.x * PS;
+#pragma unroll
+    for (int q = 0; q < GT; ++q) {
+        if (gt[q] >= 0) {
+            const int a = 8 * (gt[q] & 255) + r, b = 8 * (gt[q] >> 8) + 2 * j;
+            if (a < H && b < H) { out[a * H + b] = g[q][0]; out[b * H + a] = g[q][0]; }
+            if (a < H && b + 1 < H) { out[a * H + b + 1] = g[q][1]; out[(b + 1) * H + a] = g[q][1]; }
+        }
+    }
+    // column sums of s: element slot (t, k) always holds column (t + 256k) % HP8 -> fixed-order sum over the 32 rows of the slot grid
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { const int e = threadIdx.x + 256 * k; if (e < nel) stage[e] = csum[k]; }
+    __syncthreads();
+    if (threadIdx.x < HP8) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += stage[i * HP8 + threadIdx.x];
+        out[H * H + threadIdx.x] = t;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double a = block_sum(sca[q], red), b = block_sum(slb[q], red);
+        if (threadIdx.x == 0) { out[H * H + HP8 + q] = a; out[H * H + HP8 + 3 + q] = b; }
+    }
+    if (threadIdx.x == 0) {
+        out[H * H + HP8 + 6] = 0.0; out[H * H + HP8 + 7] = 0.0;
+        if (blockIdx.x == 0 && grouped) { sc->alpha_g0 = al[0]; sc->alpha_g1 = al[1]; sc->alpha_g2 = al[2]; }
+    }
+}
+// fixed-order reduction of the per-CTA partials: packed.AtA (local Gram), packed.SA = diag(column sums), packed.EX
+__global__ void __launch_bounds__(256) sparse_diag_reduce_kernel(Dev d, int nparts) {
+    ACTIVE_OR_RETURN(d);
+    __shared__ double sm[8][33];
+    const int H = d.H, HP8 = (H + 7) & ~7, n = H * H + HP8 + 8;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + x;
+    double* SA = d.packed + packed_sa(d);
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < H * H; q += gridDim.x * 256) if (q / H != q % H) SA[q] = 0.0;
+    double s = 0.0;
+    if (e < n) {
+#pragma unroll 4
+        for (int p = y; p < nparts; p += 8) s += d.part[(size_t)p * n + e];
+    }
+    sm[y][x] = s;
+    __syncthreads();
+    if (y == 0 && e < n) {
+        double t = sm[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][x];
+        if (e < H * H) (d.packed + packed_ata(d))[e] = t;
+        else if (e < H * H + HP8) { const int h = e - H * H; if (h < H) SA[h * H + h] = t; }
+        else if (d.kind == KIND_DUAL || d.kind == KIND_TRIAL) (d.packed + packed_ex(d))[e - H * H - HP8] = t;
+    }
+}
+static size_t sparse_diag_fused_smem(int H) { const int HP8 = (H + 7) & ~7; return (size_t)(32 * pitch4(HP8) + HP8 + 32 * HP8) * sizeof(double); }
+int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags) {
+    const int H = d.H, HP8 = (H + 7) & ~7;
+    const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
+    const size_t smem = sparse_diag_fused_smem(H);
+    const int per_sm = HP8 <= 64 ? 3 : 1;
+    const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), 32), 148 * per_sm));
+    if (HP8 <= 32) sparse_A_diag_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
+    else if (HP8 <= 64) sparse_A_diag_fused_kernel<5><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
+    else sparse_A_diag_fused_kernel<17><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
+    VB_LAUNCH_OK();
+    sparse_diag_reduce_kernel<<<cdiv(H * H + HP8 + 8, 32), 256, 0, st>>>(d, grid);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- K4: sparse / dual A update, full covariance
 // src/vbmf_sparse.jl:178-202 == src/vbmf_dual.jl:218-242.  inv(sigmaHat*kron(I_M, G0) + diagm(CA)) is block diagonal, so per
 // column m:  Sigma_m = inv(G + diag(CA_m)),  G = sigmaHat*(B'B + L*SigmaB)  [diag_var: B'diag(sv)B + L*mean(sv)*SigmaB],
@@ -987,18 +1144,17 @@ __global__ void __launch_bounds__(256, 2) sparse_A_full_warp_kernel(Dev d, int d
 template <int NT, int MINB, bool ACCS>
 __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, int diag_var, int nwarps_total) {
     ACTIVE_OR_RETURN(d);
-    constexpr int NTRI = NT * (NT + 1) / 2, N = 8 * NT, WPC = 4;
+    constexpr int NTRI = NT * (NT + 1) / 2, WPC = 4, SCR = GJ_SCRATCH + 64;
     extern __shared__ __align__(16) double wsm[];
     double* s_G = wsm;                                  // [NTRI][32][2]
-    double* s_scr = s_G + NTRI * 64;                    // [WPC][4N + 4N + 32 + 32]
-    double* s_red = s_scr + WPC * (8 * N + 64);         // [WPC][NTRI][64] running sums (ACCS) / end-of-kernel reduction
+    double* s_scr = s_G + NTRI * 64;                    // [WPC][GJ_SCRATCH + 32 + 32]
+    double* s_red = s_scr + WPC * SCR;                  // [WPC][NTRI][64] running sums (ACCS) / end-of-kernel reduction
     const int H = d.H;
     const Scalars* sc = d.sc;
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, r = lane >> 2, j = lane & 3;
     const int gw = blockIdx.x * WPC + wic;
-    double* Ps = s_scr + wic * (8 * N + 64);
-    double* Ws = Ps + 4 * N;
-    double* sv = Ws + 4 * N;                            // [32] equilibration scale 1/sqrt(diag)
+    double* scr = s_scr + wic * SCR;
+    double* sv = scr + GJ_SCRATCH;                      // [32] equilibration scale 1/sqrt(diag)
     double* cav = sv + 32;                              // [32] CA_m
     double* myred = s_red + wic * NTRI * 64;
     const double sh = sc->sigmaHat;
@@ -1048,7 +1204,7 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
                 }
         }
         double v = p * sl;
-        const bool ok = warp_block_gj_sym<NT>(c, v, lane, Ps, Ws);
+        const bool ok = warp_block_gj_sym<NT>(c, v, lane, scr);
         all_ok = all_ok && ok;
         if (live) d.A[(size_t)m * H + lane] = ok ? (diag_var ? sl * v : (sh * sl) * v) : nan("");
         // Sigma_m = D*c*D: un-equilibrate (the scale vector is re-read: holding it across the sweeps costs 24 registers) fused
@@ -1101,7 +1257,7 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
         out[e] = sum;
     }
 }
-template <int NT> static size_t k4_dmma_smem() { return (size_t)(NT * (NT + 1) / 2 * 64 + 4 * (64 * NT + 64) + 4 * (NT * (NT + 1) / 2) * 64) * sizeof(double); }
+template <int NT> static size_t k4_dmma_smem() { return (size_t)(NT * (NT + 1) / 2 * 64 + 4 * (GJ_SCRATCH + 64) + 4 * (NT * (NT + 1) / 2) * 64) * sizeof(double); }
 
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H;
@@ -1111,9 +1267,9 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
     int ngroups;
     static const bool use_reg = getenv("VBMF_B200_K4") != nullptr && strcmp(getenv("VBMF_B200_K4"), "reg") == 0;
     if (H <= 32 && !use_reg) {
-        static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 3;     // tuning probe: 2, 3 (registers), 4 (shared)
+        static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 4;     // tuning probe: 2, 3 (sums in registers), 4 / 5 (sums in shared memory; 4 CTAs per SM measured fastest: 0.407 vs 0.435 ms for 1e5 32 x 32)
         const int wpc = 4;
-        const int per_sm = (H <= 16) ? 4 : (H <= 24 ? 3 : minb);
+        const int per_sm = (H <= 16) ? 4 : (H <= 24 ? 3 : (minb == 5 ? 3 : minb));
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * per_sm));
         ngroups = grid;                                   // one partial per CTA
         if (H <= 8) sparse_A_full_dmma_kernel<1, 4, false><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc);
@@ -1121,6 +1277,7 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
         else if (H <= 24) sparse_A_full_dmma_kernel<3, 3, false><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc);
         else if (minb == 2) sparse_A_full_dmma_kernel<4, 2, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
         else if (minb == 4) sparse_A_full_dmma_kernel<4, 4, true><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        else if (minb == 5) sparse_A_full_dmma_kernel<4, 3, true><<<std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)), 128, k4_dmma_smem<4>(), st>>>(d, dv, std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)) * wpc);
         else sparse_A_full_dmma_kernel<4, 3, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
     } else if (H <= 32) {
         const int wpc = 8;
@@ -2070,6 +2227,9 @@ int kernels_init_device() {
     VB_SMEM_ATTR(dense_A_fused_kernel<2>, mxA);
     VB_SMEM_ATTR(dense_A_fused_kernel<8>, mxA);
     VB_SMEM_ATTR(dense_A_fused_kernel<32>, mxA);
+    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<2>, sparse_diag_fused_smem(128));
+    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<5>, sparse_diag_fused_smem(128));
+    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<17>, sparse_diag_fused_smem(128));
     VB_SMEM_ATTR((sparse_A_full_kernel<BlockGroup, 64>), (128 * 129 + 384) * 8);
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<1, 4, false>), k4_dmma_smem<1>());
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<2, 4, false>), k4_dmma_smem<2>());
@@ -2077,6 +2237,7 @@ int kernels_init_device() {
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 3, false>), k4_dmma_smem<4>());
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 2, false>), k4_dmma_smem<4>());
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 4, true>), k4_dmma_smem<4>());
+    VB_SMEM_ATTR((sparse_A_full_dmma_kernel<4, 3, true>), k4_dmma_smem<4>());
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<8>, (8 * 32 + 8 * 64 + 8 * 32 + 8 * 8 * 32) * 8);
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<16>, (16 * 32 + 8 * 64 + 8 * 32 + 8 * 16 * 32) * 8);
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<24>, (24 * 32 + 8 * 64 + 8 * 32 + 8 * 24 * 32) * 8);

@@ -130,23 +130,27 @@ __device__ __forceinline__ bool warp_spd_inverse_reg(double (&a)[HP], double dg,
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Blocked (rank-4) symmetric Gauss-Jordan on FP64 tensor-core fragments: the inverse the per-column full-covariance update
-// needs 1e5 times per iteration (src/vbmf_sparse.jl:188, src/vbmf_dual.jl:228).
+// needs 1e5 times per iteration (src/vbmf_sparse.jl:188, src/vbmf_dual.jl:228) and the H x H posterior covariances.
 //
 // One warp holds T = -S, S an equilibrated SPD matrix of order N = 8*NT (NT <= 4), as the upper-triangular 8 x 8 tiles
 // (ti <= tj) of the DMMA accumulator layout: lane = 4*r + j holds T[8ti + r][8tj + 2j], T[8ti + r][8tj + 2j + 1].  A block step
 // sweeps the four pivots K = 4s .. 4s+3 at once:
-//   1. the column panel Y0 = T[:, K] (N x 4) goes to shared memory (tiles below the diagonal are read through symmetry);
-//   2. with lane = row, four ordinary sweeps restricted to the panel turn it into Y = -[P*inv(D) ; -inv(D)], P = S[:, K],
-//      D = P[K, :] (pivot rows travel by shuffle; the right-hand side v rides along as a fifth column, so inv(S)*v needs
-//      no mat-vec);
-//   3. Y and Y0 are read back as A / B fragments (lane (r, j) <- row 8t + r, column j) and every stored tile takes ONE
-//      DMMA.8x8x4:  T[ti][tj] += (Y - E)[ti] * (Y0 + E)[tj]^T  (E = identity on the pivot rows), which writes the swept
-//      values of the pivot rows / columns as well (up to the constant 2 on the block's diagonal).  Keeping -S instead of S
-//      makes every sign fall on an FMA operand (free) instead of costing negations.
-// After the 2*NT steps the tiles hold inv(S) and v holds inv(S)*v.  Operand traffic per lane: 8 doubles per FOUR pivots
-// (the rank-1 register sweep above needs 32 per ONE pivot, which made it shared-memory bound), and symmetry halves the
-// FP64 work.  Accuracy equals LAPACK's LU inverse on the equilibrated matrices (tools/k4bench/acc_compare.py).
-// Ps, Ws: 4*N doubles each of per-warp shared scratch (16-byte aligned).  `ok` is uniform across the warp.
+//   1. the column panel Y0 = T[:, K] (N x 4) and the right-hand side go to shared memory (tiles below the diagonal are read
+//      through symmetry);
+//   2. with lane = row, every lane runs the four sweeps on its own panel row.  The current pivot row of each sweep is not
+//      communicated: every lane reads the 4 x 4 pivot block once and evolves it in registers alongside (24 FMAs);
+//   3. the update of every stored tile is ONE DMMA.8x8x4 assembled from the sweeps' own terms,
+//          T[ti][tj] += G[ti] * Q[tj]^T,   G[:, c] = multipliers of sweep c,   Q[:, c] = column c right before its sweep,
+//      (+1 on the pivot entry of Q, so the same product also writes the swept pivot rows / columns; +2 on the block's diagonal).
+//      Using the FINISHED panel times the ORIGINAL panel instead (X*inv(D)*X') is algebraically the same update but loses
+//      accuracy like the condition number of the 4 x 4 pivot block -- measured: 1e-7 instead of 2e-11 on A = P*Sigma at
+//      kappa = 8e4 (tools/k4bench/acc_variants.py); the sequential terms reproduce the rank-1 sweep's rounding behaviour.
+// Keeping -S instead of S makes every sign fall on an FMA operand.  After the 2*NT steps the tiles hold inv(S) and v holds
+// inv(S)*v (v rides through the sweeps as a fifth column, so no mat-vec is needed).  Operand traffic per lane: 8 fragment
+// doubles per FOUR pivots (the rank-1 register sweep above needs 32 per ONE pivot, which made it shared-memory bound);
+// symmetry halves the FP64 work.
+// Shared scratch per warp: Ps, Ws = 4 column planes of PLANE doubles each ([col][row]: conflict-free for the row-wise,
+// fragment-wise and tile-wise accesses), vs = 32 doubles.  `ok` is uniform across the warp.
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -167,66 +171,100 @@ __device__ __forceinline__ bool pivot_ok(double x) {
 // -x through the integer pipe (sign-bit flip): keeps negations that must be materialised off the FP64 pipe
 __device__ __forceinline__ double neg_alu(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 __host__ __device__ constexpr int tri_idx(int ti, int tj, int NT) { return ti * NT - ti * (ti - 1) / 2 + (tj - ti); }
+constexpr int GJ_PLANE = 36;                    // plane stride of the panel buffers: 32 rows + 4 (bank skew between the 4 columns)
+constexpr int GJ_SCRATCH = 8 * GJ_PLANE + 32;   // doubles of scratch per warp: Ps | Ws | vs
+
+// One block step's lane = row work, shared by the warp-level and the CTA-level inverse: the four sweeps on this lane's panel
+// row y[0..3] (and rhs v), driven by the 4 x 4 pivot block a[][] / rhs pivots vk[] that the lane evolves itself.
+// In: y = row of the panel of T = -S, a = rows 4s..4s+3 of the panel, `prow` = this lane's row index - 4s (0..3 on a pivot row).
+// Out: gq = multipliers (A fragment values), pq = column entries before their sweep (+1 on the pivot entry; B fragment values).
+__device__ __forceinline__ bool gj_panel_sweeps(double (&a)[4][4], double (&vk)[4], double (&y)[4], double& v, const int prow,
+                                                double (&gq)[4], double (&pq)[4]) {
+    bool ok = true;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const double dpiv = neg_alu(a[cc][cc]);                 // the pivot of S
+        ok = ok && pivot_ok(dpiv);
+        const double id = rcp_pos(dpiv);
+        const bool piv = prow == cc;
+        // x[q] -= f*x_piv[q] with f = x[cc]/d (f = 1 - 1/d on the pivot row itself, whose entries equal the pivot row's);
+        // in terms of y = -x:  y[q] += g*pr[q], g = -f = y[cc]/d (pivot row: 1/d - 1);  v -= f*v_piv = v + g*v_piv
+        const double g = piv ? id - 1.0 : y[cc] * id;
+        pq[cc] = piv ? y[cc] + 1.0 : y[cc];
+        gq[cc] = g;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q != cc) y[q] = fma(g, a[cc][q], y[q]);
+        v = fma(g, vk[cc], v);
+        y[cc] = piv ? id : g;
+        // the later pivot rows (and rhs pivots) of the block
+#pragma unroll
+        for (int i = cc + 1; i < 4; ++i) {
+            const double gi = a[i][cc] * id;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q != cc) a[i][q] = fma(gi, a[cc][q], a[i][q]);
+            vk[i] = fma(gi, vk[cc], vk[i]);
+            a[i][cc] = gi;
+        }
+    }
+    return ok;
+}
 
 template <int NT>
 __device__ __forceinline__ bool warp_block_gj_sym(double (&c)[NT * (NT + 1) / 2][2], double& v, const int lane,
-                                                  double* __restrict__ Ps, double* __restrict__ Ws) {
-    constexpr int N = 8 * NT;
+                                                  double* __restrict__ scr) {
+    constexpr int N = 8 * NT, PL = GJ_PLANE;
+    double* Ps = scr;
+    double* Ws = scr + 4 * PL;
+    double* vs = scr + 8 * PL;
     const int r = lane >> 2, j = lane & 3;
     const bool rowlane = lane < N;
     bool ok = true;
 #pragma unroll
     for (int s = 0; s < 2 * NT; ++s) {
         const int tk = s >> 1, half = s & 1;
-        // 1. publish the column panel of T = -S
+        // 1. publish the column panel of T = -S (plane [col][row]) and the rhs
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             if (t <= tk) {
-                if ((j >> 1) == half)
-                    *reinterpret_cast<double2*>(Ps + (8 * t + r) * 4 + 2 * (j & 1)) = make_double2(c[tri_idx(t, tk, NT)][0], c[tri_idx(t, tk, NT)][1]);
+                if ((j >> 1) == half) {
+                    Ps[(2 * (j & 1)) * PL + 8 * t + r] = c[tri_idx(t, tk, NT)][0];
+                    Ps[(2 * (j & 1) + 1) * PL + 8 * t + r] = c[tri_idx(t, tk, NT)][1];
+                }
             } else {
                 if ((r >> 2) == half) {
-                    Ps[(8 * t + 2 * j) * 4 + (r & 3)] = c[tri_idx(tk, t, NT)][0];
-                    Ps[(8 * t + 2 * j + 1) * 4 + (r & 3)] = c[tri_idx(tk, t, NT)][1];
+                    Ps[(r & 3) * PL + 8 * t + 2 * j] = c[tri_idx(tk, t, NT)][0];
+                    Ps[(r & 3) * PL + 8 * t + 2 * j + 1] = c[tri_idx(tk, t, NT)][1];
                 }
             }
         }
+        vs[lane] = v;
         __syncwarp();
-        // 2. lane = row: four sweeps on the (negated) panel y = -x and on the right-hand side
-        double y[4] = {0.0, 0.0, 0.0, 0.0};
-        if (rowlane) {
-            const double2 a0 = *reinterpret_cast<const double2*>(Ps + lane * 4), a1 = *reinterpret_cast<const double2*>(Ps + lane * 4 + 2);
-            y[0] = a0.x; y[1] = a0.y; y[2] = a1.x; y[3] = a1.y;
+        // 2. lane = row
+        double a[4][4], vk[4], y[4] = {0.0, 0.0, 0.0, 0.0}, gq[4], pq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 lo = *reinterpret_cast<const double2*>(Ps + q * PL + 4 * s), hi = *reinterpret_cast<const double2*>(Ps + q * PL + 4 * s + 2);
+            a[0][q] = lo.x; a[1][q] = lo.y; a[2][q] = hi.x; a[3][q] = hi.y;
         }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int kc = 4 * s + cc;
-            double pr[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pr[q] = __shfl_sync(0xffffffffu, y[q], kc);
-            const double prv = __shfl_sync(0xffffffffu, v, kc);
-            const double dpiv = neg_alu(pr[cc]);                    // the pivot of S
-            ok = ok && pivot_ok(dpiv);
-            const double id = rcp_pos(dpiv);
-            const bool piv = lane == kc;
-            // x[q] -= f*x_piv[q] with f = x[cc]/d (f = 1 - 1/d on the pivot row itself, whose entries equal the pivot row's)
-            // in terms of y = -x:  y[q] += g*pr[q], g = -f = y[cc]/d (pivot row: 1/d - 1);  v -= f*v_piv = v + g*v_piv
-            const double g = piv ? id - 1.0 : y[cc] * id;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q != cc) y[q] = fma(g, pr[q], y[q]);
-            v = fma(g, prv, v);
-            y[cc] = piv ? id : g;
+        {
+            const double2 lo = *reinterpret_cast<const double2*>(vs + 4 * s), hi = *reinterpret_cast<const double2*>(vs + 4 * s + 2);
+            vk[0] = lo.x; vk[1] = lo.y; vk[2] = hi.x; vk[3] = hi.y;
         }
         if (rowlane) {
-            *reinterpret_cast<double2*>(Ws + lane * 4) = make_double2(y[0], y[1]);
-            *reinterpret_cast<double2*>(Ws + lane * 4 + 2) = make_double2(y[2], y[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) y[q] = Ps[q * PL + lane];
+        }
+        ok = gj_panel_sweeps(a, vk, y, v, lane - 4 * s, gq, pq) && ok;
+        __syncwarp();                                   // every lane has read the pivot block before rows are overwritten
+        if (rowlane) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { Ws[q * PL + lane] = gq[q]; Ps[q * PL + lane] = pq[q]; }
         }
         __syncwarp();
         // 3. fragments and the rank-4 update of every stored tile
         double pf[NT], wf[NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { pf[t] = Ps[(8 * t + r) * 4 + j]; wf[t] = Ws[(8 * t + r) * 4 + j]; }
-        if (r == 4 * half + j) { pf[tk] += 1.0; wf[tk] -= 1.0; }
+        for (int t = 0; t < NT; ++t) { pf[t] = Ps[j * PL + 8 * t + r]; wf[t] = Ws[j * PL + 8 * t + r]; }
 #pragma unroll
         for (int ti = 0; ti < NT; ++ti)
 #pragma unroll
