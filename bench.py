@@ -261,6 +261,57 @@ def run_c2(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ one process, N devices
+def run_single_process(args, L, M, H, kind, flags, desc):
+    """The same workload through vbmf_b200_mctx_* (one host process, one host thread per GPU inside the library): what a Julia
+    caller gets from b200_context(0:N-1).  Each step is one whole-loop call on FULL-SIZE host parameter arrays (scatter of
+    AHat to the devices, K iterations, gather), Y resident; timed by the wall clock of the call."""
+    import vbmf_b200_loader
+    vb = vbmf_b200_loader.load()
+    lib = vb._lib.load()
+    mc = vb.MultiContext(devices=list(range(args.gpus)))
+    mc.synth(L, M, rank=H // 2, noise=0.1, seed=SEED)
+
+    class Shape:
+        shape = (L, M)
+    rng = np.random.default_rng(SEED + 1)
+    if kind == "dense":
+        p = vb.vbmf_init(Shape, H, rng=rng)
+        call = lambda n: vb.vbmf_(None, p, n, eps=0.0, est_covs="est_covs" in flags, est_var="est_var" in flags, ctx=mc, yhat=False)
+    elif kind == "sparse":
+        p = vb.vbmf_sparse_init(Shape, H, rng=rng, trYTY=mc.trYTY())
+        call = lambda n: vb.vbmf_sparse_(None, p, n, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags, ctx=mc, yhat=False)
+    else:
+        p = vb.vbmf_dual_init(Shape, H, H // 2, rng=rng, trYTY=mc.trYTY())
+        call = lambda n: vb.vbmf_dual_(None, p, n, eps=0.0, full_cov="full_cov" in flags, est_cb="est_cb" in flags,
+                                       est_priors="est_priors" in flags, ctx=mc, yhat=False)
+    call(args.warmup)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.15)
+    n0 = lib.vbmf_b200_launch_count()
+    t0 = time.time()
+    w0 = time.perf_counter()
+    call(args.steps)
+    w = time.perf_counter() - w0
+    t1 = time.time()
+    launches = lib.vbmf_b200_launch_count() - n0
+    clocks = sampler.stop(t0, t1)
+    state_check = {"iterations": args.warmup + args.steps, "norm_BHat_fro": float(np.linalg.norm(p.BHat)),
+                   "norm_AHat_fro": float(np.linalg.norm(p.AHat)), "trace_SigmaB": float(np.trace(p.SigmaB)),
+                   "trace_SigmaA": float(np.trace(p.SigmaA)), "noise": float(p.sigma2) if kind == "dense" else float(p.sigmaHat)}
+    line = {"metric": "VB iterations/s at %dx%dx%d (%s, Float64)" % (L, M, H, "dense vbmf" if kind == "dense" else "vbmf_" + kind),
+            "mode": "single_process", "value": args.steps / w, "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": w / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "global_shape": [L, M, H], "parallelism": "ONE host process, %d devices: vbmf_b200_mctx_* (ncclCommInitAll, "
+                       "one host thread per device inside the library)" % args.gpus,
+                       "timing": "wall clock of one whole-loop call on full-size host parameter arrays: scatter of AHat, %d iterations, gather; "
+                                 "Y resident" % args.steps},
+            "iteration_frac_of_peak": 4.0 * L * M * H / (w / args.steps) / (args.gpus * FP64_PEAK_TFLOPS * 1e12),
+            "gpu_launches": int(launches), "clocks": clocks, "state_check": state_check}
+    print(json.dumps(line), flush=True)
+    mc.close()
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -270,6 +321,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c2"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive --gpus N devices from THIS process through the multi-device context (vbmf_b200_mctx_*), the path a "
+                         "one-process Julia caller uses; no torchrun")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -283,6 +337,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, L, M, H, kind, flags, desc)
+        return
+    if args.single_process:
+        run_single_process(args, L, M, H, kind, flags, desc)
         return
 
     import torch

@@ -253,8 +253,10 @@ int vbmf_b200_solver_yhat(vbmf_b200_solver* s, double* YHat, int64_t ld);
  * runs for every test bag and class model (examples/mil_util.jl:504-511; class_alg = "vbls" :470-478 for dense parameters).
  * kind = VBMF_B200_DENSE, _SPARSE, _DUAL or _TRIAL (the four branches of vbls!, :182-197); states[p] points to the matching
  * state struct of problem p, Y[p] to its L x states[p]->M matrix.  All problems share L, H (and H0); M (and M0) may differ.
- * flags: VBMF_B200_FULL_COV (ignored for dense).  Needs no attached Y.  Limits: H <= 32, no labels, no diag_var; dense
- * problems need a diagonal invCA (what vbmf_init creates and updateCA! maintains). */
+ * flags: VBMF_B200_FULL_COV, VBMF_B200_DIAG_VAR (both ignored for dense).  Needs no attached Y.  Limits: H <= 64 for sparse / dual /
+ * trial (H > 32 with full_cov inverts one column at a time with the whole CTA) and H <= 32 for dense, no labels, the whole
+ * problem must fit one CTA's shared memory (an error names the size otherwise); dense problems need a diagonal invCA (what
+ * vbmf_init creates and updateCA! maintains). */
 int vbmf_b200_batched_vbls(vbmf_b200_ctx* ctx, int kind, int64_t nprob, const double* const* Y, void* const* states,
                            int64_t niter, int flags);
 

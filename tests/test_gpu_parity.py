@@ -806,3 +806,52 @@ def test_checkpoint_resume(G, ctx, tmp_path):
     for f in ("AHat", "BHat", "SigmaA", "SigmaB", "CA", "CB"):
         assert G.rel(getattr(r, f), log[f][..., 100]) < TOL, f
     assert abs(r.sigma2 - log["sigma2"][100]) <= TOL * abs(log["sigma2"][100])
+
+
+# ------------------------------------------------------------------------------------------------ batched vbls!: diag_var and H > 32
+@pytest.mark.parametrize("kind,full_cov,H,Mmax", [("sparse", True, 12, 30), ("sparse", False, 12, 30), ("dual", True, 20, 40), ("dual", False, 9, 25),
+                                                  ("trial", True, 10, 20)])
+def test_vbls_batched_diag_var(G, ctx, kind, full_cov, H, Mmax):
+    """vbls!(Y, params, niter; diag_var = true, full_cov) (examples/mil_util.jl:179-203): heteroscedastic noise in the
+    one-CTA-per-problem kernel -- B'diag(sv)B, B'diag(sv)Y and the per-row zeta / sigmaVecHat are per-iteration quantities."""
+    rng = np.random.default_rng(23)
+    L, nprob, niter = 17, 24, 8
+    Ys, ps, qs = [], [], []
+    for b in range(nprob):
+        M = int(rng.integers(2, Mmax + 1))
+        Y = 3.0 * synth(L, M, 3, seed=300 + b)
+        if kind == "sparse":
+            p = vo.vbmf_sparse_init(Y, H, rng=rng)
+        elif kind == "trial":
+            p = vo.vbmf_trial_init(Y, H, H - 2, M // 2, rng=rng)
+        else:
+            p = vo.vbmf_dual_init(Y, H, H - 1, rng=rng)
+        p.SigmaB = np.diag(rng.uniform(1e-3, 1e-2, H))
+        p.sigmaVecHat = rng.uniform(0.5, 2.0, L)
+        Ys.append(np.asfortranarray(Y)); ps.append(p); qs.append(G.to_gpu_params(p))
+    G.vb.vbls_batched_(Ys, qs, niter, full_cov=full_cov, diag_var=True, ctx=ctx)
+    for Y, p, q in zip(Ys, ps, qs):
+        vo.vbls(Y, p, niter, full_cov=full_cov, diag_var=True)
+        G.compare(q, p, TOL, ["AHat", "ATVecHat", "diagSigmaATVec", "SigmaA", "CA", "beta", "sigmaVecHat", "zetaVec"])
+        assert G.rel(q.YHat, p.YHat) < TOL
+
+
+@pytest.mark.parametrize("kind,full_cov,diag_var,H", [("sparse", False, False, 48), ("sparse", True, False, 40), ("dual", True, True, 36), ("dual", False, False, 64)])
+def test_vbls_batched_wide_rank(G, ctx, kind, full_cov, diag_var, H):
+    """32 < H <= 64 in the batched path (full_cov: one column at a time, the whole CTA on one shared-memory matrix)."""
+    rng = np.random.default_rng(29)
+    L, nprob, niter = 20, 6, 5
+    Ys, ps, qs = [], [], []
+    for b in range(nprob):
+        M = int(rng.integers(2, 13))
+        Y = 2.0 * synth(L, M, 3, seed=700 + b)
+        p = vo.vbmf_sparse_init(Y, H, rng=rng) if kind == "sparse" else vo.vbmf_dual_init(Y, H, H // 2, rng=rng)
+        p.SigmaB = np.diag(rng.uniform(1e-3, 1e-2, H))
+        Ys.append(np.asfortranarray(Y)); ps.append(p); qs.append(G.to_gpu_params(p))
+    G.vb.vbls_batched_(Ys, qs, niter, full_cov=full_cov, diag_var=diag_var, ctx=ctx)
+    for Y, p, q in zip(Ys, ps, qs):
+        vo.vbls(Y, p, niter, full_cov=full_cov, diag_var=diag_var)
+        G.compare(q, p, TOL, ["AHat", "diagSigmaATVec", "SigmaA", "CA", "beta", "sigmaHat", "sigmaVecHat"])
+    with pytest.raises(G.vb.VBMFError, match="H <= 64|too large"):
+        Yb = np.asfortranarray(synth(L, 5, 2, seed=1))
+        G.vb.vbls_batched_([Yb], [G.to_gpu_params(vo.vbmf_sparse_init(Yb, 65, rng=rng))], 2, ctx=ctx)

@@ -905,11 +905,12 @@ class BatchedVbls:
         self.yp = (L_.p_f64 * self.n)(*[_ptr(Y) for Y in self.Ys])
         self.sp = (C.c_void_p * self.n)(*[C.addressof(st) for st in self.structs])
 
-    def run(self, niter, full_cov=False):
+    def run(self, niter, full_cov=False, diag_var=False):
         if self.n == 0:
             return 0
         rc = _not_pd(L_.check(self.ctx.lib.vbmf_b200_batched_vbls(self.ctx.h, self.kind, self.n, self.yp, self.sp, int(niter),
-                                                                  L_.FULL_COV if full_cov else 0), allow=(-2,)))
+                                                                  (L_.FULL_COV if full_cov else 0) | (L_.DIAG_VAR if diag_var else 0)),
+                              allow=(-2,)))
         self.failed = rc == -2
         return rc
 
@@ -919,13 +920,13 @@ class BatchedVbls:
         return [p.AHat for p in self.params]
 
 
-def vbls_batched_(Ys, params_list, niter, full_cov=False, ctx=None, yhat=True, keep_blocks=False):
+def vbls_batched_(Ys, params_list, niter, full_cov=False, diag_var=False, ctx=None, yhat=True, keep_blocks=False):
     """`vbls!` (examples/mil_util.jl:179-203) for many small problems in ONE kernel launch (one CTA per problem): the MIL
     classification pattern, classify(...; class_alg = "dual") runs it for every test bag and class model.  All params must
     be of one type (vbmf_parameters, vbmf_sparse_parameters, vbmf_dual_parameters or vbmf_trial_parameters - the four
     branches of vbls!) with the same L, H (and H0); M (and M0) may differ per problem."""
     batch = BatchedVbls(Ys, params_list, ctx=ctx, yhat=yhat, keep_blocks=keep_blocks)
-    batch.run(niter, full_cov=full_cov)
+    batch.run(niter, full_cov=full_cov, diag_var=diag_var)
     return batch.readback()
 
 

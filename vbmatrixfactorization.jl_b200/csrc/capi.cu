@@ -860,13 +860,29 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
         s->ata_local = true;
     } else {
         const bool dv = (flags & F_DIAG_VAR) != 0;
-        if (fused && !(flags & F_FULL_COV) && getenv("VBMF_B200_NO_DIAG_FUSION") == nullptr) {
+        // (H > 64: the fused kernel's 68 Gram accumulator registers leave one CTA per SM and it loses to the separate
+        //  passes, 0.74 vs 0.55 ms at 125000 x 128)
+        if (fused && !(flags & F_FULL_COV) && d.H <= 64 && getenv("VBMF_B200_NO_DIAG_FUSION") == nullptr) {
             // whole-loop diagonal path: slab sum, A, diag, mask, updateCA! and A'A in one pass over vec(A')
             if (enq_k1(s, dv, false) || wait_post(s)) return -1;
             const bool slabs = !s->c->simt && s->S1 > 1;
             if (k_sparse_A_diag_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, flags)) return -1;
             s->ata_valid = false; s->q_valid = false;
             s->ata_local = true; s->ca_done = true;
+            return 0;
+        }
+        if (fused && (flags & F_FULL_COV) && k_sparse_A_full_can_fuse(d) && getenv("VBMF_B200_K4_FUSION") != nullptr) {
+            // optional (VBMF_B200_K4_FUSION=1): the per-column inverse kernel sums the K1 slabs itself and, for the sparse kind,
+            // applies the label mask and updateCA! to the column it has just produced.  Measured neutral on the step time (the
+            // extra dependent global loads / stores sit on each warp's latency chain: 0.475 vs 0.415 ms + two small kernels),
+            // so the separate passes stay the default.
+            if (enq_k1(s, dv, false) || wait_post(s)) return -1;
+            const bool slabs = !s->c->simt && s->S1 > 1;
+            const int fuse_ca = d.kind == KIND_SPARSE ? 1 : 0;
+            if (k_sparse_A_full_ex(st, d, flags, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, fuse_ca)) return -1;
+            if (!fuse_ca && k_mask(st, d)) return -1;
+            s->ata_valid = false; s->q_valid = false; s->ata_local = false;
+            s->ca_done = fuse_ca != 0;
             return 0;
         }
         if (enq_k1(s, dv) || wait_post(s)) return -1;
@@ -1255,6 +1271,7 @@ struct BatchDesc {
     int nprob, L, H, H0, kind, niter, full_cov, Mmax;
     const int* moff; const double* Y; const double* B; const double* SigmaB;
     double* A; double* CA; double* beta; double* sdiag; double* SigmaA; double* blocks; double* YHat; double* scal;
+    int diag_var; double* sigmaVec; const double* etaVec; double* zetaVec;
 };
 struct BatchDenseDesc {
     int nprob, L, H, niter, Mmax;
@@ -1302,13 +1319,13 @@ template <class ST>
 static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const double* const* Y, void* const* states,
                              int64_t niter, int flags) {
     if (nprob <= 0) return 0;
-    if (flags & F_DIAG_VAR) { set_error("batched vbls: diag_var is not supported"); return -1; }
+    const bool dvar = (flags & F_DIAG_VAR) != 0;
     const ST* s0 = (const ST*)states[0];
     const int64_t L = s0->L, H = s0->H;
     constexpr bool IS_DUAL = std::is_same<ST, vbmf_b200_dual_state>::value, IS_TRIAL = std::is_same<ST, vbmf_b200_trial_state>::value;
     int64_t H0 = H;
     if constexpr (IS_DUAL || IS_TRIAL) H0 = s0->H0;
-    if (L < 1 || H < 1 || H > 32) { set_error("batched vbls supports 1 <= H <= 32 (got H = %lld)", (long long)H); return -1; }
+    if (L < 1 || H < 1 || H > 64) { set_error("batched vbls supports 1 <= H <= 64 (got H = %lld)", (long long)H); return -1; }
     if (H0 < 0 || H0 > H) { set_error("H must be at least H0!"); return -1; }
     std::vector<int> moff(nprob + 1, 0);
     int Mmax = 0;
@@ -1319,6 +1336,7 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         if (s->L != L || s->H != H || s->M < 1) { set_error("batched vbls: problem %lld has different L/H or M < 1", (long long)p); return -1; }
         if constexpr (IS_DUAL || IS_TRIAL) { if (s->H0 != H0) { set_error("batched vbls: H0 differs"); return -1; } }
         else { if (s->n_labels > 0 && s->H1 > 0) { set_error("batched vbls: labels are not supported"); return -1; } }
+        if (dvar && (s->sigmaVecHat == nullptr || s->etaVec == nullptr)) { set_error("batched vbls: diag_var needs sigmaVecHat / etaVec of problem %lld", (long long)p); return -1; }
         moff[p + 1] = moff[p] + (int)s->M;
         Mmax = std::max<int>(Mmax, (int)s->M);
         want_yhat = want_yhat || s->YHat != nullptr;
@@ -1333,8 +1351,10 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     const size_t o_moff = take((size_t)(nprob + 1) * 4), o_Y = take(L * Mtot * 8), o_B = take(nprob * LH * 8), o_SB = take(nprob * HH * 8);
     const size_t down_begin = off;
     const size_t o_CA = take(MH * 8), o_sc = take((size_t)nprob * 16 * 8);
+    const size_t o_sv = dvar ? take((size_t)nprob * L * 8) : 0, o_ev = dvar ? take((size_t)nprob * L * 8) : 0;
     const size_t up_end = off;
     const size_t o_A = take(MH * 8), o_beta = take(MH * 8), o_s = take(MH * 8), o_SA = take(nprob * HH * 8);
+    const size_t o_zv = dvar ? take((size_t)nprob * L * 8) : 0;
     const size_t o_YH = want_yhat ? take(L * Mtot * 8) : 0, o_blk = want_blocks ? take(MH * H * 8) : 0;
     const size_t total = off;
     if (batch_reserve(c, total)) return -1;
@@ -1350,6 +1370,10 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         memcpy(&hB[p * LH], s->BHat, LH * 8);
         memcpy(&hSB[p * HH], s->SigmaB, HH * 8);
         memcpy(&hCA[(size_t)moff[p] * H], s->CA, (size_t)s->M * H * 8);
+        if (dvar) {
+            memcpy((double*)(hb + o_sv) + (size_t)p * L, s->sigmaVecHat, (size_t)L * 8);
+            memcpy((double*)(hb + o_ev) + (size_t)p * L, s->etaVec, (size_t)L * 8);
+        }
         double* sc = &hsc[(size_t)p * 16];
         sc[0] = s->sigmaHat; sc[1] = s->eta; sc[2] = s->zeta; sc[3] = s->zeta0; sc[4] = s->trYTY;
         if constexpr (IS_DUAL) { sc[7] = s->alpha00; sc[8] = s->beta00; sc[9] = s->alpha01; sc[10] = s->beta01; }
@@ -1368,6 +1392,9 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
     bd.A = (double*)(db + o_A); bd.CA = (double*)(db + o_CA); bd.beta = (double*)(db + o_beta); bd.sdiag = (double*)(db + o_s);
     bd.SigmaA = (double*)(db + o_SA); bd.blocks = want_blocks ? (double*)(db + o_blk) : nullptr; bd.YHat = want_yhat ? (double*)(db + o_YH) : nullptr;
     bd.scal = (double*)(db + o_sc);
+    bd.diag_var = dvar ? 1 : 0;
+    bd.sigmaVec = dvar ? (double*)(db + o_sv) : nullptr; bd.etaVec = dvar ? (const double*)(db + o_ev) : nullptr;
+    bd.zetaVec = dvar ? (double*)(db + o_zv) : nullptr;
     prof_mark(c, c->ev_k1);       // profiling: the kernel alone (read back through vbmf_b200_ctx_profile_read, K1 slot)
     if (bd.niter > 0) rc = k_batched_vbls(st, bd);
     prof_mark(c, c->ev_k1);
@@ -1393,6 +1420,10 @@ static int batched_vbls_impl(vbmf_b200_ctx* c, int kind, int64_t nprob, const do
         if (s->SigmaA) memcpy(s->SigmaA, &hSA[p * HH], HH * 8);
         if (s->YHat) memcpy(s->YHat, &hYH[(size_t)moff[p] * L], M * L * 8);
         if (s->SigmaATVec_blocks) memcpy(s->SigmaATVec_blocks, &hblk[o * H], M * HH * 8);
+        if (dvar) {
+            if (s->sigmaVecHat) memcpy(s->sigmaVecHat, (const double*)(hb + o_sv) + (size_t)p * L, (size_t)L * 8);
+            if (s->zetaVec) memcpy(s->zetaVec, (const double*)(hb + o_zv) + (size_t)p * L, (size_t)L * 8);
+        }
         s->sigmaHat = sc[0]; s->zeta = sc[2];
         if constexpr (IS_TRIAL) {
             s->alpha1 = sc[11]; s->alpha2 = sc[12]; s->alpha3 = sc[6];

@@ -832,7 +832,7 @@ int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags) {
 // (accumulators in registers across the CTA's tiles); column sums of s (-> diag SigmaA) and the group sums of the dual /
 // trial hyper-prior updates are carried per thread.  Partials per CTA: [H*H Gram | HP8 column sums | 8 group sums].
 template <int GT>   // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
-__global__ void __launch_bounds__(256, (GT <= 5 ? 3 : 1)) sparse_A_diag_fused_kernel(Dev d, const double* __restrict__ slabs, int S,
+__global__ void __launch_bounds__(256, (GT <= 5 ? 2 : 1)) sparse_A_diag_fused_kernel(Dev d, const double* __restrict__ slabs, int S,
                                                                                     size_t slab_stride, int diag_var) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
@@ -884,23 +884,45 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 3 : 1)) sparse_A_diag_fused_ke
             s_q0[threadIdx.x] = q0; s_r0[threadIdx.x] = r0;
         }
         __syncthreads();
+        // global loads in chunks of KCH elements per thread (independent, many in flight), then the arithmetic of the chunk:
+        // one element at a time would serialise ~4 DRAM round trips per element (measured: 1.2 ms at 125000 x 128)
+        constexpr int KCH = KMAX < 8 ? KMAX : (GT <= 5 ? 8 : 4);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
+        for (int k0 = 0; k0 < KMAX; k0 += KCH) {
+        double pre_p[KCH], pre_ca[KCH];
+#pragma unroll
+        for (int kk = 0; kk < KCH; ++kk) {
+            const int e = threadIdx.x + 256 * (k0 + kk);
+            const int i = e / HP8, c = e - i * HP8;
+            double p = 0.0, ca = 1.0;
+            if (e < nel && i < nr && c < H) {
+                const size_t idx = (size_t)(m0 + i) * H + c;
+                const double p0 = slabs[idx], p1 = S > 1 ? slabs[slab_stride + idx] : 0.0, p2 = S > 2 ? slabs[2 * slab_stride + idx] : 0.0;
+                ca = d.CAv[idx];
+                p = p0;
+                if (S > 1) p += p1;
+                if (S > 2) p += p2;
+                for (int s2 = 3; s2 < S; ++s2) p += slabs[(size_t)s2 * slab_stride + idx];
+            }
+            pre_p[kk] = p; pre_ca[kk] = ca;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KCH; ++kk) {
+            const int k = k0 + kk;
             const int e = threadIdx.x + 256 * k;
             if (e < nel) {
                 const int i = e / HP8, c = e - i * HP8;
                 double a = 0.0;
                 if (i < nr && c < H) {
                     const size_t idx = (size_t)(m0 + i) * H + c;
-                    double p = slabs[idx];
-                    for (int s2 = 1; s2 < S; ++s2) p += slabs[(size_t)s2 * slab_stride + idx];
+                    const double p = pre_p[kk], ca_in = pre_ca[kk];
                     const long long mg = (long long)d.moff + m0 + i;
                     int src = c;
                     if (mg > 0) {
                         const long long rr = (long long)s_r0[i] + c;
                         src = (int)(s_q0[i] + (rr >= Mg1 ? (Mg1 >= H ? 1 : rr / Mg1) : 0));
                     }
-                    const double sv = 1.0 / (dv[src] + d.CAv[idx]);
+                    const double sv = 1.0 / (dv[src] + ca_in);
                     a = diag_var ? sv * p : (sh * sv) * p;
                     if (d.rowmask != nullptr && c >= hmask && d.rowmask[m0 + i]) a = 0.0;
                     const int grp = (!grouped || c < d.H0) ? 0 : (mg < d.M0 ? 1 : 2);
@@ -918,6 +940,7 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 3 : 1)) sparse_A_diag_fused_ke
                 }
                 An[i * ld + c] = a;
             }
+        }
         }
         __syncthreads();
 #pragma unroll
@@ -990,7 +1013,7 @@ int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, in
     const int H = d.H, HP8 = (H + 7) & ~7;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
     const size_t smem = sparse_diag_fused_smem(H);
-    const int per_sm = HP8 <= 64 ? 3 : 1;
+    const int per_sm = HP8 <= 64 ? 2 : 1;
     const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), 32), 148 * per_sm));
     if (HP8 <= 32) sparse_A_diag_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
     else if (HP8 <= 64) sparse_A_diag_fused_kernel<5><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
@@ -1142,7 +1165,8 @@ __global__ void __launch_bounds__(256, 2) sparse_A_full_warp_kernel(Dev d, int d
 // (ACCS = true: 40 registers less, one more CTA per SM).  Shared memory: G as accumulator-layout tiles (read once per matrix
 // with conflict-free 128-bit loads), 2.5 KB of scratch per warp.
 template <int NT, int MINB, bool ACCS>
-__global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, int diag_var, int nwarps_total) {
+__global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, int diag_var, int nwarps_total, const double* __restrict__ slabs,
+                                                                        int S, size_t slab_stride, int fuse_ca) {
     ACTIVE_OR_RETURN(d);
     constexpr int NTRI = NT * (NT + 1) / 2, WPC = 4, SCR = GJ_SCRATCH + 64;
     extern __shared__ __align__(16) double wsm[];
@@ -1179,8 +1203,18 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
     __syncthreads();
     bool all_ok = true;
     for (int m = gw; m < d.Mloc; m += nwarps_total) {
-        const double ca = live ? d.CAv[(size_t)m * H + lane] : 1.0;       // padded rows / columns: identity
-        const double p = live ? d.P[(size_t)m * H + lane] : 0.0;
+        // inputs of column m: CA_m (padded rows / columns: identity) and (Y'B)[m, :] = fixed-order sum of the K1 split-K slabs.
+        // (Fetching them one column ahead with cp.async measured 12 % SLOWER, 0.454 vs 0.407 ms: plain loads stay.)
+        double ca = 1.0, p = 0.0;
+        if (live) {
+            const size_t idx = (size_t)m * H + lane;
+            ca = d.CAv[idx];
+            const double p0 = slabs[idx], p1 = S > 1 ? slabs[slab_stride + idx] : 0.0, p2 = S > 2 ? slabs[2 * slab_stride + idx] : 0.0;
+            p = p0;
+            if (S > 1) p += p1;
+            if (S > 2) p += p2;
+            for (int s2 = 3; s2 < S; ++s2) p += slabs[(size_t)s2 * slab_stride + idx];
+        }
         const double sl = rsqrt(gll + ca);
         sv[lane] = sl;
         cav[lane] = ca;
@@ -1206,7 +1240,9 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
         double v = p * sl;
         const bool ok = warp_block_gj_sym<NT>(c, v, lane, scr);
         all_ok = all_ok && ok;
-        if (live) d.A[(size_t)m * H + lane] = ok ? (diag_var ? sl * v : (sh * sl) * v) : nan("");
+        double aval = ok ? (diag_var ? sl * v : (sh * sl) * v) : nan("");
+        if (fuse_ca && d.rowmask != nullptr && lane >= H - d.H1 && d.rowmask[m]) aval = 0.0;       // label mask (src/vbmf_sparse.jl:245)
+        if (live) d.A[(size_t)m * H + lane] = aval;
         // Sigma_m = D*c*D: un-equilibrate (the scale vector is re-read: holding it across the sweeps costs 24 registers) fused
         // with the running sum; the diagonal (and the blocks on request) are emitted separately
         double srow[NT];
@@ -1228,7 +1264,11 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
                     acc[ACCS ? 0 : t][1] = fma(c[t][1], w1, acc[ACCS ? 0 : t][1]);
                 }
                 const int row = 8 * ti + r, col = 8 * tj + 2 * j;
-                if (ti == tj && j == (r >> 1) && row < H) d.sdiag[(size_t)m * H + row] = ok ? ((r & 1) ? c[t][1] * w1 : c[t][0] * w0) : nan("");
+                if (ti == tj && j == (r >> 1)) {
+                    const double sd = ok ? ((r & 1) ? c[t][1] * w1 : c[t][0] * w0) : nan("");
+                    if (row < H) d.sdiag[(size_t)m * H + row] = sd;
+                    if (fuse_ca) cav[row] = sd;
+                }
                 if (d.blocks != nullptr && row < H) {
                     double* blk = d.blocks + (size_t)m * H * H;
                     const double s0 = c[t][0] * w0, s1 = c[t][1] * w1;
@@ -1236,6 +1276,14 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
                     if (col + 1 < H) { blk[row * H + col + 1] = s1; if (ti != tj) blk[(col + 1) * H + row] = s1; }
                 }
             }
+        __syncwarp();
+        if (fuse_ca && live) {
+            // updateCA! of the sparse kind for this column (src/vbmf_sparse.jl:284-288): it only needs a, diag(Sigma_m) and
+            // replicated scalars, so doing it here saves one pass over vec(A')
+            const double beta = sc->beta0p + 0.5 * (aval * aval + cav[lane]);
+            d.beta[(size_t)m * H + lane] = beta;
+            d.CAv[(size_t)m * H + lane] = sc->alpha / beta;
+        }
         __syncwarp();
     }
     if (!all_ok && lane == 0) d.sc->chol_fail = 1;
@@ -1259,26 +1307,35 @@ __global__ void __launch_bounds__(128, MINB) sparse_A_full_dmma_kernel(Dev d, in
 }
 template <int NT> static size_t k4_dmma_smem() { return (size_t)(NT * (NT + 1) / 2 * 64 + 4 * (GJ_SCRATCH + 64) + 4 * (NT * (NT + 1) / 2) * 64) * sizeof(double); }
 
-int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) {
+static bool k4_use_reg() {
+    static const bool v = getenv("VBMF_B200_K4") != nullptr && strcmp(getenv("VBMF_B200_K4"), "reg") == 0;
+    return v;
+}
+bool k_sparse_A_full_can_fuse(const Dev& d) { return d.H <= 32 && !k4_use_reg(); }
+int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags) { return k_sparse_A_full_ex(st, d, flags, d.P, 1, 0, 0); }
+// slabs / S / slab_stride: the K1 output (S split-K slabs or the single P buffer); fuse_ca: also do updateCA! of the sparse kind
+// (tensor-core path, H <= 32, only; the caller checks *did_ca)
+int k_sparse_A_full_ex(cudaStream_t st, const Dev& d, int flags, const double* slabs, int S, size_t slab_stride, int fuse_ca) {
     const int H = d.H;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
     build_G_kernel<<<1, 256, 0, st>>>(d, dv);
     VB_LAUNCH_OK();
     int ngroups;
-    static const bool use_reg = getenv("VBMF_B200_K4") != nullptr && strcmp(getenv("VBMF_B200_K4"), "reg") == 0;
+    const bool use_reg = k4_use_reg();
+    if ((S > 1 || fuse_ca) && !k_sparse_A_full_can_fuse(d)) { set_error("k_sparse_A_full_ex: slab / updateCA fusion needs the tensor-core path"); return -1; }
     if (H <= 32 && !use_reg) {
         static const int minb = getenv("VBMF_B200_K4_MINB") ? atoi(getenv("VBMF_B200_K4_MINB")) : 4;     // tuning probe: 2, 3 (sums in registers), 4 / 5 (sums in shared memory; 4 CTAs per SM measured fastest: 0.407 vs 0.435 ms for 1e5 32 x 32)
         const int wpc = 4;
         const int per_sm = (H <= 16) ? 4 : (H <= 24 ? 3 : (minb == 5 ? 3 : minb));
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * per_sm));
         ngroups = grid;                                   // one partial per CTA
-        if (H <= 8) sparse_A_full_dmma_kernel<1, 4, false><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc);
-        else if (H <= 16) sparse_A_full_dmma_kernel<2, 4, false><<<grid, 128, k4_dmma_smem<2>(), st>>>(d, dv, grid * wpc);
-        else if (H <= 24) sparse_A_full_dmma_kernel<3, 3, false><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc);
-        else if (minb == 2) sparse_A_full_dmma_kernel<4, 2, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
-        else if (minb == 4) sparse_A_full_dmma_kernel<4, 4, true><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
-        else if (minb == 5) sparse_A_full_dmma_kernel<4, 3, true><<<std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)), 128, k4_dmma_smem<4>(), st>>>(d, dv, std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)) * wpc);
-        else sparse_A_full_dmma_kernel<4, 3, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc);
+        if (H <= 8) sparse_A_full_dmma_kernel<1, 4, false><<<grid, 128, k4_dmma_smem<1>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
+        else if (H <= 16) sparse_A_full_dmma_kernel<2, 4, false><<<grid, 128, k4_dmma_smem<2>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
+        else if (H <= 24) sparse_A_full_dmma_kernel<3, 3, false><<<grid, 128, k4_dmma_smem<3>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
+        else if (minb == 2) sparse_A_full_dmma_kernel<4, 2, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
+        else if (minb == 4) sparse_A_full_dmma_kernel<4, 4, true><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
+        else if (minb == 5) sparse_A_full_dmma_kernel<4, 3, true><<<std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)), 128, k4_dmma_smem<4>(), st>>>(d, dv, std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 148 * 3)) * wpc, slabs, S, slab_stride, fuse_ca);
+        else sparse_A_full_dmma_kernel<4, 3, false><<<grid, 128, k4_dmma_smem<4>(), st>>>(d, dv, grid * wpc, slabs, S, slab_stride, fuse_ca);
     } else if (H <= 32) {
         const int wpc = 8;
         const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), wpc), 296));
