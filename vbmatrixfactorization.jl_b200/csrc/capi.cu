@@ -410,6 +410,8 @@ struct vbmf_b200_solver {
     size_t arena_bytes = 0;
     double* Qpart = nullptr;
     int S = 1, kchunk = 16;
+    bool k2_sk = false;           // K2 uses the stream-K decomposition (gemm_dmma.cu)
+    int sk_kq = 64, sk_nk = 1, sk_grid = 1, sk_smax = 1;
     double* Ppart = nullptr;      // split-K slabs of K1 (nullptr when S1 == 1)
     int S1 = 1, kbs1 = 1;
     int* d_labels = nullptr;
@@ -464,6 +466,15 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
     plan_splitk_ytb(d.L, d.Mloc, d.H, c->num_sms, &s->S1, &s->kbs1);
     if (c->simt) s->S1 = 1;
     s->k2_simt = c->simt || (H % 2 != 0);       // the A tensor map needs a 16-byte row pitch
+    {   // stream-K for K2: opt-in (VBMF_B200_K2=streamk).  It removes the 16 slabs of L x H (reduction 28 -> 18 us at
+        // 20000 x 25000 x 64) but the kernel itself measured 4-5 % slower than the classic split (15.0 vs 14.4 ms at config 3,
+        // 1.89 vs 1.82 ms on a 25000-column shard: the tile-change test, the flush path and 26 more registers), so the
+        // classic decomposition stays the default.
+        const char* e = getenv("VBMF_B200_K2");
+        const bool want = e != nullptr && strcmp(e, "streamk") == 0;
+        s->k2_sk = !s->k2_simt && want && d.Mloc > 0;
+        if (s->k2_sk) plan_streamk(d.L, d.Mloc, d.H, c->num_sms, &s->sk_kq, &s->sk_nk, &s->sk_grid, &s->sk_smax);
+    }
 
     const size_t MH = (size_t)std::max(d.Mloc, 1) * H, LH = (size_t)H * d.ldB, HH = (size_t)H * H, Lr = (size_t)d.L;
     const size_t part_elems = std::max<size_t>({(size_t)MAX_PARTS * HH, (size_t)2400 * std::min<size_t>(H, 32) * std::min<size_t>(H, 32),
@@ -473,7 +484,7 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
         {&d.A, MH}, {&d.P, MH}, {&d.B, LH}, {&d.Bold, LH}, {&d.D, LH}, {&d.Bs, LH}, {&d.packed, LH + 2 * HH + 8},
         {&d.SigmaA, HH}, {&d.SigmaB, HH}, {&d.BtB, HH}, {&d.BtBw, HH}, {&d.DtD, HH}, {&d.Gm, HH},
         {&d.sigmaVec, Lr}, {&d.etaVec, Lr}, {&d.zetaVec, Lr}, {&d.part, part_elems}, {&d.lbacc, 32},
-        {&s->Qpart, (size_t)s->S * LH},
+        {&s->Qpart, (size_t)std::max(s->S, s->k2_sk ? s->sk_smax : 1) * LH},
     };
     if (s->S1 > 1) items.push_back({&s->Ppart, (size_t)s->S1 * MH});
     if (kind == VBMF_B200_DENSE) { items.push_back({&d.CA, HH}); items.push_back({&d.CB, HH}); items.push_back({&d.invCA, HH}); items.push_back({&d.invCB, HH}); }
@@ -814,9 +825,11 @@ static int enq_k2(vbmf_b200_solver* s) {
     prof_mark(c, c->ev_k2);
     int rc;
     if (s->k2_simt) rc = launch_gemm_ya_simt(c->st, d.Y, d.ldY, d.A, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc);
+    else if (s->k2_sk) rc = launch_gemm_ya_sk(c->st, &c->tmY2, &s->tmA, s->Qpart, d.packed + packed_q(d), d.L, d.Mloc, d.H, d.ldB, s->sk_kq, s->sk_nk, s->sk_grid, d.sc);
     else rc = launch_gemm_ya(c->st, &c->tmY2, &s->tmA, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc, c->num_sms);
     prof_mark(c, c->ev_k2);
     if (rc) return rc;
+    if (s->k2_sk) return launch_reduce_q_sk(c->st, s->Qpart, d.packed + packed_q(d), d.L, d.Mloc, d.H, d.ldB, s->sk_nk, s->sk_grid, d.sc);
     return k_reduce_q(c->st, d, s->Qpart, s->S);
 }
 // Grams of the current BHat that the A update / CB / sigma need
@@ -1182,6 +1195,10 @@ extern "C" int vbmf_b200_gemm_YA(vbmf_b200_ctx* c, const double* A, int64_t H, d
     const size_t MH = (size_t)std::max(c->Mloc, 1) * H;
     int S = 1, kchunk = 16;
     plan_splitk(c->L, c->Mloc, (int)H, c->num_sms, &S, &kchunk);
+    int kq = 64, nk = 1, skgrid = 1, smax = 1;
+    const char* ek2 = getenv("VBMF_B200_K2");
+    const bool use_sk = !(c->simt || (H % 2 != 0)) && c->Mloc > 0 && ek2 != nullptr && strcmp(ek2, "streamk") == 0;
+    if (use_sk) { plan_streamk(c->L, c->Mloc, (int)H, c->num_sms, &kq, &nk, &skgrid, &smax); S = std::max(S, smax); }
     double *dA = nullptr, *dT = nullptr, *dQp = nullptr, *dQ = nullptr;
     VB_CUDA_OK(cudaMalloc(&dA, MH * 8));
     VB_CUDA_OK(cudaMalloc(&dT, MH * 8));
@@ -1196,10 +1213,13 @@ extern "C" int vbmf_b200_gemm_YA(vbmf_b200_ctx* c, const double* A, int64_t H, d
         else {
             CUtensorMap tmA;
             if (c->Mloc > 0) rc = make_tmap_2d(&tmA, dA, (uint64_t)H, (uint64_t)c->Mloc, (uint64_t)H * 8, 16, 16);
-            if (!rc) rc = launch_gemm_ya(c->st, &c->tmY2, &tmA, dQp, c->L, c->Mloc, (int)H, ldQ, kchunk, S, nullptr, c->num_sms);
+            if (!rc && use_sk) {
+                rc = launch_gemm_ya_sk(c->st, &c->tmY2, &tmA, dQp, dQ, c->L, c->Mloc, (int)H, ldQ, kq, nk, skgrid, nullptr);
+                if (!rc) rc = launch_reduce_q_sk(c->st, dQp, dQ, c->L, c->Mloc, (int)H, ldQ, nk, skgrid, nullptr);
+            } else if (!rc) rc = launch_gemm_ya(c->st, &c->tmY2, &tmA, dQp, c->L, c->Mloc, (int)H, ldQ, kchunk, S, nullptr, c->num_sms);
         }
     }
-    if (!rc) {
+    if (!rc && !use_sk) {
         Dev d; memset(&d, 0, sizeof(d));
         d.H = (int)H; d.ldB = ldQ; d.L = c->L; d.packed = dQ;
         Scalars* none = nullptr; d.sc = none;

@@ -591,7 +591,9 @@ static int hxh_launch(cudaStream_t st, const Dev& d, int mode, int dv) {
     static const bool use_reg = getenv("VBMF_B200_HXH") != nullptr && strcmp(getenv("VBMF_B200_HXH"), "reg") == 0;
     if (!use_reg) {
         const int H = d.H;
+        static const bool one_warp = getenv("VBMF_B200_HXH") != nullptr && strcmp(getenv("VBMF_B200_HXH"), "warp") == 0;
         if (H <= 8) hxh_warp_kernel<1><<<1, 32, 0, st>>>(d, mode, dv);
+        else if (H <= 32 && !one_warp) hxh_dmma_kernel<4, 1><<<1, 512, 0, st>>>(d, mode, dv);   // 16 warps, one tile each: 26 -> ~10 us at H = 32
         else if (H <= 16) hxh_warp_kernel<2><<<1, 32, 0, st>>>(d, mode, dv);
         else if (H <= 24) hxh_warp_kernel<3><<<1, 32, 0, st>>>(d, mode, dv);
         else if (H <= 32) hxh_warp_kernel<4><<<1, 32, 0, st>>>(d, mode, dv);
