@@ -484,7 +484,9 @@ def main():
                 "k1_ms": k1, "k2_ms": k2, "k1_tflops": flops_per_launch / k1 * 1e-9 if k1 else None,
                 "k2_tflops": flops_per_launch / k2 * 1e-9 if k2 else None,
                 "iteration_frac_of_peak": 4.0 * L * M * H / (ms / args.steps * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
-                "contraction_share_of_step": (k1 + k2) / (ms / args.steps)}
+                "contraction_share_of_step": (k1 + k2) / (ms / args.steps),
+                # the per-iteration packed all-reduce (N > 1), CUDA events on the launching stream of rank 0
+                "allreduce_ms": (prof["allreduce_ms"] / prof["allreduce_launches"]) if prof.get("allreduce_launches") else None}
 
     # ---- e2e: the public API with every input in pinned host memory (upload Y + params, K iterations, download)
     e2e = None

@@ -180,7 +180,11 @@ int vbmf_b200_nccl_unique_id(void* id128);
 /* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's current stream) or NULL to create one. */
 int vbmf_b200_ctx_create(int device, int rank, int world, const void* nccl_id128, void* cuda_stream, vbmf_b200_ctx** out);
 int vbmf_b200_ctx_destroy(vbmf_b200_ctx* ctx);
-/* Y: L x M_local column-major host matrix with leading dimension ldY (the argument `Y` of every reference function). */
+/* Y: L x M_local column-major host matrix with leading dimension ldY (the argument `Y` of every reference function).
+ * Large matrices (>= 2 chunks of VBMF_B200_ATTACH_CHUNK_MB, default 2048 MB) are uploaded ASYNCHRONOUSLY in column chunks: the
+ * call returns while the copy is in flight, the first dense iteration then works through the chunks as they arrive and every
+ * other consumer waits for the upload on the device.  The host buffer must stay valid and unmodified until a call that uses Y
+ * (a run, a step that contracts with Y, trYTY, download_Y) or vbmf_b200_ctx_sync has returned. */
 int vbmf_b200_attach_Y(vbmf_b200_ctx* ctx, const double* Y, int64_t L, int64_t M_local, int64_t ldY, int64_t M_global,
                        int64_t col_offset);
 /* Declare the problem geometry without data, for the step functions that take no Y in the reference (updateCA!(params),
@@ -206,6 +210,7 @@ int64_t vbmf_b200_launch_count(void);
 int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_sms, int64_t* out6);
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
+int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* ctx, double* allreduce_ms, int64_t* allreduce_launches);
 
 /* ---- K1 / K2 on their own (parity tests of the two contractions) ---- */
 /* P (M_local x H, column-major) = Y' * B ;  B is L x H column-major.  src/vbmf.jl:98 */

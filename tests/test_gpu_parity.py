@@ -855,3 +855,54 @@ def test_vbls_batched_wide_rank(G, ctx, kind, full_cov, diag_var, H):
     with pytest.raises(G.vb.VBMFError, match="H <= 64|too large"):
         Yb = np.asfortranarray(synth(L, 5, 2, seed=1))
         G.vb.vbls_batched_([Yb], [G.to_gpu_params(vo.vbmf_sparse_init(Yb, 65, rng=rng))], 2, ctx=ctx)
+
+
+# ------------------------------------------------------------------------------------------------ asynchronous chunked upload of Y
+def test_chunked_upload_overlapped_first_iteration(G, monkeypatch):
+    """attach_Y of a large matrix returns while the column chunks are still travelling; the first dense iteration follows the
+    chunks (K1 / A epilogue / K2 per chunk), everything else waits for the upload.  Forced at a small size through
+    VBMF_B200_ATTACH_CHUNK_MB; results must equal the oracle's (and the unchunked path's) for every kind."""
+    L, M, H = 300, 4100, 16
+    Y = synth(L, M, 8, seed=41)
+    Yf = np.asfortranarray(Y)
+    p = vo.vbmf_init(Y, H, H1=2, labels=list(range(5, M, 11)), rng=np.random.default_rng(3))
+    ref = copy.deepcopy(p)
+    vo.vbmf_run(Y, ref, 1, eps=0.0, est_covs=True, est_var=True)
+    ref5 = copy.deepcopy(p)
+    vo.vbmf_run(Y, ref5, 5, eps=0.0, est_covs=True, est_var=True)
+    plain = G.to_gpu_params(p)
+    c0 = G.vb.Context(device=0)
+    G.vb.vbmf_(Yf, plain, 5, eps=0.0, est_covs=True, est_var=True, ctx=c0)
+    c0.close()
+    monkeypatch.setenv("VBMF_B200_ATTACH_CHUNK_MB", "1")          # 384-column chunks -> 11 chunks
+    c = G.vb.Context(device=0)
+    try:
+        q1 = G.to_gpu_params(p)
+        G.vb.vbmf_(Yf, q1, 1, eps=0.0, est_covs=True, est_var=True, ctx=c)       # the chunk-following iteration alone
+        G.compare(q1, ref, TOL)
+        q5 = G.to_gpu_params(p)
+        G.vb.vbmf_(Yf, q5, 5, eps=0.0, est_covs=True, est_var=True, ctx=c)       # followed by ordinary iterations
+        floor = G.sensitivity(lambda s_: vo.vbmf_run(Y, s_, 5, eps=0.0, est_covs=True, est_var=True), p, G.FIELDS["dense"])
+        G.compare(q5, ref5, max(TOL, 100 * floor))
+        G.compare(q5, plain, max(TOL, 100 * floor))
+        assert G.rel(q5.YHat, q5.BHat @ q5.AHat.T) < 1e-13
+        # the other consumers of Y wait for the upload: trYTY, the contractions, a sparse run
+        c.attach(Yf)
+        assert abs(c.trYTY() - float(np.sum(Y * Y))) <= 1e-12 * float(np.sum(Y * Y))
+        c.attach(Yf)
+        B = np.random.default_rng(0).standard_normal((L, H))
+        assert G.rel(c.gemm_YtB(B), Y.T @ B) < 1e-13
+        ps = vo.vbmf_sparse_init(Y, H, rng=np.random.default_rng(4))
+        qs = G.to_gpu_params(ps)
+        vo.vbmf_sparse_run(Y, ps, 2, eps=0.0, full_cov=False)
+        G.vb.vbmf_sparse_(Yf, qs, 2, eps=0.0, full_cov=False, ctx=c)
+        G.compare(qs, ps, TOL)
+        # odd L (pitched copy) and a last chunk that is not a multiple of the tile
+        Y2 = synth(301, 1000, 4, seed=42)
+        p2 = vo.vbmf_init(Y2, 8, rng=np.random.default_rng(5))
+        q2 = G.to_gpu_params(p2)
+        vo.vbmf_run(Y2, p2, 2, eps=0.0, est_covs=True, est_var=True)
+        G.vb.vbmf_(np.asfortranarray(Y2), q2, 2, eps=0.0, est_covs=True, est_var=True, ctx=c)
+        G.compare(q2, p2, TOL)
+    finally:
+        c.close()

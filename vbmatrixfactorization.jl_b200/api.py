@@ -96,6 +96,7 @@ class Context:
         Lr, M = Y.shape
         Mg = M if M_global is None else M_global
         L_.check(self.lib.vbmf_b200_attach_Y(self.h, _ptr(Y), Lr, M, max(Lr, 1), Mg, col_offset))
+        self._Y_host = Y              # large uploads are asynchronous: the host buffer stays alive until the next attach
         self._key = ("host", Lr, M, Mg, col_offset)
         self.L, self.M, self.M_global, self.col_offset = Lr, M, Mg, col_offset
 
@@ -153,7 +154,10 @@ class Context:
         a, b = C.c_double(), C.c_double()
         na, nb = C.c_int64(), C.c_int64()
         L_.check(self.lib.vbmf_b200_ctx_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
-        return {"k1_ms": a.value, "k1_launches": na.value, "k2_ms": b.value, "k2_launches": nb.value}
+        ar, nar = C.c_double(), C.c_int64()
+        L_.check(self.lib.vbmf_b200_ctx_profile_read_allreduce(self.h, C.byref(ar), C.byref(nar)))
+        return {"k1_ms": a.value, "k1_launches": na.value, "k2_ms": b.value, "k2_launches": nb.value,
+                "allreduce_ms": ar.value, "allreduce_launches": nar.value}
 
 
 class MultiContext:
@@ -192,6 +196,7 @@ class MultiContext:
             raise ValueError("Y must be a matrix")
         Lr, M = Y.shape
         L_.check(self.lib.vbmf_b200_mctx_attach_Y(self.h, _ptr(Y), Lr, M, max(Lr, 1)))
+        self._Y_host = Y              # large uploads are asynchronous: the host buffer stays alive until the next attach
         self.L, self.M = Lr, M
 
     def synth(self, Lr, M, rank=8, noise=0.1, seed=20260101):

@@ -92,10 +92,19 @@ struct vbmf_b200_ctx {
     double trYTY = 0.0;
     CUtensorMap tmY1, tmY2;
     bool have_Y = false;
+    // Large uploads travel in column chunks on a copy stream; K0 (row norms, trYTY) follows chunk by chunk on a statistics
+    // stream.  Until somebody needs all of Y the main stream is free: the first dense iteration works through the chunks as
+    // they arrive (enq_iteration_chunked), everything else waits for ev_stats once (ctx_wait_upload).
+    cudaStream_t copy_st = nullptr, stat_st = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    std::vector<int> chunk_c0, chunk_n;
+    cudaEvent_t ev_stats = nullptr;
+    int chunks_pending = 0;           // > 0: chunks whose arrival the main stream has not been ordered after yet
+    bool tr_pending = false;          // trYTY lives in d_tr only (not yet read back to the host)
     bool simt = false;
     // profiling of the two contractions
     bool profile = false;
-    std::vector<cudaEvent_t> ev_k1, ev_k2;
+    std::vector<cudaEvent_t> ev_k1, ev_k2, ev_ar;      // K1, K2 and (world > 1) the per-iteration all-reduce
     // grow-only staging for the batched small-problem path (device arena + pinned host mirror, same offsets)
     char* batch_dev = nullptr;
     char* batch_host = nullptr;
@@ -199,6 +208,9 @@ int nccl_comm_init_all(void** comms, int ndev, const int* devs) {
 }
 
 static void ctx_free_Y(vbmf_b200_ctx* c) {
+    if (c->copy_st) cudaStreamSynchronize(c->copy_st);
+    if (c->stat_st) cudaStreamSynchronize(c->stat_st);
+    c->chunks_pending = 0; c->tr_pending = false;
     if (c->Y) cudaFree(c->Y);
     if (c->rowY2) cudaFree(c->rowY2);
     if (c->stats_part) cudaFree(c->stats_part);
@@ -216,6 +228,11 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
     if (c->batch_host) cudaFreeHost(c->batch_host);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
+    for (auto e : c->ev_ar) cudaEventDestroy(e);
+    for (auto e : c->ev_chunk) cudaEventDestroy(e);
+    if (c->ev_stats) cudaEventDestroy(c->ev_stats);
+    if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
+    if (c->stat_st) { cudaStreamSynchronize(c->stat_st); cudaStreamDestroy(c->stat_st); }
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->own_stream) cudaStreamDestroy(c->st);
     delete c;
@@ -224,6 +241,8 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
 
 extern "C" int vbmf_b200_ctx_sync(vbmf_b200_ctx* c) {
     VB_CUDA_OK(cudaSetDevice(c->device));
+    if (c->copy_st) VB_CUDA_OK(cudaStreamSynchronize(c->copy_st));      // an asynchronous upload of Y, if any
+    if (c->stat_st) VB_CUDA_OK(cudaStreamSynchronize(c->stat_st));
     VB_CUDA_OK(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -233,6 +252,9 @@ static int ctx_alloc_Y(vbmf_b200_ctx* c, int64_t L, int64_t Mloc, int64_t Mglob,
     if (L > 0x7fffff00LL || Mglob > 0x7fffff00LL) { set_error("L and M must fit in 31 bits"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
     VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (c->copy_st) VB_CUDA_OK(cudaStreamSynchronize(c->copy_st));
+    if (c->stat_st) VB_CUDA_OK(cudaStreamSynchronize(c->stat_st));
+    c->chunks_pending = 0; c->tr_pending = false;
     const int ld = (int)((L + 1) & ~1LL);                 // TMA needs a 16-byte pitch
     const size_t bytes = std::max<size_t>((size_t)ld * (size_t)std::max<int64_t>(Mloc, 1) * 8, 16);
     // Re-attaching a matrix of the same (or a somewhat smaller) size keeps the allocation: cudaFree + cudaMalloc of tens of
@@ -275,11 +297,77 @@ static int ctx_finish_Y(vbmf_b200_ctx* c) {
     return 0;
 }
 
+// main stream ordered after the whole upload and K0; trYTY on the host when asked for
+static int ctx_wait_upload(vbmf_b200_ctx* c) {
+    if (c->chunks_pending > 0) {
+        VB_CUDA_OK(cudaStreamWaitEvent(c->st, c->ev_stats, 0));
+        c->chunks_pending = 0;
+    }
+    return 0;
+}
+static int ctx_host_trYTY(vbmf_b200_ctx* c) {
+    if (c->tr_pending) {
+        VB_CUDA_OK(cudaEventSynchronize(c->ev_stats));
+        VB_CUDA_OK(cudaMemcpy(&c->trYTY, c->d_tr, 8, cudaMemcpyDeviceToHost));
+        c->tr_pending = false;
+    }
+    return 0;
+}
+// Upload in column chunks on the copy stream, K0 chunk by chunk on the statistics stream; returns without waiting.
+static int attach_Y_chunked(vbmf_b200_ctx* c, const double* Y, int64_t ldY, int64_t chunk_cols) {
+    if (!c->copy_st) VB_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+    if (!c->stat_st) VB_CUDA_OK(cudaStreamCreateWithFlags(&c->stat_st, cudaStreamNonBlocking));
+    if (!c->ev_stats) VB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+    c->chunk_c0.clear(); c->chunk_n.clear();
+    for (int64_t c0 = 0; c0 < c->Mloc; c0 += chunk_cols) { c->chunk_c0.push_back((int)c0); c->chunk_n.push_back((int)std::min<int64_t>(chunk_cols, c->Mloc - c0)); }
+    const size_t nch = c->chunk_c0.size();
+    while (c->ev_chunk.size() < nch) { cudaEvent_t e; VB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_chunk.push_back(e); }
+    // the copy stream starts after whatever the main stream still does with the buffer (memset of the padding row)
+    cudaEvent_t e0;
+    VB_CUDA_OK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    VB_CUDA_OK(cudaEventRecord(e0, c->st));
+    VB_CUDA_OK(cudaStreamWaitEvent(c->copy_st, e0, 0));
+    VB_CUDA_OK(cudaStreamWaitEvent(c->stat_st, e0, 0));
+    VB_CUDA_OK(cudaEventDestroy(e0));
+    Dev d;
+    memset(&d, 0, sizeof(d));
+    d.L = c->L; d.Mloc = c->Mloc; d.Y = c->Y; d.ldY = c->ldY; d.rowY2 = c->rowY2; d.part = c->stats_part;
+    for (size_t k = 0; k < nch; ++k) {
+        const size_t c0 = (size_t)c->chunk_c0[k], n = (size_t)c->chunk_n[k];
+        if (ldY == c->L && c->ldY == c->L)
+            VB_CUDA_OK(cudaMemcpyAsync(c->Y + c0 * c->ldY, Y + c0 * (size_t)ldY, (size_t)c->L * n * 8, cudaMemcpyHostToDevice, c->copy_st));
+        else
+            VB_CUDA_OK(cudaMemcpy2DAsync(c->Y + c0 * c->ldY, (size_t)c->ldY * 8, Y + c0 * (size_t)ldY, (size_t)ldY * 8, (size_t)c->L * 8, n,
+                                         cudaMemcpyHostToDevice, c->copy_st));
+        VB_CUDA_OK(cudaEventRecord(c->ev_chunk[k], c->copy_st));
+        VB_CUDA_OK(cudaStreamWaitEvent(c->stat_st, c->ev_chunk[k], 0));
+        if (k_y_stats_chunk(c->stat_st, d, (int)c0, (int)n, k == 0 ? 1 : 0)) return -1;
+    }
+    if (c->world > 1) VB_NCCL_OK(g_nccl.AllReduce(c->rowY2, c->rowY2, (size_t)c->L, 8, 0, c->comm, c->stat_st));
+    if (k_total(c->stat_st, c->rowY2, c->L, c->d_tr)) return -1;
+    VB_CUDA_OK(cudaEventRecord(c->ev_stats, c->stat_st));
+    if (make_tmap_2d(&c->tmY1, c->Y, (uint64_t)c->L, (uint64_t)c->Mloc, (uint64_t)c->ldY * 8, 16, 128)) return -1;
+    if (make_tmap_2d(&c->tmY2, c->Y, (uint64_t)c->L, (uint64_t)c->Mloc, (uint64_t)c->ldY * 8, 16, 16)) return -1;
+    c->chunks_pending = (int)nch;
+    c->tr_pending = true;
+    c->trYTY = nan("");
+    c->have_Y = true;
+    return 0;
+}
+
 extern "C" int vbmf_b200_attach_Y(vbmf_b200_ctx* c, const double* Y, int64_t L, int64_t M_local, int64_t ldY,
                                   int64_t M_global, int64_t col_offset) {
     if (!c || (!Y && M_local > 0)) { set_error("attach_Y: NULL argument"); return -1; }
     if (ldY < L) { set_error("attach_Y: ldY < L"); return -1; }
     if (ctx_alloc_Y(c, L, M_local, M_global, col_offset)) return -1;
+    {   // big matrices: chunked asynchronous upload (chunk = VBMF_B200_ATTACH_CHUNK_MB, default 2048 MB; at least two chunks)
+        const char* e = getenv("VBMF_B200_ATTACH_CHUNK_MB");
+        const double chunk_mb = e ? atof(e) : 2048.0;
+        const double col_bytes = (double)c->ldY * 8.0;
+        int64_t chunk_cols = (int64_t)(chunk_mb * 1048576.0 / col_bytes) / 128 * 128;
+        if (chunk_cols < 128) chunk_cols = 128;
+        if (chunk_mb > 0 && M_local >= 2 * chunk_cols && !c->simt) return attach_Y_chunked(c, Y, ldY, chunk_cols);
+    }
     if (M_local > 0) {
         if (ldY == L && c->ldY == L) {       // contiguous on both sides: one plain copy (full PCIe rate from pinned memory)
             VB_CUDA_OK(cudaMemcpyAsync(c->Y, Y, (size_t)L * (size_t)M_local * 8, cudaMemcpyHostToDevice, c->st));
@@ -317,6 +405,7 @@ extern "C" int vbmf_b200_synth_Y(vbmf_b200_ctx* c, int64_t L, int64_t M_local, i
 extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* L_out, int64_t* used_rows) {
     if (!c || !c->have_Y || !c->Y) { set_error("preprocess_Y: no Y attached"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
+    if (ctx_wait_upload(c) || ctx_host_trYTY(c)) return -1;
     const int L = c->L, M = c->Mloc;
     cudaStream_t st = c->st;
     double *mu = nullptr, *den = nullptr, *rs = nullptr;
@@ -368,6 +457,7 @@ extern "C" int vbmf_b200_preprocess_Y(vbmf_b200_ctx* c, double lambda, int64_t* 
 extern "C" int vbmf_b200_download_Y(vbmf_b200_ctx* c, double* out, int64_t ldY) {
     if (!c || !c->have_Y || !c->Y) { set_error("download_Y: no Y attached"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
+    if (ctx_wait_upload(c)) return -1;
     if (c->Mloc > 0)
         VB_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ldY * 8, c->Y, (size_t)c->ldY * 8, (size_t)c->L * 8, (size_t)c->Mloc,
                                      cudaMemcpyDeviceToHost, c->st));
@@ -377,6 +467,7 @@ extern "C" int vbmf_b200_download_Y(vbmf_b200_ctx* c, double* out, int64_t ldY) 
 
 extern "C" int vbmf_b200_trYTY(vbmf_b200_ctx* c, double* out) {
     if (!c || !c->have_Y) { set_error("trYTY: no Y attached"); return -1; }
+    if (ctx_host_trYTY(c)) return -1;
     *out = c->trYTY;
     return 0;
 }
@@ -385,7 +476,16 @@ extern "C" int vbmf_b200_ctx_profile(vbmf_b200_ctx* c, int enable) {
     c->profile = enable != 0;
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
-    c->ev_k1.clear(); c->ev_k2.clear();
+    for (auto e : c->ev_ar) cudaEventDestroy(e);
+    c->ev_k1.clear(); c->ev_k2.clear(); c->ev_ar.clear();
+    return 0;
+}
+// CUDA-event time of the per-iteration all-reduce launches (world > 1; zero launches otherwise)
+extern "C" int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* c, double* ar_ms, int64_t* ar_n) {
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    double t = 0;
+    for (size_t i = 0; i + 1 < c->ev_ar.size(); i += 2) { float ms = 0; VB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev_ar[i], c->ev_ar[i + 1])); t += ms; }
+    *ar_ms = t; *ar_n = (int64_t)(c->ev_ar.size() / 2);
     return 0;
 }
 extern "C" int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* c, double* k1_ms, int64_t* k1_n, double* k2_ms, int64_t* k2_n) {
@@ -421,6 +521,10 @@ struct vbmf_b200_solver {
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
     bool ca_done = false;     // the fused diagonal A pass already did updateCA! of this iteration
+    bool need_tr_copy = false;    // dense: sum(Y.^2) was still being computed at upload time; copy it device-side before its first use
+    double* Qc = nullptr;         // [chunks][H*ldB] per-chunk Y*AHat of the upload-overlapped first iteration (allocated on demand)
+    size_t Qc_chunks = 0;
+    int S_chunk = 1;              // K2 slabs of the largest upload chunk (Qpart is sized for max(S, S_chunk))
     int* h_flag = nullptr;   // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // The single-CTA tail of an iteration (norms, hyper-parameter updates, convergence test) runs on a side stream so that
@@ -465,6 +569,13 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
     plan_splitk(d.L, d.Mloc, d.H, c->num_sms, &s->S, &s->kchunk);
     plan_splitk_ytb(d.L, d.Mloc, d.H, c->num_sms, &s->S1, &s->kbs1);
     if (c->simt) s->S1 = 1;
+    if (c->chunks_pending > 0 && kind == VBMF_B200_DENSE) {      // the first iteration may run chunk by chunk behind the upload
+        for (size_t k = 0; k < c->chunk_n.size(); ++k) {
+            int Sc = 1, kc = 16;
+            plan_splitk(d.L, c->chunk_n[k], d.H, c->num_sms, &Sc, &kc);
+            s->S_chunk = std::max(s->S_chunk, Sc);
+        }
+    }
     s->k2_simt = c->simt || (H % 2 != 0);       // the A tensor map needs a 16-byte row pitch
     {   // stream-K for K2: opt-in (VBMF_B200_K2=streamk).  It removes the 16 slabs of L x H (reduction 28 -> 18 us at
         // 20000 x 25000 x 64) but the kernel itself measured 4-5 % slower than the classic split (15.0 vs 14.4 ms at config 3,
@@ -484,7 +595,7 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
         {&d.A, MH}, {&d.P, MH}, {&d.B, LH}, {&d.Bold, LH}, {&d.D, LH}, {&d.Bs, LH}, {&d.packed, LH + 2 * HH + 8},
         {&d.SigmaA, HH}, {&d.SigmaB, HH}, {&d.BtB, HH}, {&d.BtBw, HH}, {&d.DtD, HH}, {&d.Gm, HH},
         {&d.sigmaVec, Lr}, {&d.etaVec, Lr}, {&d.zetaVec, Lr}, {&d.part, part_elems}, {&d.lbacc, 32},
-        {&s->Qpart, (size_t)std::max(s->S, s->k2_sk ? s->sk_smax : 1) * LH},
+        {&s->Qpart, (size_t)std::max(std::max(s->S, s->S_chunk), s->k2_sk ? s->sk_smax : 1) * LH},
     };
     if (s->S1 > 1) items.push_back({&s->Ppart, (size_t)s->S1 * MH});
     if (kind == VBMF_B200_DENSE) { items.push_back({&d.CA, HH}); items.push_back({&d.CB, HH}); items.push_back({&d.invCA, HH}); items.push_back({&d.invCB, HH}); }
@@ -560,6 +671,7 @@ extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
     if (s->ev_b) cudaEventDestroy(s->ev_b);
     if (s->ev_p) cudaEventDestroy(s->ev_p);
     if (s->arena) cudaFree(s->arena);
+    if (s->Qc) cudaFree(s->Qc);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     for (int i = 0; i < 2; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     delete s;
@@ -645,8 +757,10 @@ extern "C" int vbmf_b200_dense_upload(vbmf_b200_solver* s, const vbmf_b200_dense
         up(s, d.CA, st->CA, HH) || up(s, d.CB, st->CB, HH) || up(s, d.invCA, st->invCA, HH) || up(s, d.invCB, st->invCB, HH)) return -1;
     memset(&s->h_sc, 0, sizeof(Scalars));
     s->h_sc.sigma2 = st->sigma2;
-    s->h_sc.trYTY = s->c->trYTY;       // norm2(Y), src/vbmf.jl:154
-    return push_scalars(s);
+    s->h_sc.trYTY = s->c->trYTY;       // norm2(Y), src/vbmf.jl:154 (NaN while K0 still runs behind an asynchronous upload)
+    if (push_scalars(s)) return -1;
+    s->need_tr_copy = s->c->tr_pending;
+    return 0;
 }
 extern "C" int vbmf_b200_dense_download(vbmf_b200_solver* s, vbmf_b200_dense_state* st) {
     if (!s || !st) { set_error("NULL argument"); return -1; }
@@ -802,10 +916,20 @@ extern "C" int vbmf_b200_trial_download(vbmf_b200_solver* s, vbmf_b200_trial_sta
 }
 
 // ---- enqueue helpers ---------------------------------------------------------------------------------------------------
+// main stream after the (possibly still running) upload of Y and K0; the dense state's sum(Y.^2) follows device-side
+static int settle_upload(vbmf_b200_solver* s) {
+    if (ctx_wait_upload(s->c)) return -1;
+    if (s->need_tr_copy) {
+        if (k_copy_trYTY(s->c->st, s->d, s->c->d_tr)) return -1;
+        s->need_tr_copy = false;
+    }
+    return 0;
+}
 static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
     vbmf_b200_ctx* c = s->c;
     const Dev& d = s->d;
     if (c->Y == nullptr) { set_error("this step contracts with Y: attach Y first (the context only holds its shape)"); return -1; }
+    if (settle_upload(s)) return -1;
     prof_mark(c, c->ev_k1);
     int rc;
     if (c->simt) rc = launch_gemm_ytb_simt(c->st, d.Y, d.ldY, scaledB ? d.Bs : d.B, d.ldB, d.P, d.Mloc, d.L, d.H, d.H, d.sc);
@@ -822,6 +946,7 @@ static int enq_k2(vbmf_b200_solver* s) {
     vbmf_b200_ctx* c = s->c;
     const Dev& d = s->d;
     if (c->Y == nullptr) { set_error("this step contracts with Y: attach Y first (the context only holds its shape)"); return -1; }
+    if (settle_upload(s)) return -1;
     prof_mark(c, c->ev_k2);
     int rc;
     if (s->k2_simt) rc = launch_gemm_ya_simt(c->st, d.Y, d.ldY, d.A, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc);
@@ -920,7 +1045,9 @@ static int enq_q_ata(vbmf_b200_solver* s, bool fused) {
     s->ata_local = false;
     if (enq_k2(s)) return -1;
     const size_t n = fused ? packed_len(d) : packed_sa(d);
+    if (s->c->world > 1) prof_mark(s->c, s->c->ev_ar);
     if (ctx_allreduce(s->c, d.packed, n)) return -1;
+    if (s->c->world > 1) prof_mark(s->c, s->c->ev_ar);
     s->ata_valid = true; s->q_valid = true;
     if (fused) s->extras_valid = true;
     return 0;
@@ -1027,6 +1154,64 @@ static int enq_iteration(vbmf_b200_solver* s, int flags) {
     return 0;
 }
 
+// First dense iteration while Y is still arriving (asynchronous chunked attach): row m of AHat needs only column m of Y, and
+// Y*AHat is a sum over columns, so updateA! and the Y*AHat part of updateB! run chunk by chunk behind the copy stream
+// (K1, A epilogue, K2 and the slab reduction per chunk); the chunk results are summed in fixed order and the rest of the
+// iteration (all-reduce, SigmaB, BHat epilogue, tail) is the usual one.  Every later iteration needs all of Y.
+static int enq_iteration_chunked(vbmf_b200_solver* s, int flags) {
+    vbmf_b200_ctx* c = s->c;
+    const Dev& d = s->d;
+    cudaStream_t st = c->st;
+    const size_t nch = c->chunk_c0.size(), LH = (size_t)d.H * d.ldB, MH = (size_t)d.Mloc * d.H;
+    if (s->Qc == nullptr || s->Qc_chunks < nch) {
+        if (s->Qc) { VB_CUDA_OK(cudaStreamSynchronize(st)); cudaFree(s->Qc); s->Qc = nullptr; }
+        if (cudaMalloc(&s->Qc, nch * LH * 8) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of the per-chunk Y*AHat buffer failed"); return -1; }
+        s->Qc_chunks = nch;
+    }
+    if (!s->btb_valid) { if (wait_post(s) || enq_gram_B(s, flags)) return -1; }
+    if (wait_post(s) || k_dense_sigmaA(st, d)) return -1;
+    const bool slabs = s->S1 > 1;
+    const int max_parts = std::max(1, (int)(MAX_PARTS / nch));
+    int parts = 0;
+    for (size_t k = 0; k < nch; ++k) {
+        const int c0 = c->chunk_c0[k], n = c->chunk_n[k];
+        VB_CUDA_OK(cudaStreamWaitEvent(st, c->ev_chunk[k], 0));
+        CUtensorMap tmY1c, tmY2c, tmAc;
+        const double* Yc = c->Y + (size_t)c0 * c->ldY;
+        if (make_tmap_2d(&tmY1c, Yc, (uint64_t)c->L, (uint64_t)n, (uint64_t)c->ldY * 8, 16, 128)) return -1;
+        if (make_tmap_2d(&tmY2c, Yc, (uint64_t)c->L, (uint64_t)n, (uint64_t)c->ldY * 8, 16, 16)) return -1;
+        if (make_tmap_2d(&tmAc, d.A + (size_t)c0 * d.H, (uint64_t)d.H, (uint64_t)n, (uint64_t)d.H * 8, 16, 16)) return -1;
+        // updateA! on the chunk: P = Y_c' * BHat (slabs at the chunk's rows), then the A epilogue on those rows
+        if (launch_gemm_ytb(st, &tmY1c, &s->tmB, (slabs ? s->Ppart : d.P) + (size_t)c0 * d.H, n, d.L, d.H, d.H, s->S1, s->kbs1, MH, d.sc, c->num_sms)) return -1;
+        int np = 0;
+        if (k_dense_A_fused_range(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, MH, c0, c0 + n, parts, max_parts, &np)) return -1;
+        parts += np;
+        // Y_c * AHat_c -> Qc[k]
+        int Sc = 1, kc = 16;
+        plan_splitk(d.L, n, d.H, c->num_sms, &Sc, &kc);
+        if (launch_gemm_ya(st, &tmY2c, &tmAc, s->Qpart, d.L, n, d.H, d.ldB, kc, Sc, d.sc, c->num_sms)) return -1;
+        if (k_sum_slabs(st, s->Qpart, Sc, LH, s->Qc + k * LH, d.sc)) return -1;
+    }
+    c->chunks_pending = 0;                                   // the main stream is now ordered after every chunk
+    if (k_sum_gram_partials(st, d, parts)) return -1;        // packed.AtA (local)
+    if (k_sum_slabs(st, s->Qc, (int)nch, LH, d.packed + packed_q(d), d.sc)) return -1;
+    s->ata_local = true;
+    // sum(Y.^2) for updateSigma2!: K0 finishes on the statistics stream
+    VB_CUDA_OK(cudaStreamWaitEvent(st, c->ev_stats, 0));
+    if (s->need_tr_copy) { if (k_copy_trYTY(st, d, c->d_tr)) return -1; s->need_tr_copy = false; }
+    // updateB! from the summed payload on
+    if (ctx_allreduce(c, d.packed, packed_len(d))) return -1;
+    s->ata_local = false; s->ata_valid = true; s->q_valid = true; s->extras_valid = true;
+    if (k_sigmaB(st, d, flags) || k_B_epilogue(st, d, flags)) return -1;
+    s->btb_valid = true;
+    VB_CUDA_OK(cudaEventRecord(s->ev_b, st));
+    VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_b, 0));
+    if (k_post(s->side, d, flags, true)) return -1;
+    VB_CUDA_OK(cudaEventRecord(s->ev_p, s->side));
+    s->post_pending = true;
+    return 0;
+}
+
 extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double eps, int flags, int norm_mode,
                                     int64_t* iters, double* dout) {
     if (!s) { set_error("NULL solver"); return -1; }
@@ -1075,6 +1260,12 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
             pending = true;
             slot ^= 1;
         }
+    }
+    // Y still arriving (asynchronous chunked attach) and the kind is dense: the first iteration follows the chunks
+    if (!graph_mode && enq < niter && d.kind == KIND_DENSE && s->c->chunks_pending > 0 && !s->c->simt && !s->k2_simt && !s->c->profile &&
+        s->c->Y != nullptr && getenv("VBMF_B200_NO_UPLOAD_OVERLAP") == nullptr) {
+        if (enq_iteration_chunked(s, flags)) return -1;
+        enq = 1;
     }
     const int CHUNK = 4;
     while (!graph_mode && enq < niter) {
@@ -1158,6 +1349,7 @@ extern "C" int vbmf_b200_gemm_YtB(vbmf_b200_ctx* c, const double* B, int64_t H, 
     if (!c || !c->have_Y || !c->Y || !B || !P) { set_error("gemm_YtB: bad argument"); return -1; }
     if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
+    if (ctx_wait_upload(c)) return -1;
     const int ldB = (c->L + 1) & ~1;
     const size_t MH = (size_t)std::max(c->Mloc, 1) * H;
     double *dB = nullptr, *dP = nullptr, *dT = nullptr;
@@ -1191,6 +1383,7 @@ extern "C" int vbmf_b200_gemm_YA(vbmf_b200_ctx* c, const double* A, int64_t H, d
     if (!c || !c->have_Y || !c->Y || !A || !Q) { set_error("gemm_YA: bad argument"); return -1; }
     if (H < 1 || H > 128) { set_error("H out of range"); return -1; }
     VB_CUDA_OK(cudaSetDevice(c->device));
+    if (ctx_wait_upload(c)) return -1;
     const int ldQ = (c->L + 1) & ~1;
     const size_t MH = (size_t)std::max(c->Mloc, 1) * H;
     int S = 1, kchunk = 16;

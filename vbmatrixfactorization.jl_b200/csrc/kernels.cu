@@ -120,6 +120,31 @@ int k_total(cudaStream_t st, const double* x, int n, double* out) {
     VB_LAUNCH_OK();
     return 0;
 }
+// rowY2 (+)= per-row sum of squares of the columns [m0, m0 + n) (one upload chunk); chunks are accumulated in stream order
+__global__ void accum_rows_kernel(const double* __restrict__ part, int nparts, int L, double* __restrict__ rowY2, int first) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double s = first ? 0.0 : rowY2[l];
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * L + l];
+    rowY2[l] = s;
+}
+int k_y_stats_chunk(cudaStream_t st, const Dev& d, int m0, int n, int first) {
+    if (n <= 0 && !first) return 0;
+    const int nby = std::max(1, std::min(MAX_PARTS / 2, cdiv(std::max(n, 1), 64)));
+    const int cpb = cdiv(std::max(n, 1), nby);
+    dim3 grid(cdiv(d.L, 128), nby);
+    y_stats_kernel<<<grid, 128, 0, st>>>(d.Y + (size_t)m0 * d.ldY, d.ldY, d.L, n, cpb, d.part);
+    VB_LAUNCH_OK();
+    accum_rows_kernel<<<cdiv(d.L, 256), 256, 0, st>>>(d.part, nby, d.L, d.rowY2, first);
+    VB_LAUNCH_OK();
+    return 0;
+}
+__global__ void copy_tr_kernel(Scalars* sc, const double* d_tr) { sc->trYTY = d_tr[0]; }
+int k_copy_trYTY(cudaStream_t st, const Dev& d, const double* d_tr) {
+    copy_tr_kernel<<<1, 1, 0, st>>>(d.sc, d_tr);
+    VB_LAUNCH_OK();
+    return 0;
+}
 int k_y_stats(cudaStream_t st, const Dev& d, double* out_tr) {
     const int nby = std::max(1, std::min(MAX_PARTS / 2, cdiv(d.Mloc, 64)));
     const int cpb = cdiv(std::max(d.Mloc, 1), nby);
@@ -629,7 +654,8 @@ __device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
 __host__ __device__ inline int pitch4(int hp8) { return ((hp8 + 11) / 16) * 16 + 4; }
 
 template <int TPW>   // Gram tiles per warp: ceil((HP8/8)^2 / 8)
-__global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(Dev d, const double* __restrict__ slabs, int S, size_t slab_stride) {
+__global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(Dev d, const double* __restrict__ slabs, int S, size_t slab_stride,
+                                                                                int m_begin, int m_end, int part_base) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
     const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
@@ -655,9 +681,9 @@ __global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(
         ga[q] = at < nt8 ? at : -1;
         gb[q] = at + idx;
     }
-    const int ntiles = (d.Mloc + 31) / 32;
+    const int ntiles = (m_end - m_begin + 31) / 32;             // rows [m_begin, m_end) of AHat (the whole shard, or one upload chunk)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
+        const int m0 = m_begin + tile * 32, nr = min(32, m_end - m0);
         __syncthreads();
 #pragma unroll 4
         for (int e = threadIdx.x; e < 32 * HP8; e += 256) {      // independent loads of several elements in flight
@@ -721,7 +747,7 @@ __global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(
             }
         }
     }
-    double* out = d.part + (size_t)blockIdx.x * H * H;
+    double* out = d.part + (size_t)(part_base + blockIdx.x) * H * H;
 #pragma unroll
     for (int q = 0; q < GT; ++q) {
         if (ga[q] >= 0) {
@@ -731,18 +757,37 @@ __global__ void __launch_bounds__(256, (TPW <= 8 ? 3 : 1)) dense_A_fused_kernel(
         }
     }
 }
-// slabs: S split-K slabs of K1 (slab_stride apart) or the single P buffer (S = 1); writes AHat and packed.AtA (local part)
-int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride) {
-    if (d.Mloc <= 0) return 0;
+// slabs: S split-K slabs of K1 (slab_stride apart) or the single P buffer (S = 1); writes AHat rows [m_begin, m_end) and one
+// Gram partial per CTA at d.part[(part_base + cta)*H*H]
+static int dense_A_fused_launch(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int m_begin, int m_end,
+                                int part_base, int max_grid, int* grid_out) {
     const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8);
     const size_t smem = (size_t)((HP8 + 64) * ld) * sizeof(double);
     const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));     // latency hiding across CTAs
-    const int grid = std::max(1, std::min(cdiv(d.Mloc, 32), 148 * per_sm));
-    if (HP8 <= 32) dense_A_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
-    else if (HP8 <= 64) dense_A_fused_kernel<8><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
-    else dense_A_fused_kernel<32><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride);
+    const int grid = std::max(1, std::min(std::min(cdiv(m_end - m_begin, 32), 148 * per_sm), max_grid));
+    if (HP8 <= 32) dense_A_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, m_begin, m_end, part_base);
+    else if (HP8 <= 64) dense_A_fused_kernel<8><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, m_begin, m_end, part_base);
+    else dense_A_fused_kernel<32><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, m_begin, m_end, part_base);
     VB_LAUNCH_OK();
-    return sum_partials(st, d.part, grid, (size_t)H * H, (size_t)H * H, d.packed + packed_ata(d), d.sc);
+    *grid_out = grid;
+    return 0;
+}
+int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride) {
+    if (d.Mloc <= 0) return 0;
+    int grid = 0;
+    if (dense_A_fused_launch(st, d, slabs, S, slab_stride, 0, d.Mloc, 0, 1 << 30, &grid)) return -1;
+    return sum_partials(st, d.part, grid, (size_t)d.H * d.H, (size_t)d.H * d.H, d.packed + packed_ata(d), d.sc);
+}
+// one column chunk of the shard (first iteration overlapped with the upload of Y): partials land at part_base .. part_base + *nparts
+int k_dense_A_fused_range(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int m_begin, int m_end,
+                          int part_base, int max_parts, int* nparts) {
+    *nparts = 0;
+    if (m_end <= m_begin) return 0;
+    return dense_A_fused_launch(st, d, slabs, S, slab_stride, m_begin, m_end, part_base, max_parts, nparts);
+}
+// packed.AtA = fixed-order sum of nparts Gram partials in d.part
+int k_sum_gram_partials(cudaStream_t st, const Dev& d, int nparts) {
+    return sum_partials(st, d.part, nparts, (size_t)d.H * d.H, (size_t)d.H * d.H, d.packed + packed_ata(d), d.sc);
 }
 
 // AHat[labels, end-H1+1:end] = 0.0     src/vbmf.jl:101, src/vbmf_sparse.jl:245
@@ -839,13 +884,16 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 2 : 1)) sparse_A_diag_fused_ke
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
     __shared__ double red[32];
-    __shared__ long long s_q0[32];
-    __shared__ int s_r0[32];
+    // TR rows per tile.  (128- / 64-row tiles for H <= 32 / 64 -- 16 elements per thread in flight -- measured SLOWER, 106 vs
+    // 73 us at 100000 x 32: fewer, longer tiles balance worse over the CTAs; profiles/r02_hbm_kernels_c4_tall_tiles.csv)
+    constexpr int TR = 32;
+    constexpr int KMAX = GT == 2 ? 4 : (GT == 5 ? 8 : 16);     // elements of a TR x HP8 tile per thread (HP8 <= 32 / 64 / 128)
+    __shared__ long long s_q0[TR];
+    __shared__ int s_r0[TR];
     const int H = d.H, HP8 = (H + 7) & ~7, ld = pitch4(HP8), nt8 = HP8 / 8;
-    constexpr int KMAX = GT == 2 ? 4 : (GT == 5 ? 8 : 16);     // elements of a 32 x HP8 tile per thread (HP8 <= 32 / 64 / 128)
-    double* An = sm;                         // [32][ld]  new AHat tile (zero padded)
-    double* dv = An + 32 * ld;               // [HP8]     likelihood part of the diagonal precision
-    double* stage = dv + HP8;                // [32*HP8]  end-of-kernel staging of the per-thread column sums
+    double* An = sm;                         // [TR][ld]  new AHat tile (zero padded)
+    double* dv = An + TR * ld;               // [HP8]     likelihood part of the diagonal precision
+    double* stage = dv + HP8;                // [TR*HP8]  end-of-kernel staging of the per-thread column sums
     Scalars* sc = d.sc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
     for (int h = threadIdx.x; h < HP8; h += 256) {
@@ -873,13 +921,13 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 2 : 1)) sparse_A_diag_fused_ke
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) csum[k] = 0.0;
     double sca[3] = {0.0, 0.0, 0.0}, slb[3] = {0.0, 0.0, 0.0};
-    const int nel = 32 * HP8;
-    const int ntiles = (d.Mloc + 31) / 32;
+    const int nel = TR * HP8;
+    const int ntiles = (d.Mloc + TR - 1) / TR;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = tile * 32, nr = min(32, d.Mloc - m0);
+        const int m0 = tile * TR, nr = min(TR, d.Mloc - m0);
         __syncthreads();
         // Q2: element j of vec(A') (0-based, global) reads d[j] for j < H, else d[(j - H) / (M - 1)]: one division per row
-        if (threadIdx.x < 32) {
+        if (threadIdx.x < TR) {
             const long long mg = (long long)d.moff + m0 + threadIdx.x;
             long long q0 = 0; int r0 = 0;
             if (mg > 0 && Mg1 > 0) { const long long base = (mg - 1) * H; q0 = base / Mg1; r0 = (int)(base - q0 * Mg1); }
@@ -950,8 +998,8 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 2 : 1)) sparse_A_diag_fused_ke
             if (gt[q] >= 0) {
                 const double* pa = An + j * ld + 8 * (gt[q] & 255) + r;
                 const double* pb = An + j * ld + 8 * (gt[q] >> 8) + r;
-#pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += 4) dmma_acc2(g[q], pa[i0 * ld], pb[i0 * ld]);
+#pragma unroll 8
+                for (int i0 = 0; i0 < TR; i0 += 4) dmma_acc2(g[q], pa[i0 * ld], pb[i0 * ld]);
             }
         }
     }
@@ -965,14 +1013,14 @@ __global__ void __launch_bounds__(256, (GT <= 5 ? 2 : 1)) sparse_A_diag_fused_ke
             if (a < H && b + 1 < H) { out[a * H + b + 1] = g[q][1]; out[(b + 1) * H + a] = g[q][1]; }
         }
     }
-    // column sums of s: element slot (t, k) always holds column (t + 256k) % HP8 -> fixed-order sum over the 32 rows of the slot grid
+    // column sums of s: element slot (t, k) always holds column (t + 256k) % HP8 -> fixed-order sum over the TR rows of the slot grid
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) { const int e = threadIdx.x + 256 * k; if (e < nel) stage[e] = csum[k]; }
     __syncthreads();
     if (threadIdx.x < HP8) {
         double t = 0.0;
-        for (int i = 0; i < 32; ++i) t += stage[i * HP8 + threadIdx.x];
+        for (int i = 0; i < TR; ++i) t += stage[i * HP8 + threadIdx.x];
         out[H * H + threadIdx.x] = t;
     }
 #pragma unroll
@@ -1010,13 +1058,16 @@ __global__ void __launch_bounds__(256) sparse_diag_reduce_kernel(Dev d, int npar
         else if (d.kind == KIND_DUAL || d.kind == KIND_TRIAL) (d.packed + packed_ex(d))[e - H * H - HP8] = t;
     }
 }
-static size_t sparse_diag_fused_smem(int H) { const int HP8 = (H + 7) & ~7; return (size_t)(32 * pitch4(HP8) + HP8 + 32 * HP8) * sizeof(double); }
+static size_t sparse_diag_fused_smem(int H) {
+    const int HP8 = (H + 7) & ~7, TR = 32;
+    return (size_t)(TR * pitch4(HP8) + HP8 + TR * HP8) * sizeof(double);
+}
 int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags) {
     const int H = d.H, HP8 = (H + 7) & ~7;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
     const size_t smem = sparse_diag_fused_smem(H);
-    const int per_sm = HP8 <= 64 ? 2 : 1;
-    const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), 32), 148 * per_sm));
+    const int per_sm = HP8 <= 64 ? 2 : 1, TR = 32;
+    const int grid = std::max(1, std::min(cdiv(std::max(d.Mloc, 1), TR), 148 * per_sm));
     if (HP8 <= 32) sparse_A_diag_fused_kernel<2><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
     else if (HP8 <= 64) sparse_A_diag_fused_kernel<5><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
     else sparse_A_diag_fused_kernel<17><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
@@ -2286,8 +2337,8 @@ int kernels_init_device() {
     VB_SMEM_ATTR(dense_A_fused_kernel<2>, mxA);
     VB_SMEM_ATTR(dense_A_fused_kernel<8>, mxA);
     VB_SMEM_ATTR(dense_A_fused_kernel<32>, mxA);
-    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<2>, sparse_diag_fused_smem(128));
-    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<5>, sparse_diag_fused_smem(128));
+    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<2>, sparse_diag_fused_smem(32));
+    VB_SMEM_ATTR(sparse_A_diag_fused_kernel<5>, sparse_diag_fused_smem(64));
     VB_SMEM_ATTR(sparse_A_diag_fused_kernel<17>, sparse_diag_fused_smem(128));
     VB_SMEM_ATTR((sparse_A_full_kernel<BlockGroup, 64>), (128 * 129 + 384) * 8);
     VB_SMEM_ATTR((sparse_A_full_dmma_kernel<1, 4, false>), k4_dmma_smem<1>());

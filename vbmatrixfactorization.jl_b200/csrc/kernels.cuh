@@ -68,6 +68,11 @@ int k_total(cudaStream_t st, const double* x, int n, double* out);   // out[0] =
 int k_norms_init(cudaStream_t st, const Dev& d);                 // normBold = norm(BHat) from d.BtB
 int k_dense_sigmaA(cudaStream_t st, const Dev& d);               // SigmaA = sigma2*inv(B'B + L*SigmaB + sigma2*invCA)
 int k_dense_A_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride);   // A = (sum_s P_s * SigmaA)/sigma2, mask, A'A
+int k_dense_A_fused_range(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int m_begin, int m_end,
+                          int part_base, int max_parts, int* nparts);      // one column chunk; Gram partials stay in d.part
+int k_sum_gram_partials(cudaStream_t st, const Dev& d, int nparts);       // packed.AtA = sum of the chunk partials
+int k_y_stats_chunk(cudaStream_t st, const Dev& d, int m0, int n, int first);   // rowY2 (+)= row norms of one column chunk
+int k_copy_trYTY(cudaStream_t st, const Dev& d, const double* d_tr);      // sc->trYTY = *d_tr (device side, stream ordered)
 int k_sparse_A_diag(cudaStream_t st, const Dev& d, int flags);   // diagonal path incl. Q2 map; partial column sums of s
 int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags);   // batched H x H SPD inverse per column
 int k_sparse_A_full_ex(cudaStream_t st, const Dev& d, int flags, const double* slabs, int S, size_t slab_stride, int fuse_ca);
