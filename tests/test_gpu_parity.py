@@ -884,7 +884,7 @@ def test_chunked_upload_overlapped_first_iteration(G, monkeypatch):
         G.vb.vbmf_(Yf, q5, 5, eps=0.0, est_covs=True, est_var=True, ctx=c)       # followed by ordinary iterations
         floor = G.sensitivity(lambda s_: vo.vbmf_run(Y, s_, 5, eps=0.0, est_covs=True, est_var=True), p, G.FIELDS["dense"])
         G.compare(q5, ref5, max(TOL, 100 * floor))
-        G.compare(q5, plain, max(TOL, 100 * floor))
+        G.compare(q5, plain, max(TOL, 100 * floor), G.FIELDS["dense"])
         assert G.rel(q5.YHat, q5.BHat @ q5.AHat.T) < 1e-13
         # the other consumers of Y wait for the upload: trYTY, the contractions, a sparse run
         c.attach(Yf)
