@@ -211,6 +211,10 @@ int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_s
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
 int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* ctx, double* allreduce_ms, int64_t* allreduce_launches);
+/* 1 when this context's updateB! exchange (src/vbmf.jl:109-113 across column shards) runs through peer-mapped memory over
+ * NVLink with the library's own kernels (world 2..8 on one node, H <= 64, decided when the first solver is created; switched
+ * off with VBMF_B200_NO_PX=1), 0 when it uses the NCCL all-reduce.  (none in the reference: it is one process on one host) */
+int vbmf_b200_ctx_peer_exchange(vbmf_b200_ctx* ctx);
 
 /* ---- K1 / K2 on their own (parity tests of the two contractions) ---- */
 /* P (M_local x H, column-major) = Y' * B ;  B is L x H column-major.  src/vbmf.jl:98 */

@@ -90,10 +90,36 @@ def main():
         bad = {f: e for f, e in errs.items() if not e < 1e-10}
         assert not bad, (kind, kw, bad)
         worst = max(worst, max(errs.values()))
+    # the updateB! exchange ran through peer-mapped memory (own kernels over NVLink) unless it was switched off
+    px = ctx.peer_exchange()
+    assert px == (world <= 8 and os.environ.get("VBMF_B200_NO_PX") is None), px
+    # many row tiles per rank, ragged last tile, H = 64 / 32: dense and sparse (diagonal) through the exchange kernels
+    for kind, (L2, M2, H2), kw in (("dense", (1000, 3001, 64), dict(est_covs=True, est_var=True)),
+                                   ("sparse", (517, 2000, 32), dict(full_cov=False, est_cb=True)),
+                                   ("dual", (300, 1500, 16), dict(full_cov=True, est_priors=True, est_cb=True))):
+        Y2 = synth(L2, M2, 6, seed=17)
+        off2, n2 = vb.shard_columns(M2, world, rank)
+        ctx.attach(np.asfortranarray(Y2[:, off2:off2 + n2]), M_global=M2, col_offset=off2)
+        rng = np.random.default_rng(21)
+        po = vo.vbmf_init(Y2, H2, ca=1.0, cb=1.0, sigma2=1.0, rng=rng) if kind == "dense" else (
+            vo.vbmf_sparse_init(Y2, H2, rng=rng) if kind == "sparse" else vo.vbmf_dual_init(Y2, H2, 5, rng=rng))
+        for it in range(3):                      # teacher-forced: every iteration starts from the oracle's state
+            q = shard(G.to_gpu_params(po), off2, n2, kind)
+            if kind == "dense":
+                vo.vbmf_run(Y2, po, 1, eps=0.0, **kw); vb.vbmf_(None, q, 1, eps=0.0, ctx=ctx, yhat=False, **kw)
+            elif kind == "sparse":
+                vo.vbmf_sparse_run(Y2, po, 1, eps=0.0, **kw); vb.vbmf_sparse_(None, q, 1, eps=0.0, ctx=ctx, yhat=False, **kw)
+            else:
+                vo.vbmf_dual_run(Y2, po, 1, eps=0.0, **kw); vb.vbmf_dual_(None, q, 1, eps=0.0, ctx=ctx, yhat=False, **kw)
+            ref = shard(po, off2, n2, kind)
+            errs = {f: G.rel(getattr(q, f), getattr(ref, f)) for f in G.FIELDS[kind]}
+            bad = {f: e for f, e in errs.items() if not e < 1e-10}
+            assert not bad, (kind, it, bad)
+            worst = max(worst, max(errs.values()))
     t = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("MGPU OK world=%d worst_rel_err=%.2e" % (world, t.item()), flush=True)
+        print("MGPU OK world=%d worst_rel_err=%.2e peer_exchange=%s" % (world, t.item(), px), flush=True)
     ctx.close()
     dist.destroy_process_group()
 

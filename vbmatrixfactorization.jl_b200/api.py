@@ -147,6 +147,10 @@ class Context:
         L_.check(self.lib.vbmf_b200_gemm_YA(self.h, _ptr(A), A.shape[1], _ptr(Q)))
         return Q
 
+    def peer_exchange(self):
+        """True when updateB!'s exchange between the column shards runs through peer-mapped memory (own kernels over NVLink)."""
+        return bool(self.lib.vbmf_b200_ctx_peer_exchange(self.h))
+
     def profile(self, enable=True):
         L_.check(self.lib.vbmf_b200_ctx_profile(self.h, 1 if enable else 0))
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -35,6 +36,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
     int (*CommInitAll)(void**, int, const int*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -53,6 +55,7 @@ static int load_nccl() {
     g_nccl.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
     g_nccl.CommInitAll = (int (*)(void**, int, const int*))dlsym(h, "ncclCommInitAll");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -105,6 +108,16 @@ struct vbmf_b200_ctx {
     // profiling of the two contractions
     bool profile = false;
     std::vector<cudaEvent_t> ev_k1, ev_k2, ev_ar;      // K1, K2 and (world > 1) the per-iteration all-reduce
+    // peer exchange (kernels.cuh, PxDev): this rank's peer-visible buffer and the peers' buffers as mapped into this device
+    struct Px {
+        bool ok = false, failed = false, claimed = false;
+        char* local = nullptr;
+        size_t cap = 0;
+        char* peer[PX_MAX_WORLD] = {};
+        bool ipc[PX_MAX_WORLD] = {};
+        char* xchg = nullptr;             // device staging of the handle exchange
+        unsigned long long epoch = 0;     // barrier epochs consumed so far (identical on every rank)
+    } px;
     // grow-only staging for the batched small-problem path (device arena + pinned host mirror, same offsets)
     char* batch_dev = nullptr;
     char* batch_host = nullptr;
@@ -114,6 +127,104 @@ struct vbmf_b200_ctx {
 static int ctx_allreduce(vbmf_b200_ctx* c, double* buf, size_t n) {
     if (c->world <= 1 || n == 0) return 0;
     VB_NCCL_OK(g_nccl.AllReduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- peer exchange set-up
+// One peer-visible buffer per rank, mapped into every other rank's device: cudaIpc handles between processes (one process per
+// GPU), plain peer access inside one process (vbmf_b200_mctx_*).  The handles travel through the communicator the context
+// already has; the outcome is agreed on by all ranks (one failing rank switches the exchange off everywhere, the NCCL
+// all-reduce path stays).  Collective: every rank calls it at the same point with the same size.
+struct PxRec {
+    long long pid;
+    unsigned long long host;
+    unsigned long long ptr;
+    int dev, ok;
+    cudaIpcMemHandle_t h;
+    char pad[128 - 32 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(PxRec) == 128, "PxRec is exchanged as 128 bytes");
+static void px_release(vbmf_b200_ctx* c) {
+    auto& x = c->px;
+    for (int r = 0; r < PX_MAX_WORLD; ++r) {
+        if (x.ipc[r] && x.peer[r]) cudaIpcCloseMemHandle(x.peer[r]);
+        x.peer[r] = nullptr; x.ipc[r] = false;
+    }
+    if (x.local) cudaFree(x.local);
+    if (x.xchg) cudaFree(x.xchg);
+    x.local = nullptr; x.xchg = nullptr; x.cap = 0; x.ok = false;
+    cudaGetLastError();
+}
+static int px_setup(vbmf_b200_ctx* c, size_t data_bytes) {
+    auto& x = c->px;
+    if (c->world > PX_MAX_WORLD || x.failed || getenv("VBMF_B200_NO_PX") != nullptr) return 0;
+    const size_t need = PX_FLAG_BYTES + data_bytes;
+    if (x.ok && x.cap >= need) return 0;
+    const int W = c->world;
+    const size_t cap = (std::max(need, (size_t)32 << 20) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    if (W == 1) {
+        // test switch VBMF_B200_PX_SELF=1: a single rank runs the exchange kernels against itself (same code, W = 1)
+        if (getenv("VBMF_B200_PX_SELF") == nullptr) return 0;
+        VB_CUDA_OK(cudaStreamSynchronize(c->st));
+        px_release(c);
+        if (cudaMalloc(&x.local, cap) != cudaSuccess) { cudaGetLastError(); x.local = nullptr; x.failed = true; return 0; }
+        VB_CUDA_OK(cudaMemsetAsync(x.local, 0, cap, c->st));
+        x.cap = cap; x.ok = true;
+        return 0;
+    }
+    if (g_nccl.AllGather == nullptr) return 0;
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    px_release(c);
+    PxRec mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.pid = (long long)getpid();
+    {
+        char hn[256] = "";
+        gethostname(hn, sizeof(hn) - 1);
+        unsigned long long hsh = 1469598103934665603ULL;
+        for (const char* q = hn; *q; ++q) hsh = (hsh ^ (unsigned char)*q) * 1099511628211ULL;
+        mine.host = hsh;
+    }
+    mine.dev = c->device;
+    mine.ok = 1;
+    if (cudaMalloc(&x.local, cap) != cudaSuccess || cudaMalloc(&x.xchg, (size_t)(W + 2) * 128) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    if (mine.ok && (cudaMemsetAsync(x.local, 0, cap, c->st) != cudaSuccess || cudaIpcGetMemHandle(&mine.h, x.local) != cudaSuccess)) { cudaGetLastError(); mine.ok = 0; }
+    mine.ptr = (unsigned long long)(uintptr_t)x.local;
+    if (x.xchg == nullptr) {      // nothing to exchange through: every rank must still take part in the collectives below
+        if (cudaMalloc(&x.xchg, (size_t)(W + 2) * 128) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed (peer exchange set-up)"); x.failed = true; return -1; }
+    }
+    std::vector<PxRec> all(W);
+    VB_CUDA_OK(cudaMemcpyAsync(x.xchg, &mine, 128, cudaMemcpyHostToDevice, c->st));
+    VB_NCCL_OK(g_nccl.AllGather(x.xchg, x.xchg + 128, 128, /*ncclInt8*/ 0, c->comm, c->st));
+    VB_CUDA_OK(cudaMemcpyAsync(all.data(), x.xchg + 128, (size_t)W * 128, cudaMemcpyDeviceToHost, c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    int good = mine.ok;
+    for (int r = 0; r < W && good; ++r) {
+        if (r == c->rank) continue;
+        const PxRec& pr = all[r];
+        if (!pr.ok || pr.host != mine.host) { good = 0; break; }
+        if (pr.pid == mine.pid) {
+            int can = 0;
+            if (pr.dev == c->device || cudaDeviceCanAccessPeer(&can, c->device, pr.dev) != cudaSuccess || !can) { cudaGetLastError(); good = 0; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(pr.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); good = 0; break; }
+            cudaGetLastError();
+            x.peer[r] = (char*)(uintptr_t)pr.ptr;
+        } else {
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, pr.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+            x.peer[r] = (char*)q; x.ipc[r] = true;
+        }
+    }
+    // agree: the number of ranks that could not map everybody
+    double bad = good ? 0.0 : 1.0;
+    double* dflag = (double*)(x.xchg + (size_t)(W + 1) * 128);
+    VB_CUDA_OK(cudaMemcpyAsync(dflag, &bad, 8, cudaMemcpyHostToDevice, c->st));
+    VB_NCCL_OK(g_nccl.AllReduce(dflag, dflag, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->st));
+    VB_CUDA_OK(cudaMemcpyAsync(&bad, dflag, 8, cudaMemcpyDeviceToHost, c->st));
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (bad != 0.0) { px_release(c); x.failed = true; return 0; }
+    x.cap = cap; x.ok = true;
     return 0;
 }
 
@@ -224,6 +335,7 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
     cudaStreamSynchronize(c->st);
     ctx_free_Y(c);
     if (c->d_tr) cudaFree(c->d_tr);
+    px_release(c);
     if (c->batch_dev) cudaFree(c->batch_dev);
     if (c->batch_host) cudaFreeHost(c->batch_host);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
@@ -481,6 +593,7 @@ extern "C" int vbmf_b200_ctx_profile(vbmf_b200_ctx* c, int enable) {
     return 0;
 }
 // CUDA-event time of the per-iteration all-reduce launches (world > 1; zero launches otherwise)
+extern "C" int vbmf_b200_ctx_peer_exchange(vbmf_b200_ctx* c) { return (c != nullptr && c->px.ok) ? 1 : 0; }
 extern "C" int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* c, double* ar_ms, int64_t* ar_n) {
     VB_CUDA_OK(cudaStreamSynchronize(c->st));
     double t = 0;
@@ -521,6 +634,8 @@ struct vbmf_b200_solver {
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
     bool ca_done = false;     // the fused diagonal A pass already did updateCA! of this iteration
+    bool loop_ahead = false;      // set by solver_run while it enqueues whole iterations back to back
+    bool sigmaA_ahead = false;    // dense loop: the NEXT iteration's SigmaA was already inverted on the side stream (behind post)
     bool need_tr_copy = false;    // dense: sum(Y.^2) was still being computed at upload time; copy it device-side before its first use
     double* Qc = nullptr;         // [chunks][H*ldB] per-chunk Y*AHat of the upload-overlapped first iteration (allocated on demand)
     size_t Qc_chunks = 0;
@@ -535,6 +650,9 @@ struct vbmf_b200_solver {
     // small problems are launch bound: one iteration is captured into a CUDA graph and replayed
     cudaGraphExec_t gexec = nullptr;
     int gexec_flags = -1;
+    // peer exchange: packed / BHat / rank partials live in the context's peer-visible buffer at these byte offsets
+    bool px = false;
+    size_t px_packed = 0, px_B = 0, px_gpart = 0;
     Scalars h_sc;
 };
 
@@ -590,14 +708,31 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
     const size_t MH = (size_t)std::max(d.Mloc, 1) * H, LH = (size_t)H * d.ldB, HH = (size_t)H * H, Lr = (size_t)d.L;
     const size_t part_elems = std::max<size_t>({(size_t)MAX_PARTS * HH, (size_t)2400 * std::min<size_t>(H, 32) * std::min<size_t>(H, 32),
                                                 (size_t)300 * Lr, (size_t)16384});
+    // world > 1, H <= 64: the updateB! exchange runs through peer-mapped memory (kernels.cuh, PxDev); the payload and BHat then
+    // live in the context's peer-visible buffer.  One solver per context at a time owns it; the others use the NCCL all-reduce.
+    if ((c->world > 1 || getenv("VBMF_B200_PX_SELF") != nullptr) && H <= 64) {
+        s->px_packed = PX_FLAG_BYTES;
+        s->px_B = s->px_packed + align_up((LH + 2 * HH + 8) * 8, 256);
+        s->px_gpart = s->px_B + align_up(LH * 8, 256);
+        const size_t px_end = s->px_gpart + align_up((size_t)PX_MAX_WORLD * (2 * HH + 1) * 8, 256);
+        if (px_setup(c, px_end - PX_FLAG_BYTES)) { delete s; return -1; }
+        if (c->px.ok && !c->px.claimed) {
+            s->px = true; c->px.claimed = true;
+            if (cudaMemsetAsync(c->px.local + PX_FLAG_BYTES, 0, px_end - PX_FLAG_BYTES, c->st) != cudaSuccess) { set_error("cudaMemset failed"); c->px.claimed = false; delete s; return -1; }
+        }
+    }
     struct Item { double** p; size_t n; };
     std::vector<Item> items = {
-        {&d.A, MH}, {&d.P, MH}, {&d.B, LH}, {&d.Bold, LH}, {&d.D, LH}, {&d.Bs, LH}, {&d.packed, LH + 2 * HH + 8},
+        {&d.A, MH}, {&d.P, MH}, {&d.Bold, LH}, {&d.D, LH}, {&d.Bs, LH},
         {&d.SigmaA, HH}, {&d.SigmaB, HH}, {&d.BtB, HH}, {&d.BtBw, HH}, {&d.DtD, HH}, {&d.Gm, HH},
         {&d.sigmaVec, Lr}, {&d.etaVec, Lr}, {&d.zetaVec, Lr}, {&d.part, part_elems}, {&d.lbacc, 32},
         {&s->Qpart, (size_t)std::max(std::max(s->S, s->S_chunk), s->k2_sk ? s->sk_smax : 1) * LH},
     };
     if (s->S1 > 1) items.push_back({&s->Ppart, (size_t)s->S1 * MH});
+    if (s->px) {
+        d.packed = (double*)(c->px.local + s->px_packed);
+        d.B = (double*)(c->px.local + s->px_B);
+    } else { items.push_back({&d.B, LH}); items.push_back({&d.packed, LH + 2 * HH + 8}); }
     if (kind == VBMF_B200_DENSE) { items.push_back({&d.CA, HH}); items.push_back({&d.CB, HH}); items.push_back({&d.invCA, HH}); items.push_back({&d.invCB, HH}); }
     else {
         items.push_back({&d.CAv, MH}); items.push_back({&d.beta, MH}); items.push_back({&d.sdiag, MH});
@@ -609,11 +744,12 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
     if (cudaMalloc(&s->arena, total) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc of %zu bytes of solver state failed", total);
+        if (s->px) c->px.claimed = false;
         delete s;
         return -1;
     }
     s->arena_bytes = total;
-    if (cudaMemsetAsync(s->arena, 0, total, c->st) != cudaSuccess) { set_error("cudaMemset failed"); cudaFree(s->arena); delete s; return -1; }
+    if (cudaMemsetAsync(s->arena, 0, total, c->st) != cudaSuccess) { set_error("cudaMemset failed"); cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1; }
     char* p = s->arena;
     d.sc = (Scalars*)p; p += align_up(sizeof(Scalars), 256);
     s->d_labels = (int*)p; p += align_up((size_t)std::max(d.nlabels, 1) * 4, 256);
@@ -624,14 +760,14 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
         std::vector<int> lab(d.nlabels);
         for (int i = 0; i < d.nlabels; ++i) {
             const int64_t v = labels[i];
-            if (v < 1 || v > d.Mloc) { set_error("label %lld out of range 1..%d", (long long)v, d.Mloc); cudaFree(s->arena); delete s; return -1; }
+            if (v < 1 || v > d.Mloc) { set_error("label %lld out of range 1..%d", (long long)v, d.Mloc); cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1; }
             lab[i] = (int)(v - 1);
         }
         std::vector<unsigned char> rm((size_t)std::max(d.Mloc, 1), 0);
         for (int v : lab) rm[v] = 1;
         if (cudaMemcpyAsync(s->d_labels, lab.data(), (size_t)d.nlabels * 4, cudaMemcpyHostToDevice, c->st) != cudaSuccess ||
             cudaMemcpyAsync(d_rowmask, rm.data(), rm.size(), cudaMemcpyHostToDevice, c->st) != cudaSuccess ||
-            cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("label upload failed"); cudaFree(s->arena); delete s; return -1; }
+            cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("label upload failed"); cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1; }
         d.rowmask = (d.H1 > 0) ? d_rowmask : nullptr;
     }
     const GemmGeometry g = gemm_geometry(d.H);
@@ -639,13 +775,13 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
     rc |= make_tmap_2d(&s->tmB, d.B, (uint64_t)d.L, (uint64_t)H, (uint64_t)d.ldB * 8, 16, (uint32_t)g.bn);
     rc |= make_tmap_2d(&s->tmBs, d.Bs, (uint64_t)d.L, (uint64_t)H, (uint64_t)d.ldB * 8, 16, (uint32_t)g.bn);
     if (!s->k2_simt && d.Mloc > 0) rc |= make_tmap_2d(&s->tmA, d.A, (uint64_t)H, (uint64_t)d.Mloc, (uint64_t)H * 8, 16, 16);
-    if (rc) { cudaFree(s->arena); delete s; return -1; }
+    if (rc) { cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1; }
     if (cudaMallocHost(&s->h_flag, 2 * sizeof(int)) != cudaSuccess || cudaEventCreateWithFlags(&s->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_p, cudaEventDisableTiming) != cudaSuccess) {
-        set_error("pinned flag / event allocation failed"); cudaFree(s->arena); delete s; return -1;
+        set_error("pinned flag / event allocation failed"); cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1;
     }
     memset(&s->h_sc, 0, sizeof(Scalars));
     *out = s;
@@ -674,6 +810,7 @@ extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
     if (s->Qc) cudaFree(s->Qc);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     for (int i = 0; i < 2; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->px) s->c->px.claimed = false;
     delete s;
     return 0;
 }
@@ -992,7 +1129,11 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
     if (d.kind == KIND_DENSE) {
         // the epilogue sums the K1 slabs itself, multiplies by SigmaA/sigma2, masks, and leaves the local AHat'AHat in packed
         // K1 needs BHat only; everything after it needs the previous iteration's sigma2 / invCA (post) -> wait there
-        if (enq_k1(s, false, false) || wait_post(s) || k_dense_sigmaA(st, d)) return -1;
+        // SigmaA needs B'B, SigmaB, sigma2 and inv(CA) only -- all final once the previous iteration's tail has run -- so inside
+        // the loop it is inverted on the side stream right behind that tail, concurrently with K1 (enq_iteration)
+        if (enq_k1(s, false, false) || wait_post(s)) return -1;
+        if (!s->sigmaA_ahead && k_dense_sigmaA(st, d)) return -1;
+        s->sigmaA_ahead = false;
         const bool slabs = !s->c->simt && s->S1 > 1;
         if (k_dense_A_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H)) return -1;
         s->ata_local = true;
@@ -1052,9 +1193,43 @@ static int enq_q_ata(vbmf_b200_solver* s, bool fused) {
     if (fused) s->extras_valid = true;
     return 0;
 }
+// the peers' regions of this solver as seen from this device; consumes `nbar` barrier epochs
+static PxDev px_view(vbmf_b200_solver* s, int nbar) {
+    vbmf_b200_ctx* c = s->c;
+    PxDev p;
+    memset(&p, 0, sizeof(p));
+    p.rank = c->rank; p.W = c->world; p.epoch = c->px.epoch;
+    c->px.epoch += (unsigned long long)nbar;
+    for (int r = 0; r < c->world; ++r) {
+        char* base = r == c->rank ? c->px.local : c->px.peer[r];
+        p.flags[r] = (unsigned long long*)base;
+        p.packed[r] = (double*)(base + s->px_packed);
+        p.B[r] = (double*)(base + s->px_B);
+        p.gpart[r] = (double*)(base + s->px_gpart);
+    }
+    return p;
+}
 static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
     const Dev& d = s->d;
     cudaStream_t st = s->c->st;
+    if (fused && s->px && !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR))) {
+        // updateB! with the exchange done by our own kernels over NVLink: the small sums are gathered from the peers, SigmaB
+        // is inverted redundantly, every rank reduces its share of the rows of Y*AHat over the peers, runs the epilogue on
+        // them and writes the new BHat rows to every peer; the Grams of BHat / BHat - Bold are exchanged as rank partials.
+        // (The heteroscedastic row update needs all rows of the reduced Y*AHat on every rank: that case keeps the all-reduce.)
+        if (!s->ata_local && enq_gram_A(s)) return -1;
+        s->ata_local = false;
+        if (enq_k2(s)) return -1;
+        prof_mark(s->c, s->c->ev_ar);
+        if (k_px_small(st, d, px_view(s, 2))) return -1;
+        if (k_sigmaB(st, d, flags)) return -1;
+        if (k_B_epilogue_px(st, d, flags, px_view(s, 1))) return -1;
+        prof_mark(s->c, s->c->ev_ar);
+        s->ata_valid = true; s->extras_valid = true;
+        s->q_valid = false;                         // packed.Q is reduced on this rank's rows only
+        s->btb_valid = true;
+        return 0;
+    }
     if (!fused && d.kind != KIND_DENSE) {
         // step-level: packed.SA must hold the (global) SigmaA the state carries
         VB_CUDA_OK(cudaMemcpyAsync(d.packed + packed_sa(d), d.SigmaA, (size_t)d.H * d.H * 8, cudaMemcpyDeviceToDevice, st));
@@ -1149,6 +1324,10 @@ static int enq_iteration(vbmf_b200_solver* s, int flags) {
     VB_CUDA_OK(cudaEventRecord(s->ev_b, st));
     VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_b, 0));
     if (k_post(s->side, d, flags, true)) return -1;
+    if (d.kind == KIND_DENSE && s->loop_ahead) {       // SigmaA of the next iteration (skipped with it if the loop has just ended)
+        if (k_dense_sigmaA(s->side, d)) return -1;
+        s->sigmaA_ahead = true;
+    }
     VB_CUDA_OK(cudaEventRecord(s->ev_p, s->side));
     s->post_pending = true;
     return 0;
@@ -1223,12 +1402,14 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
     if (d.kind == KIND_DENSE) flags &= (F_EST_COVS | F_EST_VAR);
     if (k_set_control(st, d, (int)niter, eps, norm_mode, 0)) return -1;
     s->btb_valid = false;
+    s->sigmaA_ahead = false;
+    s->loop_ahead = getenv("VBMF_B200_NO_SIGMAA_AHEAD") == nullptr;
     if (enq_gram_B(s, flags) || k_norms_init(st, d)) return -1;      // old = BHat, src/vbmf.jl:188
     int64_t enq = 0;
     int slot = 0;
     bool pending = false;
     // Launch-bound regime (one iteration is ~12 launches of a few microseconds each): replay one captured iteration.
-    const bool graph_mode = s->c->world == 1 && !s->c->profile && niter >= 4 && getenv("VBMF_B200_NO_GRAPH") == nullptr &&
+    const bool graph_mode = s->c->world == 1 && !s->px && !s->c->profile && niter >= 4 && getenv("VBMF_B200_NO_GRAPH") == nullptr &&
                             (double)d.L * (double)std::max(d.Mloc, 1) * (double)d.H < 4e9;
     if (graph_mode) {
         if (enq_iteration(s, flags) || wait_post(s)) return -1;       // first iteration eagerly (also settles one-time kernel attributes)
@@ -1282,6 +1463,7 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
         pending = true;
         slot ^= 1;
     }
+    s->loop_ahead = false; s->sigmaA_ahead = false;
     if (wait_post(s) || pull_scalars(s)) return -1;
     if (iters) *iters = s->h_sc.iter;
     if (dout) *dout = s->h_sc.d;

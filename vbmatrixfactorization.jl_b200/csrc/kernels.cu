@@ -1563,8 +1563,11 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
 // DMMA version of the same epilogue for H <= 64 (HP8 = H rounded up to 8, shared pitch = 4 mod 16 as in the A epilogue):
 //   Bn = (c .* Qtile) * SigmaB [/ sigma2]        32 x HP8 x HP8 product, 4 x HP8/8 mma tiles over 8 warps
 //   G_B += Bn' Bn,  G_D += Dn' Dn                 accumulators in registers across the CTA's tiles
-template <int TPW, bool GRAM>   // Gram tiles per warp: ceil((HP8/8)^2 / 8); GRAM = false (H > 64): the Grams come from gram_dmma
-__global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(Dev d, int diag_var) {
+// PX (peer exchange, world > 1): the CTA grid covers only this rank's share of the 32-row tiles; a tile of Q is the sum of
+// the peers' local Y*AHat tiles in rank order (the reduce-scatter; the sum is also stored in place, peers never read this
+// rank's own rows), and the new BHat rows are written to every peer's BHat (the all-gather).
+template <int TPW, bool GRAM, bool PX>   // Gram tiles per warp: ceil((HP8/8)^2 / 8); GRAM = false (H > 64): the Grams come from gram_dmma
+__global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(Dev d, int diag_var, PxDev px, int tile_lo, int tile_hi) {
     ACTIVE_OR_RETURN(d);
     extern __shared__ double sm[];
     __shared__ double red[32];
@@ -1575,7 +1578,7 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
     double* Dn = Bn + 32 * ld;       // [32][ld]   (GRAM only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
     const Scalars* sc = d.sc;
-    const double* Q = d.packed + packed_q(d);
+    double* Q = d.packed + packed_q(d);
     for (int e = threadIdx.x; e < HP8 * ld; e += 256) {
         const int i = e / ld, c = e - i * ld;
         Ss[e] = (i < H && c < H) ? d.SigmaB[i * H + c] : 0.0;
@@ -1594,15 +1597,24 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         gt[q] = at < nt8 ? (at | ((at + idx) << 8)) : -1;
     }
     double tr = 0.0;
-    const int ntiles = (d.L + 31) / 32;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ntiles = PX ? tile_hi : (d.L + 31) / 32;
+    for (int tile = (PX ? tile_lo : 0) + blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int l0 = tile * 32, nr = min(32, d.L - l0);
         __syncthreads();
         for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
             const int h = e >> 5, i = e & 31;
             double q = 0.0;
             if (i < nr && h < H) {
-                q = Q[(size_t)h * d.ldB + l0 + i];
+                const size_t g = (size_t)h * d.ldB + l0 + i;
+                if (PX) {
+                    double v[PX_MAX_WORLD];
+#pragma unroll
+                    for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[rk] = rk < px.W ? __ldcg(px.packed[rk] + g) : 0.0;   // L2 only: peer data
+                    q = v[0];
+#pragma unroll
+                    for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) q += v[rk];
+                    Q[g] = q;
+                } else q = Q[g];
                 if (!dense) q *= diag_var ? d.sigmaVec[l0 + i] : sh;
             }
             T[i * ld + h] = q;
@@ -1638,7 +1650,10 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
                             d.Bold[g] = old;
                             dn = v - old;
                             d.D[g] = dn;
-                            d.B[g] = v;
+                            if (PX) {
+#pragma unroll
+                                for (int rk = 0; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) px.B[rk][g] = v;
+                            } else d.B[g] = v;
                             tr = fma(v, Q[g], tr);
                             bn = v;
                         }
@@ -1686,8 +1701,61 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         if (threadIdx.x == 0) d.part[blockIdx.x] = tr;         // Grams follow from gram_dmma on B and D
     }
 }
+// ---- peer exchange: barrier between the CTAs with the same index b on all ranks.  Slot (b, src) of a rank's flag array is
+// written by rank src only and only grows, so `>= epoch` needs no reset.  The release / acquire pair at system scope orders
+// this CTA's earlier peer stores (and, through the kernel boundary, everything the stream ran before) ahead of the peers'
+// later loads.  A peer that never arrives (a rank that failed on the host) ends the wait after ~30 s with the sticky error
+// flag set instead of hanging the device.
+__device__ __forceinline__ void px_barrier(const Dev& d, const PxDev& px, int b, unsigned long long ep) {
+    __syncthreads();
+    if ((int)threadIdx.x < px.W) {
+        const int r = threadIdx.x;
+        unsigned long long* dst = px.flags[r] + (size_t)b * PX_MAX_WORLD + px.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(ep) : "memory");
+        const unsigned long long* src = px.flags[px.rank] + (size_t)b * PX_MAX_WORLD + r;
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if (v >= ep) break;
+            if (clock64() - t0 > 60000000000LL || (*(volatile int*)&d.sc->chol_fail & 4)) { atomicOr(&d.sc->chol_fail, 4); break; }
+        }
+    }
+    __syncthreads();
+}
+// Global A'A | sum of Sigma blocks | group sums on every rank: barrier (all peers' local parts are final), sum over the
+// peers in rank order into registers, barrier (everybody has read), store in place.  CTA b handles the same elements on
+// every rank, so the per-CTA barriers are enough.
+__global__ void __launch_bounds__(256) px_small_kernel(Dev d, PxDev px) {
+    ACTIVE_OR_RETURN(d);
+    const size_t off = packed_ata(d);
+    const int n = 2 * d.H * d.H + 8;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    px_barrier(d, px, blockIdx.x, px.epoch + 1);
+    double acc = 0.0;
+    if (e < n) {
+        double v[PX_MAX_WORLD];
+#pragma unroll
+        for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[rk] = rk < px.W ? __ldcg(px.packed[rk] + off + e) : 0.0;
+        acc = v[0];
+#pragma unroll
+        for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) acc += v[rk];
+    }
+    px_barrier(d, px, blockIdx.x, px.epoch + 2);
+    if (e < n) d.packed[off + e] = acc;
+}
+int k_px_small(cudaStream_t st, const Dev& d, const PxDev& px) {
+    const int grid = cdiv(2 * d.H * d.H + 8, 256);
+    px_small_kernel<<<grid, 256, 0, st>>>(d, px);
+    VB_LAUNCH_OK();
+    return 0;
+}
+
 // fixed-order reduction of the per-CTA partials: BtB, DtD, sc->trBQ
-__global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
+// PX: the local sum is this rank's partial (its rows of BHat only): it is written to slot `rank` of every peer, and after the
+// barrier -- which also says that every peer's BHat rows have landed here -- the rank partials are summed in rank order.
+template <bool PX>
+__global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts, PxDev px) {
     ACTIVE_OR_RETURN(d);
     __shared__ double sm[8][33];
     const int H = d.H, n = 2 * H * H + 1;
@@ -1700,10 +1768,25 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts) {
     }
     sm[y][x] = s;
     __syncthreads();
+    double t = 0.0;
     if (y == 0 && e < n) {
-        double t = sm[0][x];
+        t = sm[0][x];
 #pragma unroll
         for (int k = 1; k < 8; ++k) t += sm[k][x];
+    }
+    if (PX) {
+        if (y == 0 && e < n) {
+#pragma unroll
+            for (int rk = 0; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) px.gpart[rk][(size_t)px.rank * n + e] = t;
+        }
+        px_barrier(d, px, blockIdx.x, px.epoch + 1);
+        if (y == 0 && e < n) {
+            const double* gp = px.gpart[px.rank];
+            t = __ldcg(gp + e);
+            for (int rk = 1; rk < px.W; ++rk) t += __ldcg(gp + (size_t)rk * n + e);
+        }
+    }
+    if (y == 0 && e < n) {
         if (e < H * H) d.BtB[e] = t;
         else if (e < 2 * H * H) d.DtD[e - H * H] = t;
         else d.sc->trBQ = t;
@@ -1716,10 +1799,10 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
         const int HP8 = (H + 7) & ~7;
         const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
         const int grid2 = std::max(1, std::min(cdiv(d.L, 32), 296));      // two CTAs per SM: the tile chain is latency bound
-        if (HP8 <= 32) B_epilogue_dmma_kernel<2, true><<<grid2, 256, smem, st>>>(d, dv);
-        else B_epilogue_dmma_kernel<8, true><<<grid2, 256, smem, st>>>(d, dv);
+        if (HP8 <= 32) B_epilogue_dmma_kernel<2, true, false><<<grid2, 256, smem, st>>>(d, dv, PxDev(), 0, 0);
+        else B_epilogue_dmma_kernel<8, true, false><<<grid2, 256, smem, st>>>(d, dv, PxDev(), 0, 0);
         VB_LAUNCH_OK();
-        B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2);
+        B_reduce_kernel<false><<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2, PxDev());
         VB_LAUNCH_OK();
         return 0;
     }
@@ -1728,7 +1811,7 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
         const int HP8 = (H + 7) & ~7;
         const size_t smem = (size_t)((HP8 + 32) * pitch4(HP8)) * sizeof(double);
         const int grid3 = std::max(1, std::min(cdiv(d.L, 32), 148));
-        B_epilogue_dmma_kernel<1, false><<<grid3, 256, smem, st>>>(d, dv);
+        B_epilogue_dmma_kernel<1, false, false><<<grid3, 256, smem, st>>>(d, dv, PxDev(), 0, 0);
         VB_LAUNCH_OK();
         trbq_kernel<<<1, 256, 0, st>>>(d, grid3);
         VB_LAUNCH_OK();
@@ -1743,7 +1826,23 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     if (H <= 16) BEPI(1, 16, 32) else if (H <= 32) BEPI(2, 16, 32) else if (H <= 64) BEPI(4, 16, 32) else BEPI(4, 32, 16)
 #undef BEPI
     VB_LAUNCH_OK();
-    B_reduce_kernel<<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid);
+    B_reduce_kernel<false><<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid, PxDev());
+    VB_LAUNCH_OK();
+    return 0;
+}
+// updateB!'s epilogue on this rank's share of the rows (peer exchange, H <= 64, homoscedastic noise)
+int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px) {
+    const int H = d.H, HP8 = (H + 7) & ~7;
+    if (H > 64 || (flags & F_DIAG_VAR)) { set_error("peer-exchange epilogue: H <= 64 and homoscedastic noise only"); return -1; }
+    const int ntiles = cdiv(d.L, 32);
+    const int lo = (int)((long long)ntiles * px.rank / px.W), hi = (int)((long long)ntiles * (px.rank + 1) / px.W);
+    const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
+    const int grid2 = std::max(1, std::min(hi - lo, 296));
+    if (HP8 <= 32) B_epilogue_dmma_kernel<2, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
+    else B_epilogue_dmma_kernel<8, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
+    VB_LAUNCH_OK();
+    PxDev px2 = px;
+    B_reduce_kernel<true><<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2, px2);
     VB_LAUNCH_OK();
     return 0;
 }
@@ -2353,9 +2452,11 @@ int kernels_init_device() {
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<24>, (24 * 32 + 8 * 64 + 8 * 32 + 8 * 24 * 32) * 8);
     VB_SMEM_ATTR(sparse_A_full_warp_kernel<32>, (32 * 32 + 8 * 64 + 8 * 32 + 8 * 32 * 32) * 8);
     const int mxB = (int)((64 + 96) * pitch4(64) * 8);
-    VB_SMEM_ATTR((B_epilogue_dmma_kernel<2, true>), mxB);
-    VB_SMEM_ATTR((B_epilogue_dmma_kernel<8, true>), mxB);
-    VB_SMEM_ATTR((B_epilogue_dmma_kernel<1, false>), (128 + 32) * pitch4(128) * 8);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<2, true, false>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<8, true, false>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<2, true, true>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<8, true, true>), mxB);
+    VB_SMEM_ATTR((B_epilogue_dmma_kernel<1, false, false>), (128 + 32) * pitch4(128) * 8);
     VB_SMEM_ATTR((B_epilogue_kernel<1, 16, 32>), (16 + 96) * 17 * 8);
     VB_SMEM_ATTR((B_epilogue_kernel<2, 16, 32>), (32 + 96) * 33 * 8);
     VB_SMEM_ATTR((B_epilogue_kernel<4, 16, 32>), (64 + 96) * 65 * 8);

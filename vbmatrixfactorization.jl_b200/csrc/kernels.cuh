@@ -48,6 +48,22 @@ __host__ __device__ inline size_t packed_len(const Dev& d) { return packed_ex(d)
 
 constexpr int MAX_PARTS = 592;   // upper bound on per-kernel partial blocks (4 x 148)
 
+// ---- peer exchange over NVLink (world <= 8, H <= 64, homoscedastic): the all-reduce -> SigmaB -> BHat epilogue chain of
+// updateB! as reduce-scatter + row-sharded epilogue + all-gather done by our own kernels through peer-mapped memory.
+// Every rank owns one peer-visible buffer [flags | packed | BHat | rank partials]; the pointers below are the SAME regions of
+// every rank's buffer as seen from this device (own entry = local address).
+constexpr int PX_MAX_WORLD = 8;
+constexpr int PX_NBAR = 512;                       // barrier slots (one per participating CTA index)
+constexpr size_t PX_FLAG_BYTES = (size_t)PX_NBAR * PX_MAX_WORLD * sizeof(unsigned long long);
+struct PxDev {
+    int rank, W;
+    unsigned long long epoch;                      // barriers of this launch use epoch + 1, epoch + 2, ...
+    unsigned long long* flags[PX_MAX_WORLD];       // [PX_NBAR][PX_MAX_WORLD]: slot (b, src) is written by rank src only
+    double* packed[PX_MAX_WORLD];                  // all-reduce payload of every rank (same layout as Dev::packed)
+    double* B[PX_MAX_WORLD];                       // BHat of every rank
+    double* gpart[PX_MAX_WORLD];                   // [W][2*H*H + 1]: slot r holds rank r's partial BtB | DtD | tr(B.*Q)
+};
+
 // flags shared by steps
 enum {
     F_DIAG_VAR = 1, F_FULL_COV = 2, F_EST_CB = 4, F_EST_PRIORS = 8, F_EST_COVS = 16, F_EST_VAR = 32,
@@ -85,6 +101,11 @@ int k_sum_slabs(cudaStream_t st, const double* slabs, int S, size_t n, double* o
 int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S);   // fixed-order split-K reduction -> packed.Q
 int k_sigmaB(cudaStream_t st, const Dev& d, int flags);          // SigmaB (dense / sparse), also SigmaA <- packed.SA (sparse)
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags);      // BHat, Bold, D, partial tr(B.*Q)
+// peer exchange (world > 1): global A'A / Sigma sums / group sums on every rank (two barriers, uses epochs +1, +2) ...
+int k_px_small(cudaStream_t st, const Dev& d, const PxDev& px);
+// ... and the BHat epilogue on this rank's rows: Q rows summed over the peers, BHat rows written to every peer, rank partials
+// of the Grams exchanged and summed in rank order (one barrier, epoch +1).  H <= 64 only.
+int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px);
 int k_sigma_rows(cudaStream_t st, const Dev& d);                 // diag_var: zetaVec, sigmaVecHat, mean
 int k_scale_B(cudaStream_t st, const Dev& d);                    // Bs = diag(sigmaVecHat) * BHat
 int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta);   // CA/CB/sigma/prior updates (+ delta, loop control)
