@@ -33,6 +33,8 @@ WORKLOADS = {
            "configs[2]: synthetic dense Y 20000x200000, rank-32 signal + 0.1 noise, vbmf H=64 with ARD (est_covs, est_var), Float64"),
     # diagnostic only: the per-GPU shard of c3 at 8 GPUs on ONE GPU (no exchange), to separate kernel time from exchange time
     "c3shard8": (20000, 25000, 64, "dense", ("est_covs", "est_var"), "diagnostic: one 25000-column shard of configs[2] (what each of 8 GPUs computes)"),
+    # diagnostic only: a quarter of c3's columns; on 2 GPUs every rank holds the 25000-column shard of the 8-GPU run, exchange included
+    "c3quarter": (20000, 50000, 64, "dense", ("est_covs", "est_var"), "diagnostic: 50000 columns of configs[2] (25000 per GPU on 2 GPUs)"),
     "c4": (10000, 100000, 32, "sparse", ("est_cb",), "configs[3] (diagonal covariance path): vbmf_sparse 10000x100000 H=32"),
     "c4full": (10000, 100000, 32, "sparse", ("est_cb", "full_cov"), "configs[3]: vbmf_sparse 10000x100000 H=32 full_cov (batched per-row Cholesky)"),
     # configs[4] needs >= 4 GPUs at full size (Y = 400 GB); per SURVEY 8(d) fewer GPUs run M = 125000 columns per GPU
@@ -486,7 +488,10 @@ def main():
                 "iteration_frac_of_peak": 4.0 * L * M * H / (ms / args.steps * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
                 "contraction_share_of_step": (k1 + k2) / (ms / args.steps),
                 # the per-iteration packed all-reduce (N > 1), CUDA events on the launching stream of rank 0
-                "allreduce_ms": (prof["allreduce_ms"] / prof["allreduce_launches"]) if prof.get("allreduce_launches") else None}
+                "allreduce_ms": (prof["allreduce_ms"] / prof["allreduce_launches"]) if prof.get("allreduce_launches") else None,
+                # CUDA events between the launches of one iteration on the main stream (mean over the timed iterations, this rank)
+                "segments_ms": {k: round(v, 5) for k, v in prof.get("segments_ms", {}).items()},
+                "peer_exchange": bool(ctx.peer_exchange())}
 
     # ---- e2e: the public API with every input in pinned host memory (upload Y + params, K iterations, download)
     e2e = None

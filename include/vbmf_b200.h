@@ -211,6 +211,10 @@ int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_s
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
 int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* ctx, double* allreduce_ms, int64_t* allreduce_launches);
+/* Where an iteration's time goes on the main stream while profiling is on (CUDA events between the launches): ms[t] / n[t] =
+ * total time / count of segment t = 1 K1, 2 A epilogue (+updateCA!), 3 K2, 4 split-K reduction of Y*AHat, 5 exchange between
+ * the shards, 6 SigmaB, 7 BHat epilogue, 8 Gram reduction.  Returns the number of segments (cap >= that), -1 on error. */
+int vbmf_b200_ctx_profile_read_segments(vbmf_b200_ctx* ctx, double* ms, int64_t* n, int cap);
 /* 1 when this context's updateB! exchange (src/vbmf.jl:109-113 across column shards) runs through peer-mapped memory over
  * NVLink with the library's own kernels (world 2..8 on one node, H <= 64, decided when the first solver is created; switched
  * off with VBMF_B200_NO_PX=1), 0 when it uses the NCCL all-reduce.  (none in the reference: it is one process on one host) */

@@ -160,8 +160,12 @@ class Context:
         L_.check(self.lib.vbmf_b200_ctx_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         ar, nar = C.c_double(), C.c_int64()
         L_.check(self.lib.vbmf_b200_ctx_profile_read_allreduce(self.h, C.byref(ar), C.byref(nar)))
+        seg_ms, seg_n = (C.c_double * 16)(), (C.c_int64 * 16)()
+        nseg = self.lib.vbmf_b200_ctx_profile_read_segments(self.h, seg_ms, seg_n, 16)
+        names = ["start", "k1", "a_epilogue", "k2", "reduce_q", "exchange", "sigma_b", "b_epilogue", "b_reduce"]
+        segs = {names[i]: seg_ms[i] / seg_n[i] for i in range(1, min(max(nseg, 0), len(names))) if seg_n[i] > 0}
         return {"k1_ms": a.value, "k1_launches": na.value, "k2_ms": b.value, "k2_launches": nb.value,
-                "allreduce_ms": ar.value, "allreduce_launches": nar.value}
+                "allreduce_ms": ar.value, "allreduce_launches": nar.value, "segments_ms": segs}
 
 
 class MultiContext:

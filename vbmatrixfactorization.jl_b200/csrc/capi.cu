@@ -108,6 +108,7 @@ struct vbmf_b200_ctx {
     // profiling of the two contractions
     bool profile = false;
     std::vector<cudaEvent_t> ev_k1, ev_k2, ev_ar;      // K1, K2 and (world > 1) the per-iteration all-reduce
+    std::vector<std::pair<int, cudaEvent_t>> ev_seg;   // (segment tag, event at the segment's end): where an iteration's time goes
     // peer exchange (kernels.cuh, PxDev): this rank's peer-visible buffer and the peers' buffers as mapped into this device
     struct Px {
         bool ok = false, failed = false, claimed = false;
@@ -341,6 +342,7 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
     for (auto e : c->ev_ar) cudaEventDestroy(e);
+    for (auto& e : c->ev_seg) cudaEventDestroy(e.second);
     for (auto e : c->ev_chunk) cudaEventDestroy(e);
     if (c->ev_stats) cudaEventDestroy(c->ev_stats);
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
@@ -589,7 +591,8 @@ extern "C" int vbmf_b200_ctx_profile(vbmf_b200_ctx* c, int enable) {
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
     for (auto e : c->ev_ar) cudaEventDestroy(e);
-    c->ev_k1.clear(); c->ev_k2.clear(); c->ev_ar.clear();
+    for (auto& e : c->ev_seg) cudaEventDestroy(e.second);
+    c->ev_k1.clear(); c->ev_k2.clear(); c->ev_ar.clear(); c->ev_seg.clear();
     return 0;
 }
 // CUDA-event time of the per-iteration all-reduce launches (world > 1; zero launches otherwise)
@@ -608,6 +611,26 @@ extern "C" int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* c, double* k1_ms, int64
     for (size_t i = 0; i + 1 < c->ev_k2.size(); i += 2) { float ms = 0; VB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev_k2[i], c->ev_k2[i + 1])); t2 += ms; }
     *k1_ms = t1; *k1_n = (int64_t)(c->ev_k1.size() / 2); *k2_ms = t2; *k2_n = (int64_t)(c->ev_k2.size() / 2);
     return 0;
+}
+// Segment marks of one iteration on the main stream (profiling only): the time since the previous mark is booked on `tag`.
+enum { SEG_START = 0, SEG_K1, SEG_A_EPI, SEG_K2, SEG_REDUCE_Q, SEG_EXCHANGE, SEG_SIGMA_B, SEG_B_EPI, SEG_B_REDUCE, SEG_COUNT };
+static void prof_seg(vbmf_b200_ctx* c, int tag) {
+    if (!c->profile) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, c->st); c->ev_seg.emplace_back(tag, e); }
+}
+extern "C" int vbmf_b200_ctx_profile_read_segments(vbmf_b200_ctx* c, double* ms, int64_t* n, int cap) {
+    if (!c || !ms || !n) { set_error("NULL argument"); return -1; }
+    VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < cap; ++i) { ms[i] = 0.0; n[i] = 0; }
+    for (size_t i = 1; i < c->ev_seg.size(); ++i) {
+        const int tag = c->ev_seg[i].first;
+        if (tag == SEG_START || tag >= cap) continue;
+        float t = 0;
+        VB_CUDA_OK(cudaEventElapsedTime(&t, c->ev_seg[i - 1].second, c->ev_seg[i].second));
+        ms[tag] += t; n[tag] += 1;
+    }
+    return SEG_COUNT;
 }
 static void prof_mark(vbmf_b200_ctx* c, std::vector<cudaEvent_t>& v) {
     if (!c->profile) return;
@@ -633,6 +656,7 @@ struct vbmf_b200_solver {
     // host-side validity of derived quantities (every enqueued kernel either runs or is skipped as a whole iteration)
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
+    int ata_parts = 0;        // > 0: ... as soon as that many Gram partials in d.part are summed (deferred to the side stream, beside K2)
     bool ca_done = false;     // the fused diagonal A pass already did updateCA! of this iteration
     bool loop_ahead = false;      // set by solver_run while it enqueues whole iterations back to back
     bool sigmaA_ahead = false;    // dense loop: the NEXT iteration's SigmaA was already inverted on the side stream (behind post)
@@ -652,7 +676,8 @@ struct vbmf_b200_solver {
     int gexec_flags = -1;
     // peer exchange: packed / BHat / rank partials live in the context's peer-visible buffer at these byte offsets
     bool px = false;
-    size_t px_packed = 0, px_B = 0, px_gpart = 0;
+    size_t px_packed = 0, px_B = 0, px_gpart = 0, px_small = 0;
+    cudaEvent_t ev_a = nullptr, ev_sb = nullptr;   // A side of the iteration done (main) -> small exchange + SigmaB (side) -> epilogue (main)
     Scalars h_sc;
 };
 
@@ -714,7 +739,8 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
         s->px_packed = PX_FLAG_BYTES;
         s->px_B = s->px_packed + align_up((LH + 2 * HH + 8) * 8, 256);
         s->px_gpart = s->px_B + align_up(LH * 8, 256);
-        const size_t px_end = s->px_gpart + align_up((size_t)PX_MAX_WORLD * (2 * HH + 1) * 8, 256);
+        s->px_small = s->px_gpart + align_up((size_t)PX_MAX_WORLD * (2 * HH + 1) * 8, 256);
+        const size_t px_end = s->px_small + align_up((2 * HH + 8) * 8, 256);
         if (px_setup(c, px_end - PX_FLAG_BYTES)) { delete s; return -1; }
         if (c->px.ok && !c->px.claimed) {
             s->px = true; c->px.claimed = true;
@@ -780,7 +806,9 @@ static int solver_create_impl(vbmf_b200_ctx* c, int kind, int64_t H, int64_t h_s
         cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_p, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s->ev_p, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_sb, cudaEventDisableTiming) != cudaSuccess) {
         set_error("pinned flag / event allocation failed"); cudaFree(s->arena); if (s->px) c->px.claimed = false; delete s; return -1;
     }
     memset(&s->h_sc, 0, sizeof(Scalars));
@@ -806,6 +834,8 @@ extern "C" int vbmf_b200_solver_destroy(vbmf_b200_solver* s) {
     if (s->gexec) cudaGraphExecDestroy(s->gexec);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
     if (s->ev_p) cudaEventDestroy(s->ev_p);
+    if (s->ev_a) cudaEventDestroy(s->ev_a);
+    if (s->ev_sb) cudaEventDestroy(s->ev_sb);
     if (s->arena) cudaFree(s->arena);
     if (s->Qc) cudaFree(s->Qc);
     if (s->h_flag) cudaFreeHost(s->h_flag);
@@ -1077,6 +1107,7 @@ static int enq_k1(vbmf_b200_solver* s, bool scaledB, bool reduce_slabs = true) {
         if (!rc && s->S1 > 1 && reduce_slabs) rc = k_sum_slabs(c->st, s->Ppart, s->S1, MH, d.P, d.sc);
     }
     prof_mark(c, c->ev_k1);
+    prof_seg(c, SEG_K1);
     return rc;
 }
 static int enq_k2(vbmf_b200_solver* s) {
@@ -1090,9 +1121,12 @@ static int enq_k2(vbmf_b200_solver* s) {
     else if (s->k2_sk) rc = launch_gemm_ya_sk(c->st, &c->tmY2, &s->tmA, s->Qpart, d.packed + packed_q(d), d.L, d.Mloc, d.H, d.ldB, s->sk_kq, s->sk_nk, s->sk_grid, d.sc);
     else rc = launch_gemm_ya(c->st, &c->tmY2, &s->tmA, s->Qpart, d.L, d.Mloc, d.H, d.ldB, s->kchunk, s->S, d.sc, c->num_sms);
     prof_mark(c, c->ev_k2);
+    prof_seg(c, SEG_K2);
     if (rc) return rc;
-    if (s->k2_sk) return launch_reduce_q_sk(c->st, s->Qpart, d.packed + packed_q(d), d.L, d.Mloc, d.H, d.ldB, s->sk_nk, s->sk_grid, d.sc);
-    return k_reduce_q(c->st, d, s->Qpart, s->S);
+    if (s->k2_sk) rc = launch_reduce_q_sk(c->st, s->Qpart, d.packed + packed_q(d), d.L, d.Mloc, d.H, d.ldB, s->sk_nk, s->sk_grid, d.sc);
+    else rc = k_reduce_q(c->st, d, s->Qpart, s->S);
+    prof_seg(c, SEG_REDUCE_Q);
+    return rc;
 }
 // Grams of the current BHat that the A update / CB / sigma need
 static int enq_gram_B(vbmf_b200_solver* s, int flags) {
@@ -1135,7 +1169,10 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
         if (!s->sigmaA_ahead && k_dense_sigmaA(st, d)) return -1;
         s->sigmaA_ahead = false;
         const bool slabs = !s->c->simt && s->S1 > 1;
-        if (k_dense_A_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H)) return -1;
+        if (fused && (s->px || s->c->world == 1) && d.Mloc > 0) {
+            // whole-loop run: the fixed-order sum of the Gram partials is only needed by SigmaB -> side stream (enq_updateB)
+            if (k_dense_A_fused_range(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, 0, d.Mloc, 0, 1 << 30, &s->ata_parts)) return -1;
+        } else if (k_dense_A_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H)) return -1;
         s->ata_local = true;
     } else {
         const bool dv = (flags & F_DIAG_VAR) != 0;
@@ -1206,28 +1243,49 @@ static PxDev px_view(vbmf_b200_solver* s, int nbar) {
         p.packed[r] = (double*)(base + s->px_packed);
         p.B[r] = (double*)(base + s->px_B);
         p.gpart[r] = (double*)(base + s->px_gpart);
+        p.small[r] = (double*)(base + s->px_small);
     }
     return p;
 }
 static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
     const Dev& d = s->d;
     cudaStream_t st = s->c->st;
-    if (fused && s->px && !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR))) {
-        // updateB! with the exchange done by our own kernels over NVLink: the small sums are gathered from the peers, SigmaB
+    const bool px = fused && s->px && !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR));
+    if (px || (fused && s->c->world == 1)) {
+        // px: updateB! with the exchange done by our own kernels over NVLink: the small sums are gathered from the peers, SigmaB
         // is inverted redundantly, every rank reduces its share of the rows of Y*AHat over the peers, runs the epilogue on
         // them and writes the new BHat rows to every peer; the Grams of BHat / BHat - Bold are exchanged as rank partials.
         // (The heteroscedastic row update needs all rows of the reduced Y*AHat on every rank: that case keeps the all-reduce.)
+        // One GPU: nothing to exchange.  Either way SigmaB needs the A side of the iteration only, so the Gram partial sum,
+        // the small exchange and the inverse run on the side stream beside K2 (their few CTAs share the SMs with K2's).
+        if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR) && !s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
         if (!s->ata_local && enq_gram_A(s)) return -1;
         s->ata_local = false;
+        VB_CUDA_OK(cudaEventRecord(s->ev_a, st));
+        VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_a, 0));
+        if (s->ata_parts > 0 && k_sum_gram_partials(s->side, d, s->ata_parts)) return -1;
+        s->ata_parts = 0;
+        if (px && k_px_small(s->side, d, px_view(s, 1))) return -1;
+        if (k_sigmaB(s->side, d, flags)) return -1;
+        VB_CUDA_OK(cudaEventRecord(s->ev_sb, s->side));
         if (enq_k2(s)) return -1;
-        prof_mark(s->c, s->c->ev_ar);
-        if (k_px_small(st, d, px_view(s, 2))) return -1;
-        if (k_sigmaB(st, d, flags)) return -1;
-        if (k_B_epilogue_px(st, d, flags, px_view(s, 1))) return -1;
-        prof_mark(s->c, s->c->ev_ar);
+        if (px) prof_mark(s->c, s->c->ev_ar);
+        VB_CUDA_OK(cudaStreamWaitEvent(st, s->ev_sb, 0));
+        prof_seg(s->c, SEG_SIGMA_B);
+        if (px) {
+            int nparts = 1;
+            if (k_B_epilogue_px(st, d, flags, px_view(s, 1), &nparts)) return -1;
+            prof_seg(s->c, SEG_B_EPI);
+            if (k_B_reduce_px(st, d, px_view(s, 1), nparts)) return -1;
+            prof_seg(s->c, SEG_B_REDUCE);
+            prof_mark(s->c, s->c->ev_ar);
+        } else {
+            if (k_B_epilogue(st, d, flags)) return -1;
+            prof_seg(s->c, SEG_B_EPI);
+        }
         s->ata_valid = true; s->extras_valid = true;
-        s->q_valid = false;                         // packed.Q is reduced on this rank's rows only
-        s->btb_valid = true;
+        s->q_valid = !px;                           // px: packed.Q is reduced on this rank's rows only
+        s->btb_valid = !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR));           // weighted Grams / Bs still stale with diag_var
         return 0;
     }
     if (!fused && d.kind != KIND_DENSE) {
@@ -1236,7 +1294,11 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
     }
     if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR) && !s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
     if (enq_q_ata(s, fused)) return -1;
-    if (k_sigmaB(st, d, flags) || k_B_epilogue(st, d, flags)) return -1;     // also BtB, DtD, tr(B'Q) of the new BHat
+    prof_seg(s->c, SEG_EXCHANGE);
+    if (k_sigmaB(st, d, flags)) return -1;
+    prof_seg(s->c, SEG_SIGMA_B);
+    if (k_B_epilogue(st, d, flags)) return -1;     // also BtB, DtD, tr(B'Q) of the new BHat
+    prof_seg(s->c, SEG_B_EPI);
     s->btb_valid = !(d.kind != KIND_DENSE && (flags & F_DIAG_VAR));           // weighted Grams / Bs still stale with diag_var
     return 0;
 }
@@ -1309,9 +1371,11 @@ extern "C" int vbmf_b200_solver_step(vbmf_b200_solver* s, int step, int flags) {
 static int enq_iteration(vbmf_b200_solver* s, int flags) {
     const Dev& d = s->d;
     cudaStream_t st = s->c->st;
+    prof_seg(s->c, SEG_START);
     if (enq_updateA(s, flags, true)) return -1;                       // updateA!
     if (d.kind != KIND_DENSE && !s->ca_done && enq_updateCA(s, flags, true)) return -1;   // updateCA! (local; hoisted before the all-reduce)
     s->ca_done = false;
+    prof_seg(s->c, SEG_A_EPI);
     if (enq_updateB(s, flags, true)) return -1;                       // updateB! (+ Grams of BHat and of BHat - Bold)
     if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR)) {
         if (k_sigma_rows(st, d)) return -1;                           // updateSigma! (per-row)

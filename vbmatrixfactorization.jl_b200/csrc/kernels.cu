@@ -1471,6 +1471,28 @@ int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
     return sum_partials(st, Qpart, S, n, n, d.packed + packed_q(d), d.sc);
 }
 
+// ---- peer exchange: barrier between the CTAs with the same index b on all ranks.  Slot (b, src) of a rank's flag array is
+// written by rank src only and only grows, so `>= epoch` needs no reset.  The release / acquire pair at system scope orders
+// this CTA's earlier peer stores (and, through the kernel boundary, everything the stream ran before) ahead of the peers'
+// later loads.  A peer that never arrives (a rank that failed on the host) ends the wait after ~30 s with the sticky error
+// flag set instead of hanging the device.
+__device__ __forceinline__ void px_barrier(const Dev& d, const PxDev& px, int b, unsigned long long ep) {
+    __syncthreads();
+    if ((int)threadIdx.x < px.W) {
+        const int r = threadIdx.x;
+        unsigned long long* dst = px.flags[r] + (size_t)b * PX_MAX_WORLD + px.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(ep) : "memory");
+        const unsigned long long* src = px.flags[px.rank] + (size_t)b * PX_MAX_WORLD + r;
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if (v >= ep) break;
+            if (clock64() - t0 > 60000000000LL || (*(volatile int*)&d.sc->chol_fail & 4)) { atomicOr(&d.sc->chol_fail, 4); break; }
+        }
+    }
+    __syncthreads();
+}
 // ------------------------------------------------------------------------------------------- B epilogue
 __global__ void trbq_kernel(Dev d, int nparts);
 // dense : BHat = ((Y*AHat)*SigmaB)/sigma2                       src/vbmf.jl:112
@@ -1585,6 +1607,7 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
     }
     const bool dense = d.kind == KIND_DENSE;
     const double s2 = sc->sigma2, sh = sc->sigmaHat;
+    if (PX) px_barrier(d, px, blockIdx.x, px.epoch + 1);        // every peer's local Y*AHat (split-K reduction) is complete
     constexpr int NTW = TPW == 2 ? 2 : (TPW == 8 ? 4 : 8);      // product column tiles per warp: ceil(nt8 / 2)
     constexpr int GT = GRAM ? (TPW == 2 ? 2 : 5) : 1;           // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
     double gB[GT][2], gD[GT][2];
@@ -1601,23 +1624,45 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
     for (int tile = (PX ? tile_lo : 0) + blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int l0 = tile * 32, nr = min(32, d.L - l0);
         __syncthreads();
-        for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
-            const int h = e >> 5, i = e & 31;
-            double q = 0.0;
-            if (i < nr && h < H) {
-                const size_t g = (size_t)h * d.ldB + l0 + i;
-                if (PX) {
-                    double v[PX_MAX_WORLD];
+        if (PX) {
+            // all remote loads of four elements are issued before the first sum is stored (the in-place store would otherwise
+            // order every element's round trip behind the previous one)
+            constexpr int CH = 4;
+            for (int e0 = threadIdx.x; e0 < 32 * HP8; e0 += 256 * CH) {
+                double v[CH][PX_MAX_WORLD];
 #pragma unroll
-                    for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[rk] = rk < px.W ? __ldcg(px.packed[rk] + g) : 0.0;   // L2 only: peer data
-                    q = v[0];
+                for (int c = 0; c < CH; ++c) {
+                    const int e = e0 + 256 * c, h = e >> 5, i = e & 31;
+                    const bool ok = e < 32 * HP8 && i < nr && h < H;
+                    const size_t g = (size_t)h * d.ldB + l0 + i;
 #pragma unroll
-                    for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) q += v[rk];
-                    Q[g] = q;
-                } else q = Q[g];
-                if (!dense) q *= diag_var ? d.sigmaVec[l0 + i] : sh;
+                    for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[c][rk] = (ok && rk < px.W) ? __ldcg(px.packed[rk] + g) : 0.0;   // L2 only: peer data
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int e = e0 + 256 * c, h = e >> 5, i = e & 31;
+                    if (e < 32 * HP8) {
+                        double q = v[c][0];
+#pragma unroll
+                        for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) q += v[c][rk];
+                        if (i < nr && h < H) {
+                            Q[(size_t)h * d.ldB + l0 + i] = q;
+                            if (!dense) q *= sh;
+                        } else q = 0.0;
+                        T[i * ld + h] = q;
+                    }
+                }
             }
-            T[i * ld + h] = q;
+        } else {
+            for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
+                const int h = e >> 5, i = e & 31;
+                double q = 0.0;
+                if (i < nr && h < H) {
+                    q = Q[(size_t)h * d.ldB + l0 + i];
+                    if (!dense) q *= diag_var ? d.sigmaVec[l0 + i] : sh;
+                }
+                T[i * ld + h] = q;
+            }
         }
         __syncthreads();
         {   // warp -> row tile (warp & 3), column tiles (warp >> 2) + 2u with one independent accumulator each
@@ -1634,6 +1679,18 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
                     if (nt < nt8) dmma_acc(c2[u], af, Ss[(k0 + j) * ld + 8 * nt + r]);
                 }
             }
+            // the previous BHat entries first, all in flight together and past L1 (a store to an address whose load is still
+            // pending stalls the memory pipe: measured 0.055 -> 0.17 ms at 20000 x 64 when the store followed its load directly)
+            double oldv[NTW][2];
+#pragma unroll
+            for (int u = 0; u < NTW; ++u) {
+                const int nt = (warp >> 2) + 2 * u;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int col = 8 * nt + 2 * j + i;
+                    oldv[u][i] = (nt < nt8 && row < nr && col < H) ? __ldcg(d.B + (size_t)col * d.ldB + l0 + row) : 0.0;
+                }
+            }
 #pragma unroll
             for (int u = 0; u < NTW; ++u) {
                 const int nt = (warp >> 2) + 2 * u;
@@ -1646,10 +1703,8 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
                             double v = c2[u][i];
                             if (dense) v /= s2;
                             const size_t g = (size_t)col * d.ldB + l0 + row;
-                            const double old = d.B[g];
-                            d.Bold[g] = old;
-                            dn = v - old;
-                            d.D[g] = dn;
+                            dn = v - oldv[u][i];
+                            if (!GRAM) d.D[g] = dn;              // H > 64: gram_dmma forms D'D from it (with GRAM nobody reads D)
                             if (PX) {
 #pragma unroll
                                 for (int rk = 0; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) px.B[rk][g] = v;
@@ -1701,48 +1756,25 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         if (threadIdx.x == 0) d.part[blockIdx.x] = tr;         // Grams follow from gram_dmma on B and D
     }
 }
-// ---- peer exchange: barrier between the CTAs with the same index b on all ranks.  Slot (b, src) of a rank's flag array is
-// written by rank src only and only grows, so `>= epoch` needs no reset.  The release / acquire pair at system scope orders
-// this CTA's earlier peer stores (and, through the kernel boundary, everything the stream ran before) ahead of the peers'
-// later loads.  A peer that never arrives (a rank that failed on the host) ends the wait after ~30 s with the sticky error
-// flag set instead of hanging the device.
-__device__ __forceinline__ void px_barrier(const Dev& d, const PxDev& px, int b, unsigned long long ep) {
-    __syncthreads();
-    if ((int)threadIdx.x < px.W) {
-        const int r = threadIdx.x;
-        unsigned long long* dst = px.flags[r] + (size_t)b * PX_MAX_WORLD + px.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(ep) : "memory");
-        const unsigned long long* src = px.flags[px.rank] + (size_t)b * PX_MAX_WORLD + r;
-        const long long t0 = clock64();
-        unsigned long long v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
-            if (v >= ep) break;
-            if (clock64() - t0 > 60000000000LL || (*(volatile int*)&d.sc->chol_fail & 4)) { atomicOr(&d.sc->chol_fail, 4); break; }
-        }
-    }
-    __syncthreads();
-}
-// Global A'A | sum of Sigma blocks | group sums on every rank: barrier (all peers' local parts are final), sum over the
-// peers in rank order into registers, barrier (everybody has read), store in place.  CTA b handles the same elements on
-// every rank, so the per-CTA barriers are enough.
+// Global A'A | sum of Sigma blocks | group sums on every rank: the local part goes into this rank's send slot, barrier, sum of
+// the peers' slots in rank order, stored in place (peers read the slot, never `packed`).  The slot is rewritten one iteration
+// later, behind the Gram-reduction barrier that every peer passes only after it has left this kernel.
 __global__ void __launch_bounds__(256) px_small_kernel(Dev d, PxDev px) {
     ACTIVE_OR_RETURN(d);
     const size_t off = packed_ata(d);
     const int n = 2 * d.H * d.H + 8;
     const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < n) px.small[px.rank][e] = d.packed[off + e];
     px_barrier(d, px, blockIdx.x, px.epoch + 1);
-    double acc = 0.0;
     if (e < n) {
         double v[PX_MAX_WORLD];
 #pragma unroll
-        for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[rk] = rk < px.W ? __ldcg(px.packed[rk] + off + e) : 0.0;
-        acc = v[0];
+        for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[rk] = rk < px.W ? __ldcg(px.small[rk] + e) : 0.0;
+        double acc = v[0];
 #pragma unroll
         for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) acc += v[rk];
+        d.packed[off + e] = acc;
     }
-    px_barrier(d, px, blockIdx.x, px.epoch + 2);
-    if (e < n) d.packed[off + e] = acc;
 }
 int k_px_small(cudaStream_t st, const Dev& d, const PxDev& px) {
     const int grid = cdiv(2 * d.H * d.H + 8, 256);
@@ -1831,18 +1863,22 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     return 0;
 }
 // updateB!'s epilogue on this rank's share of the rows (peer exchange, H <= 64, homoscedastic noise)
-int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px) {
+int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px, int* nparts) {
     const int H = d.H, HP8 = (H + 7) & ~7;
     if (H > 64 || (flags & F_DIAG_VAR)) { set_error("peer-exchange epilogue: H <= 64 and homoscedastic noise only"); return -1; }
     const int ntiles = cdiv(d.L, 32);
     const int lo = (int)((long long)ntiles * px.rank / px.W), hi = (int)((long long)ntiles * (px.rank + 1) / px.W);
     const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
-    const int grid2 = std::max(1, std::min(hi - lo, 296));
+    // the same grid on every rank (CTA b meets CTA b of the peers at the barrier); a CTA without a tile writes a zero partial
+    const int grid2 = std::max(1, std::min(cdiv(ntiles, px.W), 296));
     if (HP8 <= 32) B_epilogue_dmma_kernel<2, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
     else B_epilogue_dmma_kernel<8, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
     VB_LAUNCH_OK();
-    PxDev px2 = px;
-    B_reduce_kernel<true><<<std::max(1, cdiv(2 * H * H + 1, 32)), 256, 0, st>>>(d, grid2, px2);
+    *nparts = grid2;
+    return 0;
+}
+int k_B_reduce_px(cudaStream_t st, const Dev& d, const PxDev& px, int nparts) {
+    B_reduce_kernel<true><<<std::max(1, cdiv(2 * d.H * d.H + 1, 32)), 256, 0, st>>>(d, nparts, px);
     VB_LAUNCH_OK();
     return 0;
 }

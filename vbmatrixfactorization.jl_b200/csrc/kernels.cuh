@@ -62,6 +62,7 @@ struct PxDev {
     double* packed[PX_MAX_WORLD];                  // all-reduce payload of every rank (same layout as Dev::packed)
     double* B[PX_MAX_WORLD];                       // BHat of every rank
     double* gpart[PX_MAX_WORLD];                   // [W][2*H*H + 1]: slot r holds rank r's partial BtB | DtD | tr(B.*Q)
+    double* small[PX_MAX_WORLD];                   // [2*H*H + 8]: every rank's local A'A | Sigma sums | group sums (send slot)
 };
 
 // flags shared by steps
@@ -101,11 +102,13 @@ int k_sum_slabs(cudaStream_t st, const double* slabs, int S, size_t n, double* o
 int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S);   // fixed-order split-K reduction -> packed.Q
 int k_sigmaB(cudaStream_t st, const Dev& d, int flags);          // SigmaB (dense / sparse), also SigmaA <- packed.SA (sparse)
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags);      // BHat, Bold, D, partial tr(B.*Q)
-// peer exchange (world > 1): global A'A / Sigma sums / group sums on every rank (two barriers, uses epochs +1, +2) ...
+// peer exchange (world > 1), one barrier (epoch + 1) each:
+// global A'A / Sigma sums / group sums on every rank (needs only the A side of the iteration: runs beside K2) ...
 int k_px_small(cudaStream_t st, const Dev& d, const PxDev& px);
-// ... and the BHat epilogue on this rank's rows: Q rows summed over the peers, BHat rows written to every peer, rank partials
-// of the Grams exchanged and summed in rank order (one barrier, epoch +1).  H <= 64 only.
-int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px);
+// ... the BHat epilogue on this rank's rows: Q rows summed over the peers, BHat rows written to every peer ...
+// ... and the rank partials of the Grams exchanged and summed in rank order.  H <= 64 only.
+int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px, int* nparts);
+int k_B_reduce_px(cudaStream_t st, const Dev& d, const PxDev& px, int nparts);
 int k_sigma_rows(cudaStream_t st, const Dev& d);                 // diag_var: zetaVec, sigmaVecHat, mean
 int k_scale_B(cudaStream_t st, const Dev& d);                    // Bs = diag(sigmaVecHat) * BHat
 int k_post(cudaStream_t st, const Dev& d, int flags, bool with_delta);   // CA/CB/sigma/prior updates (+ delta, loop control)
