@@ -327,6 +327,8 @@ def main():
                     help="drive --gpus N devices from THIS process through the multi-device context (vbmf_b200_mctx_*), the path a "
                          "one-process Julia caller uses; no torchrun")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--segments", action="store_true",
+                    help="diagnosis: CUDA events between the launches of every iteration (adds stream bubbles; not for headline numbers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.workload == "c2":
@@ -416,7 +418,7 @@ def main():
     sampler.start()
     time.sleep(0.15)
     barrier()
-    ctx.profile(True)
+    ctx.profile(True, segments=args.segments)
     n0 = lib.vbmf_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()

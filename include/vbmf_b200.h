@@ -208,12 +208,16 @@ int64_t vbmf_b200_launch_count(void);
  * count over M_local, out[3] = columns per K2 split (multiple of 16), out[4] = CTAs per SM, out[5] = tile width BN.
  * (none in the reference: src/vbmf.jl:98,112 are single BLAS calls) */
 int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_sms, int64_t* out6);
+/* enable: 0 off, 1 time the K1 / K2 launches and the exchange, 3 also mark the segments of every iteration (a few more event
+ * records on the stream: use it for diagnosis, not for headline numbers) */
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
 int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* ctx, double* allreduce_ms, int64_t* allreduce_launches);
 /* Where an iteration's time goes on the main stream while profiling is on (CUDA events between the launches): ms[t] / n[t] =
  * total time / count of segment t = 1 K1, 2 A epilogue (+updateCA!), 3 K2, 4 split-K reduction of Y*AHat, 5 exchange between
- * the shards, 6 SigmaB, 7 BHat epilogue, 8 Gram reduction.  Returns the number of segments (cap >= that), -1 on error. */
+ * the shards, 6 SigmaB, 7 BHat epilogue, 8 Gram reduction; 9..11 = mean time (ms) CTA 0 waited at the three peer-exchange
+ * barriers (small sums, epilogue, Gram reduction), 12..20 = phases of CTA 0 in the last exchange-epilogue / Gram-reduction
+ * launch.  Returns the number of segments (cap >= that; 32 is enough), -1 on error. */
 int vbmf_b200_ctx_profile_read_segments(vbmf_b200_ctx* ctx, double* ms, int64_t* n, int cap);
 /* 1 when this context's updateB! exchange (src/vbmf.jl:109-113 across column shards) runs through peer-mapped memory over
  * NVLink with the library's own kernels (world 2..8 on one node, H <= 64, decided when the first solver is created; switched

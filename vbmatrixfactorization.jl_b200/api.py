@@ -151,8 +151,8 @@ class Context:
         """True when updateB!'s exchange between the column shards runs through peer-mapped memory (own kernels over NVLink)."""
         return bool(self.lib.vbmf_b200_ctx_peer_exchange(self.h))
 
-    def profile(self, enable=True):
-        L_.check(self.lib.vbmf_b200_ctx_profile(self.h, 1 if enable else 0))
+    def profile(self, enable=True, segments=False):
+        L_.check(self.lib.vbmf_b200_ctx_profile(self.h, (3 if segments else 1) if enable else 0))
 
     def profile_read(self):
         a, b = C.c_double(), C.c_double()
@@ -160,9 +160,11 @@ class Context:
         L_.check(self.lib.vbmf_b200_ctx_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         ar, nar = C.c_double(), C.c_int64()
         L_.check(self.lib.vbmf_b200_ctx_profile_read_allreduce(self.h, C.byref(ar), C.byref(nar)))
-        seg_ms, seg_n = (C.c_double * 16)(), (C.c_int64 * 16)()
-        nseg = self.lib.vbmf_b200_ctx_profile_read_segments(self.h, seg_ms, seg_n, 16)
-        names = ["start", "k1", "a_epilogue", "k2", "reduce_q", "exchange", "sigma_b", "b_epilogue", "b_reduce"]
+        seg_ms, seg_n = (C.c_double * 32)(), (C.c_int64 * 32)()
+        nseg = self.lib.vbmf_b200_ctx_profile_read_segments(self.h, seg_ms, seg_n, 32)
+        names = ["start", "k1", "a_epilogue", "k2", "reduce_q", "exchange", "sigma_b", "b_epilogue", "b_reduce",
+                 "wait_small", "wait_epilogue", "wait_reduce", "epi_fill", "epi_barrier", "epi_load", "epi_product", "epi_gram",
+                 "epi_out", "red_local", "red_barrier", "red_final"]
         segs = {names[i]: seg_ms[i] / seg_n[i] for i in range(1, min(max(nseg, 0), len(names))) if seg_n[i] > 0}
         return {"k1_ms": a.value, "k1_launches": na.value, "k2_ms": b.value, "k2_launches": nb.value,
                 "allreduce_ms": ar.value, "allreduce_launches": nar.value, "segments_ms": segs}

@@ -118,7 +118,9 @@ struct vbmf_b200_ctx {
         bool ipc[PX_MAX_WORLD] = {};
         char* xchg = nullptr;             // device staging of the handle exchange
         unsigned long long epoch = 0;     // barrier epochs consumed so far (identical on every rank)
+        unsigned long long* wait_ns = nullptr;   // device [3][2]: barrier wait of CTA 0 per site (profiling with segments only)
     } px;
+    bool profile_segments = false;        // vbmf_b200_ctx_profile(ctx, 3): also mark the segments of every iteration (adds event records)
     // grow-only staging for the batched small-problem path (device arena + pinned host mirror, same offsets)
     char* batch_dev = nullptr;
     char* batch_host = nullptr;
@@ -337,6 +339,7 @@ extern "C" int vbmf_b200_ctx_destroy(vbmf_b200_ctx* c) {
     ctx_free_Y(c);
     if (c->d_tr) cudaFree(c->d_tr);
     px_release(c);
+    if (c->px.wait_ns) cudaFree(c->px.wait_ns);
     if (c->batch_dev) cudaFree(c->batch_dev);
     if (c->batch_host) cudaFreeHost(c->batch_host);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
@@ -587,7 +590,13 @@ extern "C" int vbmf_b200_trYTY(vbmf_b200_ctx* c, double* out) {
 }
 
 extern "C" int vbmf_b200_ctx_profile(vbmf_b200_ctx* c, int enable) {
-    c->profile = enable != 0;
+    c->profile = (enable & 1) != 0;
+    c->profile_segments = c->profile && (enable & 2) != 0;
+    if (c->profile_segments && c->px.wait_ns == nullptr) {
+        VB_CUDA_OK(cudaSetDevice(c->device));
+        if (cudaMalloc(&c->px.wait_ns, 256) != cudaSuccess) { cudaGetLastError(); c->px.wait_ns = nullptr; }
+    }
+    if (c->px.wait_ns) cudaMemsetAsync(c->px.wait_ns, 0, 256, c->st);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
     for (auto e : c->ev_k2) cudaEventDestroy(e);
     for (auto e : c->ev_ar) cudaEventDestroy(e);
@@ -613,9 +622,11 @@ extern "C" int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* c, double* k1_ms, int64
     return 0;
 }
 // Segment marks of one iteration on the main stream (profiling only): the time since the previous mark is booked on `tag`.
-enum { SEG_START = 0, SEG_K1, SEG_A_EPI, SEG_K2, SEG_REDUCE_Q, SEG_EXCHANGE, SEG_SIGMA_B, SEG_B_EPI, SEG_B_REDUCE, SEG_COUNT };
+enum { SEG_START = 0, SEG_K1, SEG_A_EPI, SEG_K2, SEG_REDUCE_Q, SEG_EXCHANGE, SEG_SIGMA_B, SEG_B_EPI, SEG_B_REDUCE,
+       SEG_WAIT_SMALL, SEG_WAIT_EPI, SEG_WAIT_REDUCE,                // mean barrier wait of CTA 0 (peer exchange)
+       SEG_PH0, SEG_COUNT = SEG_PH0 + 9 };                           // phases of CTA 0 in the last epilogue / Gram reduction launch
 static void prof_seg(vbmf_b200_ctx* c, int tag) {
-    if (!c->profile) return;
+    if (!c->profile_segments) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, c->st); c->ev_seg.emplace_back(tag, e); }
 }
@@ -629,6 +640,16 @@ extern "C" int vbmf_b200_ctx_profile_read_segments(vbmf_b200_ctx* c, double* ms,
         float t = 0;
         VB_CUDA_OK(cudaEventElapsedTime(&t, c->ev_seg[i - 1].second, c->ev_seg[i].second));
         ms[tag] += t; n[tag] += 1;
+    }
+    if (c->px.wait_ns != nullptr && cap >= SEG_COUNT) {
+        unsigned long long w[6] = {0, 0, 0, 0, 0, 0};
+        VB_CUDA_OK(cudaMemcpy(w, c->px.wait_ns, sizeof(w), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) { ms[SEG_WAIT_SMALL + k] = (double)w[2 * k] * 1e-6; n[SEG_WAIT_SMALL + k] = (int64_t)w[2 * k + 1]; }
+        unsigned long long ph[12];
+        VB_CUDA_OK(cudaMemcpy(ph, c->px.wait_ns + 8, sizeof(ph), cudaMemcpyDeviceToHost));
+        // epilogue: SigmaB fill, barrier, Q loads, product + stores, Gram, partial out; reduction: local sum, push + barrier, final
+        const int from[9] = {0, 1, 2, 3, 4, 5, 8, 9, 10}, to[9] = {1, 2, 3, 4, 5, 6, 9, 10, 11};
+        for (int k = 0; k < 9; ++k) if (ph[to[k]] >= ph[from[k]] && ph[from[k]] != 0) { ms[SEG_PH0 + k] = (double)(ph[to[k]] - ph[from[k]]) * 1e-6; n[SEG_PH0 + k] = 1; }
     }
     return SEG_COUNT;
 }
@@ -1231,10 +1252,12 @@ static int enq_q_ata(vbmf_b200_solver* s, bool fused) {
     return 0;
 }
 // the peers' regions of this solver as seen from this device; consumes `nbar` barrier epochs
-static PxDev px_view(vbmf_b200_solver* s, int nbar) {
+static PxDev px_view(vbmf_b200_solver* s, int nbar, int site) {
     vbmf_b200_ctx* c = s->c;
     PxDev p;
     memset(&p, 0, sizeof(p));
+    p.site = site;
+    p.wait_ns = c->profile_segments ? c->px.wait_ns : nullptr;
     p.rank = c->rank; p.W = c->world; p.epoch = c->px.epoch;
     c->px.epoch += (unsigned long long)nbar;
     for (int r = 0; r < c->world; ++r) {
@@ -1265,7 +1288,7 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
         VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_a, 0));
         if (s->ata_parts > 0 && k_sum_gram_partials(s->side, d, s->ata_parts)) return -1;
         s->ata_parts = 0;
-        if (px && k_px_small(s->side, d, px_view(s, 1))) return -1;
+        if (px && k_px_small(s->side, d, px_view(s, 1, 0))) return -1;
         if (k_sigmaB(s->side, d, flags)) return -1;
         VB_CUDA_OK(cudaEventRecord(s->ev_sb, s->side));
         if (enq_k2(s)) return -1;
@@ -1274,9 +1297,9 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
         prof_seg(s->c, SEG_SIGMA_B);
         if (px) {
             int nparts = 1;
-            if (k_B_epilogue_px(st, d, flags, px_view(s, 1), &nparts)) return -1;
+            if (k_B_epilogue_px(st, d, flags, px_view(s, 1, 1), &nparts)) return -1;
             prof_seg(s->c, SEG_B_EPI);
-            if (k_B_reduce_px(st, d, px_view(s, 1), nparts)) return -1;
+            if (k_B_reduce_px(st, d, px_view(s, 1, 2), nparts)) return -1;
             prof_seg(s->c, SEG_B_REDUCE);
             prof_mark(s->c, s->c->ev_ar);
         } else {

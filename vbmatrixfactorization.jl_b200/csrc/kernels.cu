@@ -1471,12 +1471,22 @@ int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S) {
     return sum_partials(st, Qpart, S, n, n, d.packed + packed_q(d), d.sc);
 }
 
+// profiling: CTA 0 stamps the phases of its last launch (absolute ns) behind the wait counters
+__device__ __forceinline__ void px_stamp(const PxDev& px, int slot) {
+    if (px.wait_ns != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+        px.wait_ns[8 + slot] = t;
+    }
+}
 // ---- peer exchange: barrier between the CTAs with the same index b on all ranks.  Slot (b, src) of a rank's flag array is
 // written by rank src only and only grows, so `>= epoch` needs no reset.  The release / acquire pair at system scope orders
 // this CTA's earlier peer stores (and, through the kernel boundary, everything the stream ran before) ahead of the peers'
 // later loads.  A peer that never arrives (a rank that failed on the host) ends the wait after ~30 s with the sticky error
 // flag set instead of hanging the device.
 __device__ __forceinline__ void px_barrier(const Dev& d, const PxDev& px, int b, unsigned long long ep) {
+    __shared__ unsigned long long px_wait_max;
+    if (threadIdx.x == 0) px_wait_max = 0;
     __syncthreads();
     if ((int)threadIdx.x < px.W) {
         const int r = threadIdx.x;
@@ -1484,14 +1494,22 @@ __device__ __forceinline__ void px_barrier(const Dev& d, const PxDev& px, int b,
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(ep) : "memory");
         const unsigned long long* src = px.flags[px.rank] + (size_t)b * PX_MAX_WORLD + r;
         const long long t0 = clock64();
-        unsigned long long v;
+        unsigned long long v, g0 = 0;
+        const bool timed = px.wait_ns != nullptr && b == 0;      // profiling: how long CTA 0 waits for its slowest peer
+        if (timed) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
             if (v >= ep) break;
             if (clock64() - t0 > 60000000000LL || (*(volatile int*)&d.sc->chol_fail & 4)) { atomicOr(&d.sc->chol_fail, 4); break; }
         }
+        if (timed) {
+            unsigned long long g1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+            atomicMax(&px_wait_max, g1 - g0);
+        }
     }
     __syncthreads();
+    if (px.wait_ns != nullptr && b == 0 && threadIdx.x == 0) { atomicAdd(px.wait_ns + 2 * px.site, px_wait_max); atomicAdd(px.wait_ns + 2 * px.site + 1, 1ULL); }
 }
 // ------------------------------------------------------------------------------------------- B epilogue
 __global__ void trbq_kernel(Dev d, int nparts);
@@ -1582,6 +1600,73 @@ __global__ void __launch_bounds__(TD * TD) B_epilogue_kernel(Dev d, int diag_var
     tr = block_sum(tr, red);
     if (threadIdx.x == 0) out[2 * H * H] = tr;
 }
+// ---- peer exchange: tile transfers of the row-sharded epilogue.  W is a template parameter and the rounds are real loops so
+// that the executed code stays small: a CTA runs this once or twice, and a fully unrolled, predicated 8-rank version spent
+// 24-32 us per tile fetching its own instructions (measured: the load phase took that long even with W = 1, all local).
+// A 32 x HP8 tile is HP8 * 16 row pairs (16-byte accesses, 256 contiguous bytes per column); two pairs per thread and round.
+template <int W>
+__device__ __forceinline__ void px_load_tile(const PxDev& px, double* __restrict__ Q, double* __restrict__ T, int ld, int ldB, int l0,
+                                             int nr, int H, int HP8, double scale) {
+    const int npairs = HP8 * 16;
+#pragma unroll 1
+    for (int p0 = threadIdx.x; p0 < npairs; p0 += 512) {
+        double2 v[2][W];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int p = p0 + 256 * c, h = p >> 4, i = 2 * (p & 15);
+            const bool ok = p < npairs && h < H && i < nr;
+            const size_t g = (size_t)h * ldB + l0 + i;
+#pragma unroll
+            for (int rk = 0; rk < W; ++rk) v[c][rk] = ok ? __ldcg(reinterpret_cast<const double2*>(px.packed[rk] + g)) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int p = p0 + 256 * c, h = p >> 4, i = 2 * (p & 15);
+            if (p < npairs) {
+                double2 q = v[c][0];
+#pragma unroll
+                for (int rk = 1; rk < W; ++rk) { q.x += v[c][rk].x; q.y += v[c][rk].y; }      // rank order
+                if (!(h < H && i < nr)) q = make_double2(0.0, 0.0);
+                else {
+                    if (i + 1 >= nr) q.y = 0.0;
+                    *reinterpret_cast<double2*>(Q + (size_t)h * ldB + l0 + i) = q;      // the row pitch is even: the pad row exists
+                }
+                T[i * ld + h] = q.x * scale;
+                T[(i + 1) * ld + h] = q.y * scale;
+            }
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void px_store_tile(const PxDev& px, const double* __restrict__ Bn, int ld, int ldB, int l0, int nr, int H, int HP8) {
+    const int npairs = HP8 * 16;
+#pragma unroll 1
+    for (int p = threadIdx.x; p < npairs; p += 256) {
+        const int h = p >> 4, i = 2 * (p & 15);
+        if (h < H && i < nr) {
+            const double2 b = make_double2(Bn[i * ld + h], Bn[(i + 1) * ld + h]);
+            const size_t g = (size_t)h * ldB + l0 + i;
+            if (i + 1 < nr) {
+#pragma unroll
+                for (int rk = 0; rk < W; ++rk) *reinterpret_cast<double2*>(px.B[rk] + g) = b;
+            } else {
+#pragma unroll
+                for (int rk = 0; rk < W; ++rk) px.B[rk][g] = b.x;
+            }
+        }
+    }
+}
+#define PX_DISPATCH_W(W_, CALL)                                                                  \
+    switch (W_) {                                                                                \
+        case 1: { constexpr int PW = 1; CALL; } break;                                           \
+        case 2: { constexpr int PW = 2; CALL; } break;                                           \
+        case 3: { constexpr int PW = 3; CALL; } break;                                           \
+        case 4: { constexpr int PW = 4; CALL; } break;                                           \
+        case 5: { constexpr int PW = 5; CALL; } break;                                           \
+        case 6: { constexpr int PW = 6; CALL; } break;                                           \
+        case 7: { constexpr int PW = 7; CALL; } break;                                           \
+        default: { constexpr int PW = 8; CALL; } break;                                          \
+    }
 // DMMA version of the same epilogue for H <= 64 (HP8 = H rounded up to 8, shared pitch = 4 mod 16 as in the A epilogue):
 //   Bn = (c .* Qtile) * SigmaB [/ sigma2]        32 x HP8 x HP8 product, 4 x HP8/8 mma tiles over 8 warps
 //   G_B += Bn' Bn,  G_D += Dn' Dn                 accumulators in registers across the CTA's tiles
@@ -1601,13 +1686,16 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
     const Scalars* sc = d.sc;
     double* Q = d.packed + packed_q(d);
+    if (PX) px_stamp(px, 0);
     for (int e = threadIdx.x; e < HP8 * ld; e += 256) {
         const int i = e / ld, c = e - i * ld;
         Ss[e] = (i < H && c < H) ? d.SigmaB[i * H + c] : 0.0;
     }
     const bool dense = d.kind == KIND_DENSE;
     const double s2 = sc->sigma2, sh = sc->sigmaHat;
+    if (PX) px_stamp(px, 1);
     if (PX) px_barrier(d, px, blockIdx.x, px.epoch + 1);        // every peer's local Y*AHat (split-K reduction) is complete
+    if (PX) px_stamp(px, 2);
     constexpr int NTW = TPW == 2 ? 2 : (TPW == 8 ? 4 : 8);      // product column tiles per warp: ceil(nt8 / 2)
     constexpr int GT = GRAM ? (TPW == 2 ? 2 : 5) : 1;           // upper-triangular Gram tiles per warp: ceil(nt8*(nt8+1)/2 / 8)
     double gB[GT][2], gD[GT][2];
@@ -1625,34 +1713,8 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         const int l0 = tile * 32, nr = min(32, d.L - l0);
         __syncthreads();
         if (PX) {
-            // all remote loads of four elements are issued before the first sum is stored (the in-place store would otherwise
-            // order every element's round trip behind the previous one)
-            constexpr int CH = 4;
-            for (int e0 = threadIdx.x; e0 < 32 * HP8; e0 += 256 * CH) {
-                double v[CH][PX_MAX_WORLD];
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int e = e0 + 256 * c, h = e >> 5, i = e & 31;
-                    const bool ok = e < 32 * HP8 && i < nr && h < H;
-                    const size_t g = (size_t)h * d.ldB + l0 + i;
-#pragma unroll
-                    for (int rk = 0; rk < PX_MAX_WORLD; ++rk) v[c][rk] = (ok && rk < px.W) ? __ldcg(px.packed[rk] + g) : 0.0;   // L2 only: peer data
-                }
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int e = e0 + 256 * c, h = e >> 5, i = e & 31;
-                    if (e < 32 * HP8) {
-                        double q = v[c][0];
-#pragma unroll
-                        for (int rk = 1; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) q += v[c][rk];
-                        if (i < nr && h < H) {
-                            Q[(size_t)h * d.ldB + l0 + i] = q;
-                            if (!dense) q *= sh;
-                        } else q = 0.0;
-                        T[i * ld + h] = q;
-                    }
-                }
-            }
+            const double scale = dense ? 1.0 : sh;
+            PX_DISPATCH_W(px.W, px_load_tile<PW>(px, Q, T, ld, d.ldB, l0, nr, H, HP8, scale));
         } else {
             for (int e = threadIdx.x; e < 32 * HP8; e += 256) {
                 const int h = e >> 5, i = e & 31;
@@ -1665,6 +1727,7 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
             }
         }
         __syncthreads();
+        if (PX && tile == tile_lo + (int)blockIdx.x) px_stamp(px, 3);       // (the phase stamps describe the CTA's first tile)
         {   // warp -> row tile (warp & 3), column tiles (warp >> 2) + 2u with one independent accumulator each
             const int mt = warp & 3, row = 8 * mt + r;
             double c2[NTW][2];
@@ -1681,14 +1744,16 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
             }
             // the previous BHat entries first, all in flight together and past L1 (a store to an address whose load is still
             // pending stalls the memory pipe: measured 0.055 -> 0.17 ms at 20000 x 64 when the store followed its load directly)
-            double oldv[NTW][2];
+            double oldv[NTW][2], qv[NTW][2];                  // ... and the Y*AHat entries of tr(BHat' * Y*AHat) with them
 #pragma unroll
             for (int u = 0; u < NTW; ++u) {
                 const int nt = (warp >> 2) + 2 * u;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int col = 8 * nt + 2 * j + i;
-                    oldv[u][i] = (nt < nt8 && row < nr && col < H) ? __ldcg(d.B + (size_t)col * d.ldB + l0 + row) : 0.0;
+                    const bool ok = nt < nt8 && row < nr && col < H;
+                    oldv[u][i] = ok ? __ldcg(d.B + (size_t)col * d.ldB + l0 + row) : 0.0;
+                    qv[u][i] = ok ? __ldcg(Q + (size_t)col * d.ldB + l0 + row) : 0.0;
                 }
             }
 #pragma unroll
@@ -1705,11 +1770,8 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
                             const size_t g = (size_t)col * d.ldB + l0 + row;
                             dn = v - oldv[u][i];
                             if (!GRAM) d.D[g] = dn;              // H > 64: gram_dmma forms D'D from it (with GRAM nobody reads D)
-                            if (PX) {
-#pragma unroll
-                                for (int rk = 0; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) px.B[rk][g] = v;
-                            } else d.B[g] = v;
-                            tr = fma(v, Q[g], tr);
+                            if (!PX) d.B[g] = v;                 // PX: all ranks' BHat rows are written from the staged tile below
+                            tr = fma(v, qv[u][i], tr);
                             bn = v;
                         }
                         if (GRAM) { Bn[row * ld + col] = bn; Dn[row * ld + col] = dn; }
@@ -1719,6 +1781,10 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         }
         if (GRAM) {
             __syncthreads();
+            if (PX) {
+                PX_DISPATCH_W(px.W, px_store_tile<PW>(px, Bn, ld, d.ldB, l0, nr, H, HP8));
+                if (tile == tile_lo + (int)blockIdx.x) px_stamp(px, 4);
+            }
             // symmetric Grams: tiles on and above the diagonal only, mirrored when the partial is written
 #pragma unroll
             for (int q = 0; q < GT; ++q) {
@@ -1733,6 +1799,7 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
             }
         }
     }
+    if (PX) px_stamp(px, 5);
     if (GRAM) {
         double* out = d.part + (size_t)blockIdx.x * (2 * H * H + 1);
 #pragma unroll
@@ -1751,6 +1818,7 @@ __global__ void __launch_bounds__(256, (GRAM ? 2 : 1)) B_epilogue_dmma_kernel(De
         }
         tr = block_sum(tr, red);
         if (threadIdx.x == 0) out[2 * H * H] = tr;
+        if (PX) px_stamp(px, 6);
     } else {
         tr = block_sum(tr, red);
         if (threadIdx.x == 0) d.part[blockIdx.x] = tr;         // Grams follow from gram_dmma on B and D
@@ -1794,12 +1862,14 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts, PxDev 
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + x;
     double s = 0.0;
+    if (PX) px_stamp(px, 8);
     if (e < n) {
 #pragma unroll 4
         for (int p = y; p < nparts; p += 8) s += d.part[(size_t)p * n + e];
     }
     sm[y][x] = s;
     __syncthreads();
+    if (PX) px_stamp(px, 9);
     double t = 0.0;
     if (y == 0 && e < n) {
         t = sm[0][x];
@@ -1812,6 +1882,7 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts, PxDev 
             for (int rk = 0; rk < PX_MAX_WORLD; ++rk) if (rk < px.W) px.gpart[rk][(size_t)px.rank * n + e] = t;
         }
         px_barrier(d, px, blockIdx.x, px.epoch + 1);
+        px_stamp(px, 10);
         if (y == 0 && e < n) {
             const double* gp = px.gpart[px.rank];
             t = __ldcg(gp + e);
@@ -1823,6 +1894,7 @@ __global__ void __launch_bounds__(256) B_reduce_kernel(Dev d, int nparts, PxDev 
         else if (e < 2 * H * H) d.DtD[e - H * H] = t;
         else d.sc->trBQ = t;
     }
+    if (PX) px_stamp(px, 11);
 }
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
     const int H = d.H, dv = (flags & F_DIAG_VAR) ? 1 : 0;

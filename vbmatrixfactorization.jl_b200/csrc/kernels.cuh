@@ -63,6 +63,8 @@ struct PxDev {
     double* B[PX_MAX_WORLD];                       // BHat of every rank
     double* gpart[PX_MAX_WORLD];                   // [W][2*H*H + 1]: slot r holds rank r's partial BtB | DtD | tr(B.*Q)
     double* small[PX_MAX_WORLD];                   // [2*H*H + 8]: every rank's local A'A | Sigma sums | group sums (send slot)
+    unsigned long long* wait_ns;                   // profiling (may be NULL): [3][2] = {sum of wait ns, waits} of CTA 0 per barrier site
+    int site;                                      // 0 small exchange, 1 epilogue, 2 Gram reduction
 };
 
 // flags shared by steps
