@@ -7,7 +7,9 @@
 
 One step = one VB iteration (updateA!, updateB!, updateCA!, updateCB!, updateSigma2!, delta; src/vbmf.jl:193-214) over the
 resident column shard of Y.  Y is column-sharded across ranks (fixed total problem => strong scaling); the per-iteration
-exchange is one packed NCCL all-reduce of [Y*AHat | AHat'AHat | ...].
+exchange of [Y*AHat | AHat'AHat | ...] runs through peer-mapped memory over NVLink with the library's own kernels (reduce-scatter
+of Y*AHat, row-sharded BHat epilogue, all-gather of BHat; world <= 8, H <= 64) or, with VBMF_B200_NO_PX=1 / outside those
+limits, as one packed NCCL all-reduce.
 
 Timed region: W untimed warm-up iterations, then exactly K iterations between barrier + synchronize, CUDA events on the
 stream the kernels run on, max over ranks.  Y (32 GB at N=1) is far larger than L2, so no explicit L2 flush is needed.
@@ -550,8 +552,9 @@ def main():
         "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "c5" else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "global_shape": [L, M, H], "columns_per_gpu": Mloc, "parallelism": "column-sharded Y, dp%d, one packed "
-                   "NCCL all-reduce per iteration" % world if world > 1 else "single GPU", "l2": "inputs larger than L2 (Y shard %.1f GB), no flush"
+        "config": {"workload": desc, "global_shape": [L, M, H], "columns_per_gpu": Mloc, "parallelism": ("column-sharded Y, dp%d, " % world + (
+                       "per-iteration exchange over peer-mapped memory with own kernels (reduce-scatter of Y*AHat, row-sharded BHat epilogue, "
+                       "all-gather of BHat over NVLink)" if ctx.peer_exchange() else "one packed NCCL all-reduce per iteration")) if world > 1 else "single GPU", "l2": "inputs larger than L2 (Y shard %.1f GB), no flush"
                    % (L * Mloc * 8 / 1e9), "norm": "spectral", "eps": 0.0},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "final_delta": d, "state_check": state_check,

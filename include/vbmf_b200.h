@@ -211,6 +211,10 @@ int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H, int num_s
 /* enable: 0 off, 1 time the K1 / K2 launches and the exchange, 3 also mark the segments of every iteration (a few more event
  * records on the stream: use it for diagnosis, not for headline numbers) */
 int vbmf_b200_ctx_profile(vbmf_b200_ctx* ctx, int enable);
+/* Host-side row split of the peer-exchange epilogue (pure host logic, needs no device): out[0], out[1] = the 32-row tiles
+ * [lo, hi) of BHat that `rank` of `world` (1..8) reduces, updates and broadcasts, out[2] = CTAs per rank (the same on every
+ * rank).  (none in the reference: src/vbmf.jl:112 is one BLAS call on one host) */
+int vbmf_b200_px_plan(int64_t L, int world, int rank, int64_t* out3);
 int vbmf_b200_ctx_profile_read(vbmf_b200_ctx* ctx, double* k1_ms, int64_t* k1_launches, double* k2_ms, int64_t* k2_launches);
 int vbmf_b200_ctx_profile_read_allreduce(vbmf_b200_ctx* ctx, double* allreduce_ms, int64_t* allreduce_launches);
 /* Where an iteration's time goes on the main stream while profiling is on (CUDA events between the launches): ms[t] / n[t] =

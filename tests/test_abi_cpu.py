@@ -272,3 +272,27 @@ def test_sharded_context_refuses_ambiguous_y(vb):
     api._ctx_for(np.zeros((5, 4)), c)
     assert c.attached == ((5, 4), 8, 4)          # the shard keeps its global geometry
     assert api._ctx_for(None, c) is c
+
+
+def test_peer_exchange_row_split_host_logic(vb):
+    """Row split of the peer-exchange epilogue (host logic, no device needed): the ranks' 32-row tile ranges are contiguous,
+    disjoint and cover every tile of BHat exactly once, no rank holds more than ceil(tiles / world), and the CTA count is the
+    same on every rank and covers the largest share (or the cap of two CTAs per SM)."""
+    import ctypes as C
+    lib = vb._lib.load()
+    out = (C.c_int64 * 3)()
+    rng = np.random.default_rng(1)
+    for L in [1, 31, 32, 33, 96, 517, 1000, 10000, 20000, 50000] + [int(x) for x in rng.integers(1, 200000, 60)]:
+        ntiles = -(-L // 32)
+        for world in range(1, 9):
+            prev_hi, grids = 0, set()
+            for rank in range(world):
+                assert lib.vbmf_b200_px_plan(L, world, rank, C.cast(out, C.c_void_p)) == 0
+                lo, hi, grid = list(out)
+                assert lo == prev_hi and lo <= hi <= ntiles and hi - lo <= -(-ntiles // world), (L, world, rank, lo, hi)
+                prev_hi = hi
+                grids.add(grid)
+                assert grid >= 1 and (grid >= hi - lo or grid == 296)
+            assert prev_hi == ntiles and len(grids) == 1, (L, world, prev_hi, grids)
+    assert lib.vbmf_b200_px_plan(100, 9, 0, C.cast(out, C.c_void_p)) != 0       # more than 8 ranks use the NCCL path
+    assert lib.vbmf_b200_px_plan(100, 2, 2, C.cast(out, C.c_void_p)) != 0

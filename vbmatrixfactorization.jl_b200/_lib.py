@@ -83,6 +83,7 @@ SYMBOLS = {
     "vbmf_b200_ctx_profile_read": (C.c_int, [C.c_void_p, p_f64, p_i64, p_f64, p_i64]),
     "vbmf_b200_ctx_profile_read_allreduce": (C.c_int, [C.c_void_p, p_f64, p_i64]),
     "vbmf_b200_ctx_peer_exchange": (C.c_int, [C.c_void_p]),
+    "vbmf_b200_px_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, p_i64]),
     "vbmf_b200_ctx_profile_read_segments": (C.c_int, [C.c_void_p, p_f64, p_i64, C.c_int]),
     "vbmf_b200_gemm_YtB": (C.c_int, [C.c_void_p, p_f64, c_i64, p_f64]),
     "vbmf_b200_gemm_YA": (C.c_int, [C.c_void_p, p_f64, c_i64, p_f64]),

@@ -245,6 +245,13 @@ extern "C" int vbmf_b200_plan_contractions(int64_t L, int64_t M_local, int64_t H
     out6[0] = S1; out6[1] = kbs; out6[2] = S2; out6[3] = kchunk; out6[4] = g.ctas_per_sm; out6[5] = g.bn;
     return 0;
 }
+extern "C" int vbmf_b200_px_plan(int64_t L, int world, int rank, int64_t* out3) {
+    if (!out3 || L < 1 || L > 0x7fffff00LL || world < 1 || world > PX_MAX_WORLD || rank < 0 || rank >= world) { set_error("px_plan: bad argument"); return -1; }
+    int lo = 0, hi = 0, grid = 1;
+    px_tile_range((int)L, world, rank, &lo, &hi, &grid);
+    out3[0] = lo; out3[1] = hi; out3[2] = grid;
+    return 0;
+}
 extern "C" int vbmf_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

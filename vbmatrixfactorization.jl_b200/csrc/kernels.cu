@@ -1938,11 +1938,9 @@ int k_B_epilogue(cudaStream_t st, const Dev& d, int flags) {
 int k_B_epilogue_px(cudaStream_t st, const Dev& d, int flags, const PxDev& px, int* nparts) {
     const int H = d.H, HP8 = (H + 7) & ~7;
     if (H > 64 || (flags & F_DIAG_VAR)) { set_error("peer-exchange epilogue: H <= 64 and homoscedastic noise only"); return -1; }
-    const int ntiles = cdiv(d.L, 32);
-    const int lo = (int)((long long)ntiles * px.rank / px.W), hi = (int)((long long)ntiles * (px.rank + 1) / px.W);
+    int lo = 0, hi = 0, grid2 = 1;
+    px_tile_range(d.L, px.W, px.rank, &lo, &hi, &grid2);
     const size_t smem = (size_t)((HP8 + 96) * pitch4(HP8)) * sizeof(double);
-    // the same grid on every rank (CTA b meets CTA b of the peers at the barrier); a CTA without a tile writes a zero partial
-    const int grid2 = std::max(1, std::min(cdiv(ntiles, px.W), 296));
     if (HP8 <= 32) B_epilogue_dmma_kernel<2, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
     else B_epilogue_dmma_kernel<8, true, true><<<grid2, 256, smem, st>>>(d, 0, px, lo, hi);
     VB_LAUNCH_OK();

@@ -104,6 +104,15 @@ int k_sum_slabs(cudaStream_t st, const double* slabs, int S, size_t n, double* o
 int k_reduce_q(cudaStream_t st, const Dev& d, const double* Qpart, int S);   // fixed-order split-K reduction -> packed.Q
 int k_sigmaB(cudaStream_t st, const Dev& d, int flags);          // SigmaB (dense / sparse), also SigmaA <- packed.SA (sparse)
 int k_B_epilogue(cudaStream_t st, const Dev& d, int flags);      // BHat, Bold, D, partial tr(B.*Q)
+// Row split of the exchange epilogue: 32-row tiles [lo, hi) of rank `rank`, and the CTA count, which is the SAME on every rank
+// (CTA b meets CTA b of the peers at the barrier; a CTA without a tile contributes a zero partial).
+inline void px_tile_range(int L, int W, int rank, int* lo, int* hi, int* grid) {
+    const int ntiles = (L + 31) / 32;
+    *lo = (int)((long long)ntiles * rank / W);
+    *hi = (int)((long long)ntiles * (rank + 1) / W);
+    const int per = (ntiles + W - 1) / W;
+    *grid = per < 1 ? 1 : (per > 296 ? 296 : per);
+}
 // peer exchange (world > 1), one barrier (epoch + 1) each:
 // global A'A / Sigma sums / group sums on every rank (needs only the A side of the iteration: runs beside K2) ...
 int k_px_small(cudaStream_t st, const Dev& d, const PxDev& px);
