@@ -492,6 +492,8 @@ def main():
                 "iteration_frac_of_peak": 4.0 * L * M * H / (ms / args.steps * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
                 "contraction_share_of_step": (k1 + k2) / (ms / args.steps),
                 # the per-iteration packed all-reduce (N > 1), CUDA events on the launching stream of rank 0
+                # N > 1: CUDA-event time of the exchange per iteration -- the NCCL all-reduce alone, or (peer_exchange) the whole
+                # stretch from K2's split-K reduction to the Gram reduction: exchange epilogue on this rank's rows + Gram exchange
                 "allreduce_ms": (prof["allreduce_ms"] / prof["allreduce_launches"]) if prof.get("allreduce_launches") else None,
                 # CUDA events between the launches of one iteration on the main stream (mean over the timed iterations, this rank)
                 "segments_ms": {k: round(v, 5) for k, v in prof.get("segments_ms", {}).items()},

@@ -1561,6 +1561,10 @@ extern "C" int vbmf_b200_solver_run(vbmf_b200_solver* s, int64_t niter, double e
     if (wait_post(s) || pull_scalars(s)) return -1;
     if (iters) *iters = s->h_sc.iter;
     if (dout) *dout = s->h_sc.d;
+    if (s->h_sc.chol_fail & 4) {
+        set_error("peer exchange: a rank did not reach a device-side barrier within ~30 s (did every rank enter the same call?); the state is invalid");
+        return -1;
+    }
     if (s->h_sc.chol_fail) { set_error("a posterior precision matrix was not positive definite (NaN written, loop ended)"); return -2; }
     return 0;
 }

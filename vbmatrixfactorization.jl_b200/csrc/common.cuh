@@ -36,7 +36,7 @@ struct Scalars {
     double meanSigmaVec;               // mean(sigmaVecHat), diag_var
     double trBQ;                       // sum(BHat .* (Y*AHat))
     double lb;                         // last lower bound
-    int    chol_fail;                  // sticky: a pivot was <= 0 / NaN in an SPD inverse
+    int    chol_fail;                  // sticky: bit 0: a pivot was <= 0 / NaN in an SPD inverse; bit 2: a peer-exchange barrier timed out
     int    pad_;
 };
 
