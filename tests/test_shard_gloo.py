@@ -147,3 +147,102 @@ def test_shard_columns_partition():
             assert parts[0][0] == 0 and sum(n for _, n in parts) == M
             for (o1, n1), (o2, _) in zip(parts, parts[1:]):
                 assert o1 + n1 == o2
+
+
+# ------------------------------------------------------------------------------------------------ peer-exchange data flow
+def _px_rows(L, world, rank):
+    """This rank's rows of BHat in the peer exchange: the 32-row tiles the library's own host planner assigns it."""
+    import ctypes as C
+    import vbmf_b200_loader
+    lib = vbmf_b200_loader.load()._lib.load()
+    out = (C.c_int64 * 3)()
+    assert lib.vbmf_b200_px_plan(L, world, rank, C.cast(out, C.c_void_p)) == 0
+    return min(out[0] * 32, L), min(out[1] * 32, L)
+
+
+def _gather(x, world):
+    parts = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(parts, x)
+    return [t.numpy() for t in parts]
+
+
+def _px_dense_iteration(Y, p, off, n, M, world, rank):
+    """One dense iteration with the exchange the device runs for world > 1 (csrc/kernels.cu, peer exchange): local A side; the
+    small sums gathered from every rank and added in rank order; every rank reduces ITS rows of Y*AHat over the ranks, runs
+    the BHat epilogue on them and broadcasts the rows; the Grams of BHat / BHat - Bold travel as rank partials."""
+    L, H = p.L, p.H
+    Yg = Y[:, off:off + n]
+    norm_old = float(np.sqrt(np.linalg.eigvalsh(p.BtB)[-1]))          # norm(old), carried between iterations on the device
+    # updateA! on the shard (src/vbmf.jl:95-102); SigmaA is replicated
+    p.SigmaA = p.sigma2 * vo._inv(p.BtB + L * p.SigmaB + p.sigma2 * p.invCA)
+    A = ((Yg.T @ p.BHat) @ p.SigmaA) / p.sigma2
+    p.AHat = A
+    Qloc = Yg @ A
+    # small exchange: every rank's A'A, summed in rank order
+    AtA = sum(_gather(torch.from_numpy(np.ascontiguousarray(A.T @ A)), world))
+    p.SigmaB = p.sigma2 * vo._inv(AtA + M * p.SigmaA + p.sigma2 * p.invCB)
+    # reduce-scatter of Y*AHat into the row-sharded epilogue
+    Qall = _gather(torch.from_numpy(np.ascontiguousarray(Qloc)), world)
+    lo, hi = _px_rows(L, world, rank)
+    Qrows = sum(q[lo:hi] for q in Qall)
+    Brows = (Qrows @ p.SigmaB) / p.sigma2
+    Drows = Brows - p.BHat[lo:hi]
+    part = np.concatenate([(Brows.T @ Brows).reshape(-1), (Drows.T @ Drows).reshape(-1), [float(np.sum(Brows * Qrows))]])
+    # all-gather of the BHat rows (every rank writes its rows into every peer's BHat) and of the rank partials
+    Bnew = np.empty_like(p.BHat)
+    pad = torch.zeros((-(-L // world) + 32, H), dtype=torch.float64)
+    pad[:hi - lo] = torch.from_numpy(Brows)
+    for r, rows in enumerate(_gather(pad, world)):
+        rlo, rhi = _px_rows(L, world, r)
+        Bnew[rlo:rhi] = rows[:rhi - rlo]
+    parts = _gather(torch.from_numpy(part), world)
+    tot = sum(parts)
+    p.BHat = Bnew
+    p.BtB, DtD, trBQ = tot[:H * H].reshape(H, H), tot[H * H:2 * H * H].reshape(H, H), tot[-1]
+    # replicated tail from the exchanged Grams: updateCA!, updateCB!, updateSigma2!, delta (src/vbmf.jl:129-157, src/util.jl:27-29)
+    for h in range(H):
+        p.CA[h, h] = AtA[h, h] / M + p.SigmaA[h, h]
+        p.CB[h, h] = p.BtB[h, h] / L + p.SigmaB[h, h]
+    p.invCA, p.invCB = vo._inv(p.CA), vo._inv(p.CB)
+    p.sigma2 = (p.trYTY - 2.0 * trBQ + float(np.trace((AtA + M * p.SigmaA) @ (p.BtB + L * p.SigmaB)))) / (L * M)
+    return float(np.sqrt(np.linalg.eigvalsh(DtD)[-1])) / norm_old      # delta = norm(old - new) / norm(old), spectral (Q1)
+
+
+def _px_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, M, H = 150, 211, 6            # 5 row tiles of 32 (the last one ragged): uneven shares between the ranks
+    Y = synth(L, M, 3, seed=4)
+    off, n = shard_columns(M, world, rank)
+    pg = vo.vbmf_init(Y, H, ca=1.0, cb=1.0, sigma2=1.0, rng=np.random.default_rng(8))
+    p = copy.deepcopy(pg)
+    p.AHat = pg.AHat[off:off + n].copy()
+    p.BtB = p.BHat.T @ p.BHat
+    p.trYTY = float(np.sum(Y * Y))
+    niter = 6
+    d = None
+    for _ in range(niter):
+        d = _px_dense_iteration(Y, p, off, n, M, world, rank)
+    _, it_o, d_o = vo.vbmf_run(Y, pg, niter, eps=0.0, est_covs=True, est_var=True, yhat=False)
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    errs = [rel(p.BHat, pg.BHat), rel(p.SigmaB, pg.SigmaB), rel(p.SigmaA, pg.SigmaA), rel(p.AHat, pg.AHat[off:off + n]),
+            rel(p.CA, pg.CA), rel(p.CB, pg.CB), abs(p.sigma2 - pg.sigma2) / pg.sigma2, abs(d - d_o) / d_o * 1e-2]
+    t = torch.tensor([max(errs)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        with open(out, "w") as f:
+            f.write(repr(float(t.item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_exchange_data_flow_matches_unsharded(world, tmp_path):
+    """The decomposition the device uses instead of an all-reduce (small sums in rank order, reduce-scatter of Y*AHat by the
+    planner's row tiles, row-sharded BHat epilogue, all-gather of the rows, Grams as rank partials) reproduces the unsharded
+    oracle, with uneven row shares (world 3: 2 / 1 / 2 tiles, the last tile ragged)."""
+    out = str(tmp_path / "err.txt")
+    mp.spawn(_px_worker, args=(world, 29950 + world, out), nprocs=world, join=True)
+    assert float(open(out).read()) < 1e-11
