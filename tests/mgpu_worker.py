@@ -96,7 +96,9 @@ def main():
     # many row tiles per rank, ragged last tile, H = 64 / 32: dense and sparse (diagonal) through the exchange kernels
     for kind, (L2, M2, H2), kw in (("dense", (1000, 3001, 64), dict(est_covs=True, est_var=True)),
                                    ("sparse", (517, 2000, 32), dict(full_cov=False, est_cb=True)),
-                                   ("dual", (300, 1500, 16), dict(full_cov=True, est_priors=True, est_cb=True))):
+                                   ("dual", (300, 1500, 16), dict(full_cov=True, est_priors=True, est_cb=True)),
+                                   # L*H large enough that the peer-visible buffer has to grow (collective re-mapping)
+                                   ("dense", (40000, 136, 64), dict(est_covs=True, est_var=True))):
         Y2 = synth(L2, M2, 6, seed=17)
         off2, n2 = vb.shard_columns(M2, world, rank)
         ctx.attach(np.asfortranarray(Y2[:, off2:off2 + n2]), M_global=M2, col_offset=off2)

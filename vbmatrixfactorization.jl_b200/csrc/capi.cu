@@ -147,12 +147,16 @@ struct PxRec {
     char pad[128 - 32 - sizeof(cudaIpcMemHandle_t)];
 };
 static_assert(sizeof(PxRec) == 128, "PxRec is exchanged as 128 bytes");
-static void px_release(vbmf_b200_ctx* c) {
+static void px_unmap_peers(vbmf_b200_ctx* c) {
     auto& x = c->px;
     for (int r = 0; r < PX_MAX_WORLD; ++r) {
         if (x.ipc[r] && x.peer[r]) cudaIpcCloseMemHandle(x.peer[r]);
         x.peer[r] = nullptr; x.ipc[r] = false;
     }
+}
+static void px_release(vbmf_b200_ctx* c) {
+    auto& x = c->px;
+    px_unmap_peers(c);
     if (x.local) cudaFree(x.local);
     if (x.xchg) cudaFree(x.xchg);
     x.local = nullptr; x.xchg = nullptr; x.cap = 0; x.ok = false;
@@ -163,6 +167,7 @@ static int px_setup(vbmf_b200_ctx* c, size_t data_bytes) {
     if (c->world > PX_MAX_WORLD || x.failed || getenv("VBMF_B200_NO_PX") != nullptr) return 0;
     const size_t need = PX_FLAG_BYTES + data_bytes;
     if (x.ok && x.cap >= need) return 0;
+    if (x.claimed) return 0;              // a live solver points into the buffer: it cannot be re-allocated now (the new solver uses NCCL)
     const int W = c->world;
     const size_t cap = (std::max(need, (size_t)32 << 20) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
     if (W == 1) {
@@ -177,6 +182,14 @@ static int px_setup(vbmf_b200_ctx* c, size_t data_bytes) {
     }
     if (g_nccl.AllGather == nullptr) return 0;
     VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (x.local != nullptr && x.xchg != nullptr) {
+        // growing: every rank unmaps its peers' buffers BEFORE any rank frees its own (an exported allocation must outlive
+        // its imported mappings); a one-element all-reduce is the host-visible barrier between the two steps
+        px_unmap_peers(c);
+        double* dflag = (double*)(x.xchg + (size_t)(W + 1) * 128);
+        VB_NCCL_OK(g_nccl.AllReduce(dflag, dflag, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->st));
+        VB_CUDA_OK(cudaStreamSynchronize(c->st));
+    }
     px_release(c);
     PxRec mine;
     memset(&mine, 0, sizeof(mine));
