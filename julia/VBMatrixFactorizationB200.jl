@@ -19,7 +19,7 @@ import VBMatrixFactorization: vbmf_parameters, vbmf_sparse_parameters, vbmf_dual
 import VBMatrixFactorization: vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, vbmf_trial!, vbmf_trial,
                               lowerBound, lowerBoundTrimmed
 
-export b200_context, b200_close, b200_default_context!, vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, vbmf_trial!, vbmf_trial,
+export b200_context, b200_close, b200_peer_exchange, b200_default_context!, vbmf!, vbmf, vbmf_sparse!, vbmf_sparse, vbmf_dual!, vbmf_dual, vbmf_trial!, vbmf_trial,
        lowerBound, lowerBoundTrimmed, vbls_batched!, preprocess
 
 const LIB = get(ENV, "VBMF_B200_LIB", "libvbmf_b200.so")
@@ -102,6 +102,16 @@ function b200_context(devices::AbstractVector)
     h = Ref{Ptr{Void}}(C_NULL)
     check(ccall((:vbmf_b200_mctx_create, LIB), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Void}}), length(devs), devs, h))
     return B200Context(h[], true, length(devs))
+end
+# Several GPUs: true when the per-iteration exchange of updateB! runs through peer-mapped memory over NVLink (the library's own
+# kernels; world 2..8 on one node, H <= 64, decided when the first solver is created) instead of the NCCL all-reduce.
+function b200_peer_exchange(ctx::B200Context)
+    if !ctx.multi
+        return ccall((:vbmf_b200_ctx_peer_exchange, LIB), Cint, (Ptr{Void},), ctx.handle) != 0
+    end
+    h = Ref{Ptr{Void}}(C_NULL)
+    check(ccall((:vbmf_b200_mctx_ctx, LIB), Cint, (Ptr{Void}, Cint, Ptr{Ptr{Void}}), ctx.handle, 0, h))
+    return ccall((:vbmf_b200_ctx_peer_exchange, LIB), Cint, (Ptr{Void},), h[]) != 0
 end
 b200_close(ctx::B200Context) = ctx.multi ? ccall((:vbmf_b200_mctx_destroy, LIB), Cint, (Ptr{Void},), ctx.handle) :
                                            ccall((:vbmf_b200_ctx_destroy, LIB), Cint, (Ptr{Void},), ctx.handle)
