@@ -698,6 +698,7 @@ struct vbmf_b200_solver {
     bool btb_valid = false, ata_valid = false, q_valid = false, extras_valid = false, mean_valid = false;
     bool ata_local = false;   // packed.AtA holds this shard's AHat'AHat (not yet all-reduced)
     int ata_parts = 0;        // > 0: ... as soon as that many Gram partials in d.part are summed (deferred to the side stream, beside K2)
+    int diag_parts = 0;       // > 0: the fused diagonal pass left that many partials (A'A | column sums | group sums) in d.part, same deferral
     bool ca_done = false;     // the fused diagonal A pass already did updateCA! of this iteration
     bool loop_ahead = false;      // set by solver_run while it enqueues whole iterations back to back
     bool sigmaA_ahead = false;    // dense loop: the NEXT iteration's SigmaA was already inverted on the side stream (behind post)
@@ -1223,7 +1224,9 @@ static int enq_updateA(vbmf_b200_solver* s, int flags, bool fused) {
             // whole-loop diagonal path: slab sum, A, diag, mask, updateCA! and A'A in one pass over vec(A')
             if (enq_k1(s, dv, false) || wait_post(s)) return -1;
             const bool slabs = !s->c->simt && s->S1 > 1;
-            if (k_sparse_A_diag_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, flags)) return -1;
+            // (the reduction of the partials is only needed by SigmaB and the tail: side stream, beside K2 -- enq_updateB)
+            const bool defer = s->c->world == 1 || (s->px && !dv);
+            if (k_sparse_A_diag_fused(st, d, slabs ? s->Ppart : d.P, slabs ? s->S1 : 1, (size_t)d.Mloc * d.H, flags, defer ? &s->diag_parts : nullptr)) return -1;
             s->ata_valid = false; s->q_valid = false;
             s->ata_local = true; s->ca_done = true;
             return 0;
@@ -1302,12 +1305,15 @@ static int enq_updateB(vbmf_b200_solver* s, int flags, bool fused) {
         // One GPU: nothing to exchange.  Either way SigmaB needs the A side of the iteration only, so the Gram partial sum,
         // the small exchange and the inverse run on the side stream beside K2 (their few CTAs share the SMs with K2's).
         if (d.kind != KIND_DENSE && (flags & F_DIAG_VAR) && !s->mean_valid) { if (k_mean_sigma(st, d)) return -1; s->mean_valid = true; }
-        if (!s->ata_local && enq_gram_A(s)) return -1;
-        s->ata_local = false;
         VB_CUDA_OK(cudaEventRecord(s->ev_a, st));
         VB_CUDA_OK(cudaStreamWaitEvent(s->side, s->ev_a, 0));
+        // AHat'AHat (full covariance path: a Gram pass over AHat; otherwise the deferred sums of the A-side partials)
+        if (!s->ata_local && k_gram(s->side, d, d.A, true, d.Mloc, nullptr, d.packed + packed_ata(d))) return -1;
+        s->ata_local = false;
         if (s->ata_parts > 0 && k_sum_gram_partials(s->side, d, s->ata_parts)) return -1;
         s->ata_parts = 0;
+        if (s->diag_parts > 0 && k_sparse_diag_reduce(s->side, d, s->diag_parts)) return -1;
+        s->diag_parts = 0;
         if (px && k_px_small(s->side, d, px_view(s, 1, 0))) return -1;
         if (k_sigmaB(s->side, d, flags)) return -1;
         VB_CUDA_OK(cudaEventRecord(s->ev_sb, s->side));

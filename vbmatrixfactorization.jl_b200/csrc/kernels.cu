@@ -1062,7 +1062,15 @@ static size_t sparse_diag_fused_smem(int H) {
     const int HP8 = (H + 7) & ~7, TR = 32;
     return (size_t)(TR * pitch4(HP8) + HP8 + TR * HP8) * sizeof(double);
 }
-int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags) {
+int k_sparse_diag_reduce(cudaStream_t st, const Dev& d, int nparts) {
+    const int H = d.H, HP8 = (H + 7) & ~7;
+    sparse_diag_reduce_kernel<<<cdiv(H * H + HP8 + 8, 32), 256, 0, st>>>(d, nparts);
+    VB_LAUNCH_OK();
+    return 0;
+}
+// defer_parts != NULL: the fixed-order reduction of the per-CTA partials is left to the caller (k_sparse_diag_reduce on
+// another stream: only SigmaB and the tail need its results), *defer_parts = number of partials in d.part
+int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags, int* defer_parts) {
     const int H = d.H, HP8 = (H + 7) & ~7;
     const int dv = (flags & F_DIAG_VAR) ? 1 : 0;
     const size_t smem = sparse_diag_fused_smem(H);
@@ -1072,9 +1080,8 @@ int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, in
     else if (HP8 <= 64) sparse_A_diag_fused_kernel<5><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
     else sparse_A_diag_fused_kernel<17><<<grid, 256, smem, st>>>(d, slabs, S, slab_stride, dv);
     VB_LAUNCH_OK();
-    sparse_diag_reduce_kernel<<<cdiv(H * H + HP8 + 8, 32), 256, 0, st>>>(d, grid);
-    VB_LAUNCH_OK();
-    return 0;
+    if (defer_parts != nullptr) { *defer_parts = grid; return 0; }
+    return k_sparse_diag_reduce(st, d, grid);
 }
 
 // ------------------------------------------------------------------------------------------- K4: sparse / dual A update, full covariance

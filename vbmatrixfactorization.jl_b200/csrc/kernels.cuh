@@ -97,7 +97,8 @@ int k_sparse_A_full(cudaStream_t st, const Dev& d, int flags);   // batched H x 
 int k_sparse_A_full_ex(cudaStream_t st, const Dev& d, int flags, const double* slabs, int S, size_t slab_stride, int fuse_ca);
 bool k_sparse_A_full_can_fuse(const Dev& d);                     // tensor-core path in use (H <= 32): slab sum / updateCA! can be fused
 // whole-loop diagonal path in one pass: slab sum, A, diag, mask, beta/CA (+ group sums), A'A, diag SigmaA -> packed
-int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags);
+int k_sparse_A_diag_fused(cudaStream_t st, const Dev& d, const double* slabs, int S, size_t slab_stride, int flags, int* defer_parts = nullptr);
+int k_sparse_diag_reduce(cudaStream_t st, const Dev& d, int nparts);   // the deferred reduction of the fused diagonal pass
 int k_mask(cudaStream_t st, const Dev& d);
 int k_update_CA(cudaStream_t st, const Dev& d, int sums_only = 0);   // sparse / dual element-wise ARD update (+ dual sums)
 int k_sum_slabs(cudaStream_t st, const double* slabs, int S, size_t n, double* out, const Scalars* sc);   // out = sum_s slabs[s]
