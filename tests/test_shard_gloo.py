@@ -28,8 +28,11 @@ def shard_columns(M, world, rank):
     return vbmf_b200_loader.load().shard_columns(M, world, rank)
 
 
-def _sharded_sparse_iteration(Y, p, off, n, M, full_cov, est_cb, dual, est_priors):
-    """One iteration on the shard [off, off+n): local A side, packed all-reduce, replicated B side."""
+def _sharded_sparse_iteration(Y, p, off, n, M, full_cov, est_cb, dual, est_priors, exchange="allreduce", world=1, rank=0):
+    """One iteration on the shard [off, off+n): local A side, the exchange, replicated B side.  exchange = "allreduce": one
+    packed all-reduce (the NCCL path); "px": the peer-exchange data flow -- small sums gathered and added in rank order,
+    Y*AHat reduce-scattered by the planner's row tiles into a row-sharded BHat update, BHat rows all-gathered, tr(BHat.*Q) and
+    BHat'BHat as rank partials."""
     H, L = p.H, p.L
     Yg = Y[:, off:off + n]
     # ---- updateA! on the shard (src/vbmf_sparse.jl:176-247): Q2 uses the global index j = (off+m)*H + h
@@ -61,19 +64,39 @@ def _sharded_sparse_iteration(Y, p, off, n, M, full_cov, est_cb, dual, est_prior
     else:
         p.beta = p.beta0 + 0.5 * (p.ATVecHat ** 2 + p.diagSigmaATVec)
         p.CA = p.alpha / p.beta
-    # ---- packed all-reduce: [Q | A'A | SA | extras]
-    packed = np.concatenate([(Yg @ A).reshape(-1), (A.T @ A).reshape(-1), SA.reshape(-1), extras])
-    t = torch.from_numpy(packed)
-    dist.all_reduce(t)
-    Q = packed[:L * H].reshape(L, H); AtA = packed[L * H:L * H + H * H].reshape(H, H)
-    p.SigmaA = packed[L * H + H * H:L * H + 2 * H * H].reshape(H, H).copy(); ex = packed[-8:]
-    # ---- replicated: updateB!, updateCB!, updateSigma!, priors
-    GA = AtA + p.SigmaA
-    p.SigmaB = np.linalg.inv(np.diag(p.CB) + p.sigmaHat * GA)
-    p.BHat = (p.sigmaHat * Q) @ p.SigmaB
+    if exchange == "px":
+        small = sum(_gather(torch.from_numpy(np.concatenate([(A.T @ A).reshape(-1), SA.reshape(-1), extras])), world))
+        AtA = small[:H * H].reshape(H, H); p.SigmaA = small[H * H:2 * H * H].reshape(H, H).copy(); ex = small[-8:]
+        GA = AtA + p.SigmaA
+        p.SigmaB = np.linalg.inv(np.diag(p.CB) + p.sigmaHat * GA)
+        Qall = _gather(torch.from_numpy(np.ascontiguousarray(Yg @ A)), world)
+        lo, hi = _px_rows(L, world, rank)
+        Qrows = sum(q[lo:hi] for q in Qall)
+        Brows = (p.sigmaHat * Qrows) @ p.SigmaB
+        pad = torch.zeros((-(-L // world) + 32, H), dtype=torch.float64)
+        pad[:hi - lo] = torch.from_numpy(Brows)
+        Bnew = np.empty((L, H))
+        for r, rows in enumerate(_gather(pad, world)):
+            rlo, rhi = _px_rows(L, world, r)
+            Bnew[rlo:rhi] = rows[:rhi - rlo]
+        tot = sum(_gather(torch.from_numpy(np.concatenate([(Brows.T @ Brows).reshape(-1), [float(np.sum(Brows * Qrows))]])), world))
+        p.BHat, BtB, trBQ = Bnew, tot[:H * H].reshape(H, H), float(tot[-1])
+    else:
+        # ---- packed all-reduce: [Q | A'A | SA | extras]
+        packed = np.concatenate([(Yg @ A).reshape(-1), (A.T @ A).reshape(-1), SA.reshape(-1), extras])
+        t = torch.from_numpy(packed)
+        dist.all_reduce(t)
+        Q = packed[:L * H].reshape(L, H); AtA = packed[L * H:L * H + H * H].reshape(H, H)
+        p.SigmaA = packed[L * H + H * H:L * H + 2 * H * H].reshape(H, H).copy(); ex = packed[-8:]
+        # ---- replicated: updateB!
+        GA = AtA + p.SigmaA
+        p.SigmaB = np.linalg.inv(np.diag(p.CB) + p.sigmaHat * GA)
+        p.BHat = (p.sigmaHat * Q) @ p.SigmaB
+        BtB, trBQ = p.BHat.T @ p.BHat, float(np.sum(p.BHat * Q))
+    # ---- replicated: updateCB!, updateSigma!, priors
     if est_cb:
         vo.sparse_updateCB(p)
-    p.zeta = p.zeta0 + 0.5 * p.trYTY - float(np.sum(p.BHat * Q)) + 0.5 * float(np.sum(GA * (p.BHat.T @ p.BHat + L * p.SigmaB)))
+    p.zeta = p.zeta0 + 0.5 * p.trYTY - trBQ + 0.5 * float(np.sum(GA * (BtB + L * p.SigmaB)))
     p.sigmaHat = p.eta / p.zeta
     if dual and est_priors:
         from scipy.special import digamma
@@ -94,11 +117,11 @@ def _sharded_sparse_iteration(Y, p, off, n, M, full_cov, est_cb, dual, est_prior
         p.beta01 = N1 * p.alpha01 / ex[1]
 
 
-def _worker(rank, world, port, case, out):
+def _worker(rank, world, port, case, out, exchange="allreduce"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    L, M, H = 24, 101, 4
+    L, M, H = (24, 101, 4) if exchange == "allreduce" else (150, 101, 4)     # px: five 32-row tiles, uneven shares
     Y = synth(L, M, 2, seed=3)
     off, n = shard_columns(M, world, rank)
     kind, full_cov = case
@@ -112,7 +135,7 @@ def _worker(rank, world, port, case, out):
     p.AHat = pg.AHat[off:off + n].copy()
     niter = 5
     for _ in range(niter):
-        _sharded_sparse_iteration(Y, p, off, n, M, full_cov, True, dual, True)
+        _sharded_sparse_iteration(Y, p, off, n, M, full_cov, True, dual, True, exchange, world, rank)
     if dual:
         vo.vbmf_dual_run(Y, pg, niter, eps=0.0, full_cov=full_cov, est_priors=True, est_cb=True)
     else:
@@ -137,6 +160,17 @@ def test_world2_sharding_matches_unsharded(case, tmp_path):
     out = str(tmp_path / "err.txt")
     port = 29600 + abs(hash(case)) % 300
     mp.spawn(_worker, args=(2, port, case, out), nprocs=2, join=True)
+    assert float(open(out).read()) < 1e-11
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", [("sparse", False), ("dual", True)])
+def test_peer_exchange_data_flow_sparse_kinds(case, world, tmp_path):
+    """The same decomposition for the sparse / dual kinds: the small part also carries the sum of the Sigma blocks and the
+    group sums of the ARD update (hyper-prior roots of vbmf_dual included)."""
+    out = str(tmp_path / "err.txt")
+    port = 29300 + abs(hash(case)) % 300 + world
+    mp.spawn(_worker, args=(world, port, case, out, "px"), nprocs=world, join=True)
     assert float(open(out).read()) < 1e-11
 
 
