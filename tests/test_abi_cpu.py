@@ -296,3 +296,26 @@ def test_peer_exchange_row_split_host_logic(vb):
             assert prev_hi == ntiles and len(grids) == 1, (L, world, prev_hi, grids)
     assert lib.vbmf_b200_px_plan(100, 9, 0, C.cast(out, C.c_void_p)) != 0       # more than 8 ranks use the NCCL path
     assert lib.vbmf_b200_px_plan(100, 2, 2, C.cast(out, C.c_void_p)) != 0
+
+
+def test_log_helpers_survive_a_second_logged_run(vb, tmp_path):
+    """create_log / update_log_ / save_log / load_log are host logic (src/data_manip.jl:6-118).  A logged run leaves the
+    trajectory on the params object (`params.log`); creating a log from the SAME object again -- resuming with logging -- must
+    skip it (round 1 crashed there with a TypeError), and only numeric fields are logged."""
+    rng = np.random.default_rng(0)
+    Y = rng.standard_normal((6, 9))
+    for p in (vb.vbmf_init(Y, 3, rng=rng), vb.vbmf_sparse_init(Y, 3, rng=rng), vb.vbmf_dual_init(Y, 3, 1, rng=rng)):
+        log = vb.create_log(p)
+        assert "log" not in log and "YHat" not in log and "BHat" in log
+        p.BHat = p.BHat + 1.0
+        vb.update_log_(log, p)
+        p.log = log                       # what a logged run leaves behind
+        p.failed = False
+        p.desc = "text is not logged"
+        log2 = vb.create_log(p)           # second logged run on the same params
+        assert set(log2) == set(log)
+        vb.update_log_(log2, p)
+        d = vb.save_log(log2, Y, {"ca": 1.0}, str(tmp_path), desc="twice_%s" % p.kind)
+        back, Yback = vb.load_log(d)
+        assert back["BHat"].shape == p.BHat.shape + (2,) and np.array_equal(back["BHat"][..., 1], p.BHat)
+        assert np.array_equal(Yback, Y)
